@@ -1,0 +1,140 @@
+/* terran_b200 — C ABI of the B200-native Terran hot path.
+ *
+ * The reference (terran-project/terran) is pure Python/PyTorch and has no FFI;
+ * each entry point below names the reference code it replaces.  All pointers
+ * marked "device" are CUDA device pointers on the current device (the Python
+ * side passes torch tensor .data_ptr()); `stream` is a cudaStream_t (may be 0).
+ * Every function returns 0 on success and a non-zero code on failure, in which
+ * case tr_last_error() describes the failure (the Python binding raises).
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef TERRAN_B200_H
+#define TERRAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tr_net tr_net;
+
+/* ---- library ----------------------------------------------------------- */
+int tr_version(void);
+const char* tr_last_error(void);
+/* cudaSetDevice + capability check (sm_100 required). Replaces the implicit
+ * `default_device` selection of terran/defaults.py:3-5. */
+int tr_init(int device);
+
+/* ---- layer program ("net") ----------------------------------------------
+ * A net is a list of fused layer ops over NHWC fp16 activation buffers plus a
+ * packed weight blob (BatchNorm folded, fp16 [cout][kh][kw][cin] filters).
+ * terran_b200/weights.py builds it from the reference state_dict layout
+ * (SURVEY.md Appendix C); shapes are inferred per call from (N,H,W).
+ * Replaces nn.Module construction + load_state_dict
+ * (retinaface/wrapper.py:16-22, arcface/wrapper.py:13-19, openpose/wrapper.py:26-34). */
+enum { TR_OP_STEM = 0, TR_OP_CONV = 1, TR_OP_DWCONV = 2, TR_OP_MAXPOOL = 3, TR_OP_COPY = 4,
+       TR_OP_VIEW = 5 };
+enum { TR_ACT_NONE = 0, TR_ACT_RELU = 1, TR_ACT_PRELU = 2 };
+
+typedef struct tr_buffer_desc {
+  int32_t channels;   /* total channels (multiple of 8) */
+  int32_t is_f32;     /* 1: fp32 NHWC output buffer, 0: fp16 */
+} tr_buffer_desc;
+
+typedef struct tr_op_desc {
+  int32_t type;
+  int32_t in, in_coff, in_c;        /* input buffer (-1 = the u8 image), channel offset, channels */
+  int32_t out, out_coff, out_c;     /* output buffer, channel offset, channels written */
+  int32_t out2, out2_coff;          /* optional second output (out*scale2+shift2) or -1 */
+  int32_t res, res_coff, res_up2;   /* optional residual (-1 = none); res_up2: read at (h/2,w/2) */
+  int32_t k, stride, pad, act;
+  int32_t cout_pad;                 /* filter rows in the blob (multiple of 16) */
+  int32_t cin_real, cout_real;      /* un-padded channel counts (algorithmic flop accounting) */
+  int32_t force_direct;             /* 1: never use the tcgen05 kernel for this op */
+  int64_t w_off, scale_off, shift_off, slope_off, scale2_off, shift2_off; /* blob byte offsets, -1 = none */
+  float in_scale, in_shift;         /* stem only: x' = x*in_scale + in_shift on in-bounds taps */
+} tr_op_desc;
+
+int tr_net_create(const tr_buffer_desc* buffers, int n_buffers, const tr_op_desc* ops, int n_ops,
+                  const void* weights_host, size_t weight_bytes, tr_net** out);
+void tr_net_destroy(tr_net* net);
+/* 0 = auto (tcgen05 where eligible), 1 = force the CUDA-core direct kernels (cross-check). */
+int tr_net_set_mode(tr_net* net, int force_direct);
+/* Run the program on a u8 image batch with arbitrary element strides (so both
+ * NHWC RGB frames and the reference's NCHW BGR crops are accepted as they are). */
+int tr_net_run(tr_net* net, const uint8_t* image_dev, int N, int H, int W, int64_t stride_n,
+               int64_t stride_h, int64_t stride_w, int64_t stride_c, void* stream);
+/* Buffer of the most recent run: device pointer and NHWC dims. */
+int tr_net_buffer(tr_net* net, int buffer, void** ptr, int* N, int* H, int* W, int* channels);
+/* Export C channels starting at coff of an fp16 buffer to NCHW fp32 (device). */
+int tr_net_export_nchw(tr_net* net, int buffer, int coff, int C, float* out_dev, void* stream);
+/* Same for an fp32 buffer; softmax_pairs != 0 soft-maxes channel a against a^2
+ * (the class-pair softmax of retinaface/model.py:283-295). */
+int tr_net_export_nchw_f32(tr_net* net, int buffer, int coff, int C, float* out_dev,
+                           int softmax_pairs, void* stream);
+/* Algorithmic (un-padded) flops of the tensor-core ops and launch counts of the
+ * most recent run (for bench.py). */
+int tr_net_stats(tr_net* net, double* tc_flops, int* tc_launches, int* total_launches);
+/* Per-op device timing: when enabled every op of a run is bracketed by CUDA
+ * events on the launch stream; tr_net_profile synchronises and returns, per op,
+ * the milliseconds, whether it ran on the tcgen05 kernel and its algorithmic
+ * flops.  Returns the number of ops through *n_ops (at most cap are written). */
+int tr_net_set_profile(tr_net* net, int enable);
+int tr_net_profile(tr_net* net, float* ms, int32_t* is_tc, double* flops, int cap, int* n_ops);
+
+/* ---- single ops (parity tests, roofline micro-benchmarks) ---------------- */
+/* NHWC fp16 convolution with fused scale/shift/activation/residual epilogue.
+ * use_tc: 1 = tcgen05 implicit GEMM, 0 = CUDA-core direct kernel. */
+int tr_conv2d(const void* in_dev, int N, int H, int W, int in_cs, int in_coff, int cin_pad,
+              const void* w_dev, const float* scale_dev, const float* shift_dev,
+              const float* slope_dev, int cout_pad, int cout_store, int k, int stride, int pad,
+              int act, const void* res_dev, int res_cs, int res_up2, void* out_dev, int out_cs,
+              int out_coff, int out_is_f32, int use_tc, int repeat, float* ms, void* stream);
+
+/* ---- RetinaFace post-processing ------------------------------------------
+ * Replaces anchors_plane / decode_bboxes / decode_landmarks / threshold /
+ * argsort / torchvision.ops.nms of retinaface/wrapper.py:154-236.
+ * heads (fused == 0): the 9 reference outputs, order s32,s16,s8 x (prob NCHW (N,4,h,w)
+ * soft-maxed, bbox (N,8,h,w), landmark (N,20,h,w)), fp32 device pointers.
+ * Output rows: [score, x1,y1,x2,y2, 10 landmark coords, anchor index (int bits)]. */
+size_t tr_detect_workspace_bytes(int N, int H, int W);
+int tr_retinaface_decode_nms(const float* const* heads9_dev, int N, int H, int W, float threshold,
+                             double nms_threshold, int max_det, void* workspace_dev,
+                             int32_t* out_count_dev, int32_t* out_candidates_dev,
+                             float* out_det_dev, void* stream);
+/* Same on the fused fp32 NHWC head buffers (buffer ids for stride 32,16,8) of a net run. */
+int tr_retinaface_detect(tr_net* net, const int* head_buffers3, float threshold,
+                         double nms_threshold, int max_det, void* workspace_dev,
+                         int32_t* out_count_dev, int32_t* out_candidates_dev, float* out_det_dev,
+                         void* stream);
+
+/* ---- ArcFace ---------------------------------------------------------------
+ * Row-wise x / ||x||_2 with zero rows divided by 1: replaces
+ * sklearn.preprocessing.normalize(axis=1) of arcface/wrapper.py:174-176. */
+int tr_l2_normalize(const float* in_dev, float* out_dev, int N, int D, void* stream);
+
+/* ---- OpenPose parse ---------------------------------------------------------
+ * Replaces openpose/wrapper.py:214-483: x8 bicubic up-sampling (fused, never
+ * materialised), peak extraction, PAF line integrals, greedy limb matching,
+ * human assembly, keypoint rescale.  paf (N,38,h,w), heat (N,19,h,w) fp32 NCHW.
+ * keypoints: [N][TR_HUMAN_CAP][18][3] int32 (x, y, present); score [N][TR_HUMAN_CAP] f64;
+ * status bits per frame: 1 peak cap, 2 candidate cap, 4 human cap exceeded. */
+enum { TR_PEAK_CAP = 512, TR_CAND_CAP = 4096, TR_HUMAN_CAP = 128 };
+size_t tr_pose_workspace_bytes(int N);
+int tr_openpose_parse(const float* paf_dev, const float* heat_dev, int N, int h, int w, double scale,
+                      void* workspace_dev, int32_t* out_count_dev, int32_t* out_keypoints_dev,
+                      double* out_score_dev, int32_t* out_status_dev, void* stream);
+void tr_bicubic_table(float out32[32]);
+
+/* ---- frame pre-processing ---------------------------------------------------
+ * cv2.resize(INTER_LINEAR) on uint8 NHWC, bit-exact: replaces the host resize of
+ * face/detection/__init__.py:15-57 and pose/openpose/wrapper.py:93-113. */
+int tr_resize_bilinear_u8(const uint8_t* src_dev, int N, int H, int W, uint8_t* dst_dev, int h,
+                          int w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

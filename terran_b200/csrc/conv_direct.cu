@@ -1,0 +1,425 @@
+// CUDA-core kernels: the generic direct convolution (cross-check for the
+// tcgen05 path and the fallback for shapes it does not take), the u8 stem
+// convolutions, depthwise 3x3, 2x2 max-pool, channel-slice copy, layout export,
+// L2 normalisation and the cv2-exact bilinear resize.  All HBM-bound byte/half
+// work: coalesced 16-byte accesses over the NHWC channel axis.
+#include "common.cuh"
+
+namespace trb {
+
+namespace {
+
+__device__ __forceinline__ float act_f(float y, int act, float slope) {
+  if (act == ACT_RELU) return fmaxf(y, 0.f);
+  if (act == ACT_PRELU) return y >= 0.f ? y : y * slope;
+  return y;
+}
+
+// ---------------------------------------------------------------- direct conv
+// One thread = one output pixel x 8 output channels, fp32 accumulation.
+struct DirectParams {
+  const __half* in; int in_cs, in_coff, H, W, N;
+  const __half* w; int cin_pad, kh, kw, stride, pad;
+  const float* scale; const float* shift; const float* slope;
+  const float* scale2; const float* shift2;
+  int act, H_out, W_out, cout_store;
+  __half* out; int out_cs, out_coff;
+  __half* out2; int out2_cs, out2_coff;
+  const __half* res; int res_cs, res_coff, res_up2, res_H, res_W;
+  float* out_f32;
+};
+
+__global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) {
+  const long npix = static_cast<long>(p.N) * p.H_out * p.W_out;
+  const long pix = blockIdx.x * 128L + threadIdx.x;
+  if (pix >= npix) return;
+  const int c = blockIdx.y * 8;
+  if (c >= p.cout_store) return;
+  const int ow = pix % p.W_out;
+  const int oh = (pix / p.W_out) % p.H_out;
+  const int on = pix / (static_cast<long>(p.W_out) * p.H_out);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int taps = p.kh * p.kw;
+  for (int r = 0; r < p.kh; ++r) {
+    const int ih = oh * p.stride + r - p.pad;
+    if (ih < 0 || ih >= p.H) continue;
+    for (int s = 0; s < p.kw; ++s) {
+      const int iw = ow * p.stride + s - p.pad;
+      if (iw < 0 || iw >= p.W) continue;
+      const __half* ip = p.in + ((static_cast<long>(on) * p.H + ih) * p.W + iw) * p.in_cs + p.in_coff;
+      const __half* wp = p.w + (static_cast<long>(c) * taps + r * p.kw + s) * p.cin_pad;
+      for (int k = 0; k < p.cin_pad; k += 8) {
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(ip + k));
+        const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(xh[j]);
+          x[2 * j] = f.x; x[2 * j + 1] = f.y;
+        }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wp + static_cast<long>(o) * taps * p.cin_pad + k));
+          const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(wh[j]);
+            acc[o] = fmaf(x[2 * j], f.x, acc[o]);
+            acc[o] = fmaf(x[2 * j + 1], f.y, acc[o]);
+          }
+        }
+      }
+    }
+  }
+  float y[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const float t = fmaf(acc[o], __ldg(p.scale + c + o), __ldg(p.shift + c + o));
+    y[o] = act_f(t, p.act, p.act == ACT_PRELU ? __ldg(p.slope + c + o) : 0.f);
+  }
+  if (p.res) {
+    long rpix = pix;
+    if (p.res_up2) rpix = (static_cast<long>(on) * p.res_H + (oh >> 1)) * p.res_W + (ow >> 1);
+    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res + rpix * p.res_cs + p.res_coff + c));
+    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(rh[j]);
+      y[2 * j] += f.x; y[2 * j + 1] += f.y;
+    }
+  }
+  if (p.out_f32) {
+    float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.out_cs + p.out_coff + c);
+    o[0] = make_float4(y[0], y[1], y[2], y[3]);
+    o[1] = make_float4(y[4], y[5], y[6], y[7]);
+  } else {
+    uint4 ov;
+    __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh2[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+    *reinterpret_cast<uint4*>(p.out + pix * p.out_cs + p.out_coff + c) = ov;
+  }
+  if (p.out2) {
+    uint4 ov;
+    __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a0 = fmaf(y[2 * j], __ldg(p.scale2 + c + 2 * j), __ldg(p.shift2 + c + 2 * j));
+      const float a1 = fmaf(y[2 * j + 1], __ldg(p.scale2 + c + 2 * j + 1), __ldg(p.shift2 + c + 2 * j + 1));
+      oh2[j] = __floats2half2_rn(a0, a1);
+    }
+    *reinterpret_cast<uint4*>(p.out2 + pix * p.out2_cs + p.out2_coff + c) = ov;
+  }
+}
+
+// ------------------------------------------------------------------ u8 stems
+// 3x3, pad 1, 3 input channels read straight from the u8 frame (any strides,
+// any channel order: the BGR flip of the reference is folded into the packed
+// weights).  x' = x*in_scale + in_shift is applied to IN-BOUNDS taps only, so
+// the zero padding sees zeros exactly like the reference (which pads after the
+// affine).  One thread = one output pixel, all COUT channels.
+template <int COUT>
+__global__ void __launch_bounds__(128) stem_kernel(const StemArgs a, int H_out, int W_out) {
+  __shared__ float sw[27 * COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+    // packed as [cout][kh][kw][c]; stored transposed [tap*3+c][cout] for broadcast reads
+    const int o = i / 27, t = i % 27;
+    sw[t * COUT + o] = a.w[i];
+  }
+  __syncthreads();
+  const long npix = static_cast<long>(a.N) * H_out * W_out;
+  const long pix = blockIdx.x * 128L + threadIdx.x;
+  if (pix >= npix) return;
+  const int ow = pix % W_out;
+  const int oh = (pix / W_out) % H_out;
+  const int on = pix / (static_cast<long>(W_out) * H_out);
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+  for (int r = 0; r < 3; ++r) {
+    const int ih = oh * a.stride + r - 1;
+    if (ih < 0 || ih >= a.H) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int iw = ow * a.stride + s - 1;
+      if (iw < 0 || iw >= a.W) continue;
+      const uint8_t* ip = a.in + on * a.sn + ih * a.sh + iw * a.sw;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float x = fmaf(static_cast<float>(ip[ch * a.sc]), a.in_scale, a.in_shift);
+        const float* wrow = sw + ((r * 3 + s) * 3 + ch) * COUT;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(x, wrow[o], acc[o]);
+      }
+    }
+  }
+  __half* op = a.out.ptr + pix * a.out.cs + a.out.coff;
+  __half* op2 = a.out2.ptr ? a.out2.ptr + pix * a.out2.cs + a.out2.coff : nullptr;
+#pragma unroll
+  for (int o = 0; o < COUT; o += 8) {
+    uint4 ov, ov2;
+    __half2* h = reinterpret_cast<__half2*>(&ov);
+    __half2* h2 = reinterpret_cast<__half2*>(&ov2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float y0 = fmaf(acc[o + 2 * j], a.scale[o + 2 * j], a.shift[o + 2 * j]);
+      float y1 = fmaf(acc[o + 2 * j + 1], a.scale[o + 2 * j + 1], a.shift[o + 2 * j + 1]);
+      y0 = act_f(y0, a.act, a.act == ACT_PRELU ? a.slope[o + 2 * j] : 0.f);
+      y1 = act_f(y1, a.act, a.act == ACT_PRELU ? a.slope[o + 2 * j + 1] : 0.f);
+      h[j] = __floats2half2_rn(y0, y1);
+      if (op2)
+        h2[j] = __floats2half2_rn(fmaf(y0, a.scale2[o + 2 * j], a.shift2[o + 2 * j]),
+                                  fmaf(y1, a.scale2[o + 2 * j + 1], a.shift2[o + 2 * j + 1]));
+    }
+    *reinterpret_cast<uint4*>(op + o) = ov;
+    if (op2) *reinterpret_cast<uint4*>(op2 + o) = ov2;
+  }
+}
+
+// ------------------------------------------------------------- depthwise 3x3
+__global__ void __launch_bounds__(256) dwconv_kernel(const DwArgs a, int H_out, int W_out) {
+  const int groups = a.in.C / 8;
+  const long total = static_cast<long>(a.in.N) * H_out * W_out * groups;
+  const long idx = blockIdx.x * 256L + threadIdx.x;
+  if (idx >= total) return;
+  const int g = idx % groups;
+  const long pix = idx / groups;
+  const int ow = pix % W_out;
+  const int oh = (pix / W_out) % H_out;
+  const int on = pix / (static_cast<long>(W_out) * H_out);
+  const int c = g * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < 3; ++r) {
+    const int ih = oh * a.stride + r - 1;
+    if (ih < 0 || ih >= a.in.H) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int iw = ow * a.stride + s - 1;
+      if (iw < 0 || iw >= a.in.W) continue;
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(
+          a.in.ptr + ((static_cast<long>(on) * a.in.H + ih) * a.in.W + iw) * a.in.cs + a.in.coff + c));
+      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+      const float* wp = a.w + (r * 3 + s) * a.in.C + c;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(xh[j]);
+        acc[2 * j] = fmaf(f.x, wv[2 * j], acc[2 * j]);
+        acc[2 * j + 1] = fmaf(f.y, wv[2 * j + 1], acc[2 * j + 1]);
+      }
+    }
+  }
+  uint4 ov;
+  __half2* h = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float y0 = fmaxf(fmaf(acc[2 * j], __ldg(a.scale + c + 2 * j), __ldg(a.shift + c + 2 * j)), 0.f);
+    const float y1 = fmaxf(fmaf(acc[2 * j + 1], __ldg(a.scale + c + 2 * j + 1), __ldg(a.shift + c + 2 * j + 1)), 0.f);
+    h[j] = __floats2half2_rn(y0, y1);
+  }
+  *reinterpret_cast<uint4*>(a.out.ptr + pix * a.out.cs + a.out.coff + c) = ov;
+}
+
+// ---------------------------------------------------------------- 2x2 maxpool
+__global__ void __launch_bounds__(256) maxpool2_kernel(const View in, const View out) {
+  const int groups = out.C / 8;
+  const long total = static_cast<long>(out.N) * out.H * out.W * groups;
+  const long idx = blockIdx.x * 256L + threadIdx.x;
+  if (idx >= total) return;
+  const int g = idx % groups;
+  const long pix = idx / groups;
+  const int ow = pix % out.W;
+  const int oh = (pix / out.W) % out.H;
+  const int on = pix / (static_cast<long>(out.W) * out.H);
+  const __half* base = in.ptr + ((static_cast<long>(on) * in.H + oh * 2) * in.W + ow * 2) * in.cs + in.coff + g * 8;
+  uint4 v00 = __ldg(reinterpret_cast<const uint4*>(base));
+  const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(base + in.cs));
+  const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long>(in.W) * in.cs));
+  const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long>(in.W) * in.cs + in.cs));
+  __half2* a = reinterpret_cast<__half2*>(&v00);
+  const __half2* b = reinterpret_cast<const __half2*>(&v01);
+  const __half2* c = reinterpret_cast<const __half2*>(&v10);
+  const __half2* d = reinterpret_cast<const __half2*>(&v11);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = __hmax2(__hmax2(a[j], b[j]), __hmax2(c[j], d[j]));
+  *reinterpret_cast<uint4*>(out.ptr + pix * out.cs + out.coff + g * 8) = v00;
+}
+
+__global__ void __launch_bounds__(256) copy_slice_kernel(const View in, const View out) {
+  const int groups = in.C / 8;
+  const long total = static_cast<long>(in.N) * in.H * in.W * groups;
+  const long idx = blockIdx.x * 256L + threadIdx.x;
+  if (idx >= total) return;
+  const int g = idx % groups;
+  const long pix = idx / groups;
+  *reinterpret_cast<uint4*>(out.ptr + pix * out.cs + out.coff + g * 8) =
+      __ldg(reinterpret_cast<const uint4*>(in.ptr + pix * in.cs + in.coff + g * 8));
+}
+
+__global__ void __launch_bounds__(256) export_nchw_kernel(const View in, int C, float* out) {
+  const long total = static_cast<long>(in.N) * C * in.H * in.W;
+  const long idx = blockIdx.x * 256L + threadIdx.x;
+  if (idx >= total) return;
+  const int w = idx % in.W;
+  const int h = (idx / in.W) % in.H;
+  const int c = (idx / (static_cast<long>(in.W) * in.H)) % C;
+  const int n = idx / (static_cast<long>(in.W) * in.H * C);
+  out[idx] = __half2float(in.ptr[((static_cast<long>(n) * in.H + h) * in.W + w) * in.cs + in.coff + c]);
+}
+
+// fp32 NHWC slice -> NCHW; with softmax_pairs the 4 channels are the class
+// logits and channel a is soft-maxed against channel a^2 (model.py:283-286).
+__global__ void __launch_bounds__(256)
+export_nchw_f32_kernel(const float* in, int N, int H, int W, int cs, int coff, int C, float* out,
+                       int softmax_pairs) {
+  const long total = static_cast<long>(N) * C * H * W;
+  const long idx = blockIdx.x * 256L + threadIdx.x;
+  if (idx >= total) return;
+  const int w = idx % W;
+  const int h = (idx / W) % H;
+  const int c = (idx / (static_cast<long>(W) * H)) % C;
+  const int n = idx / (static_cast<long>(W) * H * C);
+  const float* px = in + ((static_cast<long>(n) * H + h) * W + w) * cs + coff;
+  float v = px[c];
+  if (softmax_pairs) {
+    const float o = px[c ^ 2];
+    const float m = fmaxf(v, o);
+    const float ev = expf(v - m), eo = expf(o - m);
+    v = ev / (ev + eo);
+  }
+  out[idx] = v;
+}
+
+// x / max-safe L2 norm per row (sklearn normalize: zero rows divide by 1).
+__global__ void __launch_bounds__(128) l2_normalize_kernel(const float* in, float* out, int D) {
+  const float* x = in + static_cast<long>(blockIdx.x) * D;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < D; i += 128) s = fmaf(x[i], x[i], s);
+  __shared__ float red[4];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = red[0] + red[1] + red[2] + red[3];
+  float nrm = sqrtf(s);
+  if (nrm == 0.f) nrm = 1.f;
+  for (int i = threadIdx.x; i < D; i += 128) out[static_cast<long>(blockIdx.x) * D + i] = x[i] / nrm;
+}
+
+// cv2.resize(INTER_LINEAR) on uint8, bit-exact integer restatement
+// (SURVEY.md Appendix A.5): 11-bit fixed-point taps, the intermediate row sum
+// is >>4, the vertical blend is ((b0*r0)>>16) + ((b1*r1)>>16) + 2 >> 2.
+__global__ void __launch_bounds__(256)
+resize_u8_kernel(const uint8_t* src, int N, int H, int W, uint8_t* dst, int h, int w,
+                 double sy_d, double sx_d) {
+  const long total = static_cast<long>(N) * h * w;
+  const long idx = blockIdx.x * 256L + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = idx % w;
+  const int oy = (idx / w) % h;
+  const int n = idx / (static_cast<long>(w) * h);
+  auto tap = [](int o, double scale, int n_src, int& i0, int& i1, int& a0, int& a1) {
+    float f = static_cast<float>((o + 0.5) * scale - 0.5);
+    int s = static_cast<int>(floorf(f));
+    f -= s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= n_src - 1) { s = n_src - 1; f = 0.f; }
+    i0 = s;
+    i1 = min(s + 1, n_src - 1);
+    a1 = static_cast<int>(rintf(f * 2048.f));
+    a0 = static_cast<int>(rintf((1.f - f) * 2048.f));
+  };
+  int x0, x1, ax0, ax1, y0, y1, ay0, ay1;
+  tap(ox, sx_d, W, x0, x1, ax0, ax1);
+  tap(oy, sy_d, H, y0, y1, ay0, ay1);
+  const uint8_t* r0 = src + (static_cast<long>(n) * H + y0) * W * 3;
+  const uint8_t* r1 = src + (static_cast<long>(n) * H + y1) * W * 3;
+  uint8_t* o = dst + idx * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int top = r0[x0 * 3 + c] * ax0 + r0[x1 * 3 + c] * ax1;
+    const int bot = r1[x0 * 3 + c] * ax0 + r1[x1 * 3 + c] * ax1;
+    const int v = (((ay0 * (top >> 4)) >> 16) + ((ay1 * (bot >> 4)) >> 16) + 2) >> 2;
+    o[c] = static_cast<uint8_t>(min(max(v, 0), 255));
+  }
+}
+
+}  // namespace
+
+void conv_direct_launch(const ConvArgs& a, cudaStream_t s) {
+  TR_CHECK(a.cin_pad % 8 == 0 && a.cout_store % 8 == 0, "direct conv needs 8-channel granules");
+  DirectParams p{};
+  p.in = a.in.ptr; p.in_cs = a.in.cs; p.in_coff = a.in.coff; p.H = a.in.H; p.W = a.in.W; p.N = a.in.N;
+  p.w = a.w; p.cin_pad = a.cin_pad; p.kh = a.kh; p.kw = a.kw; p.stride = a.stride; p.pad = a.pad;
+  p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.scale2 = a.scale2; p.shift2 = a.shift2;
+  p.act = a.act; p.H_out = a.H_out; p.W_out = a.W_out; p.cout_store = a.cout_store;
+  p.out = a.out.ptr; p.out_cs = a.out.cs; p.out_coff = a.out.coff;
+  p.out2 = a.out2.ptr; p.out2_cs = a.out2.cs; p.out2_coff = a.out2.coff;
+  p.res = a.res.ptr; p.res_cs = a.res.cs; p.res_coff = a.res.coff; p.res_up2 = a.res_up2;
+  p.res_H = a.res.H; p.res_W = a.res.W;
+  p.out_f32 = a.out_f32;
+  const long npix = static_cast<long>(p.N) * p.H_out * p.W_out;
+  dim3 grid(static_cast<unsigned>((npix + 127) / 128), a.cout_store / 8);
+  conv_direct_kernel<<<grid, 128, 0, s>>>(p);
+  TR_CUDA(cudaGetLastError());
+}
+
+void stem_launch(const StemArgs& a, cudaStream_t s) {
+  const int H_out = (a.H + 2 - 3) / a.stride + 1, W_out = (a.W + 2 - 3) / a.stride + 1;
+  const long npix = static_cast<long>(a.N) * H_out * W_out;
+  const unsigned grid = static_cast<unsigned>((npix + 127) / 128);
+  if (a.cout == 8) stem_kernel<8><<<grid, 128, 0, s>>>(a, H_out, W_out);
+  else if (a.cout == 64) stem_kernel<64><<<grid, 128, 0, s>>>(a, H_out, W_out);
+  else fail("stem conv supports 8 or 64 output channels");
+  TR_CUDA(cudaGetLastError());
+}
+
+void dwconv_launch(const DwArgs& a, cudaStream_t s) {
+  const int H_out = (a.in.H + 2 - 3) / a.stride + 1, W_out = (a.in.W + 2 - 3) / a.stride + 1;
+  TR_CHECK(H_out == a.out.H && W_out == a.out.W, "depthwise output dims");
+  const long total = static_cast<long>(a.in.N) * H_out * W_out * (a.in.C / 8);
+  dwconv_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(a, H_out, W_out);
+  TR_CUDA(cudaGetLastError());
+}
+
+void maxpool2_launch(const View& in, const View& out, cudaStream_t s) {
+  const long total = static_cast<long>(out.N) * out.H * out.W * (out.C / 8);
+  maxpool2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out);
+  TR_CUDA(cudaGetLastError());
+}
+
+void copy_slice_launch(const View& in, const View& out, cudaStream_t s) {
+  const long total = static_cast<long>(in.N) * in.H * in.W * (in.C / 8);
+  copy_slice_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out);
+  TR_CUDA(cudaGetLastError());
+}
+
+void export_nchw_launch(const View& in, int C, float* out, cudaStream_t s) {
+  const long total = static_cast<long>(in.N) * C * in.H * in.W;
+  export_nchw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, C, out);
+  TR_CUDA(cudaGetLastError());
+}
+
+void export_nchw_f32_launch(const float* in, int N, int H, int W, int cs, int coff, int C,
+                            float* out, int softmax_pairs, cudaStream_t s) {
+  const long total = static_cast<long>(N) * C * H * W;
+  export_nchw_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+      in, N, H, W, cs, coff, C, out, softmax_pairs);
+  TR_CUDA(cudaGetLastError());
+}
+
+void l2_normalize_launch(const float* in, float* out, int N, int D, cudaStream_t s) {
+  if (N == 0) return;
+  l2_normalize_kernel<<<N, 128, 0, s>>>(in, out, D);
+  TR_CUDA(cudaGetLastError());
+}
+
+void resize_bilinear_u8_launch(const uint8_t* src, int N, int H, int W, uint8_t* dst, int h,
+                               int w, cudaStream_t s) {
+  const long total = static_cast<long>(N) * h * w;
+  resize_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+      src, N, H, W, dst, h, w, double(H) / h, double(W) / w);
+  TR_CUDA(cudaGetLastError());
+}
+
+}  // namespace trb

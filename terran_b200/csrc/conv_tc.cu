@@ -1,0 +1,539 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (sm_100a).
+//
+//   D[pixels, cout] = sum over taps (r,s) and channel chunks of
+//                     A_tap[pixels, KC] * W_tap[cout, KC]^T
+//
+// Activations are NHWC fp16.  For every filter tap the A operand is just a
+// shifted window of the input, so a plain *tiled* TMA load of the box
+// {KC channels, bw, bh, bn} at coordinates shifted by the tap gives the
+// im2col tile directly in the canonical K-major swizzled layout, and TMA's
+// out-of-bounds zero fill implements the convolution's zero padding.  Stride-2
+// convolutions view the input as {2C, W/2, 2, H/2, N} so a tap selects a
+// (row parity, column parity) plane and the window stays dense.
+//
+// Warp roles (192 threads, one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2-5   epilogue: tcgen05.ld -> scale/shift/activation/residual -> HBM
+// Pipelines: smem ring (full/empty mbarriers) between TMA and MMA, and a
+// double-buffered TMEM accumulator (tmem_full/tmem_empty) between MMA and the
+// epilogue, so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Replaces the cuDNN/ATen convolutions behind every nn.Conv2d of the
+// reference's models (retinaface/model.py, arcface/model.py, openpose/model.py).
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <vector>
+
+namespace trb {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kSmemBudget = 200 * 1024;
+
+struct TcParams {
+  int bw, bh, bn, rows;
+  int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
+  int N_tile;
+  int N, H_out, W_out;
+  int kh, kw, pad, stride;
+  int KC, kchunks, cin_pad;
+  int in_coff, in_cs;
+  int k_blocks;
+  int stages;
+  uint32_t a_bytes, b_bytes, stage_bytes;
+  uint32_t sbo_bytes, layout_type, idesc;
+  uint32_t tmem_cols;
+  // epilogue
+  const float* scale; const float* shift; const float* slope;
+  const float* scale2; const float* shift2;
+  int act;
+  __half* out; int out_cs, out_coff, cout_store;
+  __half* out2; int out2_cs, out2_coff;
+  const __half* res; int res_cs, res_coff, res_up2, res_H, res_W;
+  float* out_f32;
+  int* err;   // device flag set on a pipeline timeout
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Bounded wait: a broken pipeline traps (sticky error the host reports)
+// instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);          // start address
+  d |= static_cast<uint64_t>(1) << 16;                          // LBO (unused: swizzled K-major)
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;             // 8-row group stride
+  d |= static_cast<uint64_t>(1) << 46;                          // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(layout_type) << 61;                // swizzle mode
+  return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
+        "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float apply_act(float y, int act, float slope) {
+  if (act == ACT_RELU) return fmaxf(y, 0.f);
+  if (act == ACT_PRELU) return y >= 0.f ? y : y * slope;
+  return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // Manual 1024-byte alignment (SWIZZLE_128B atoms repeat every 1024 bytes).
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + p.stages * p.stage_bytes;
+  // barrier layout: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int taps = p.kh * p.kw;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int wb = mt % p.tiles_w; mt /= p.tiles_w;
+        const int hb = mt % p.tiles_h; mt /= p.tiles_h;
+        const int nb = mt;
+        const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = nb * p.bn;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / p.kw, s = tap % p.kw;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
+            const uint32_t sa = base + stage * p.stage_bytes;
+            const uint32_t sb = sa + p.a_bytes;
+            mbar_expect_tx(full_bar(stage), p.rows * p.KC * 2 + p.N_tile * p.KC * 2);
+            const int c = p.in_coff + kc * p.KC;
+            if (p.stride == 1) {
+              tma_load_5d(sa, &tmA, full_bar(stage), c, w0 + s - p.pad, h0 + r - p.pad, n0, 0);
+            } else {
+              const int oy = r - p.pad, ox = s - p.pad;
+              const int py = oy & 1, px = ox & 1;
+              tma_load_5d(sa, &tmA, full_bar(stage), px * p.in_cs + c, w0 + ((ox - px) >> 1), py,
+                          h0 + ((oy - py) >> 1), n0);
+            }
+            tma_load_2d(sb, &tmB, full_bar(stage), tap * p.cin_pad + kc * p.KC, nt * p.N_tile);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const int ksteps = p.KC / 16;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + acc * p.N_tile;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase, p.err, 3);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + stage * p.stage_bytes;
+          const uint32_t sb = sa + p.a_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = umma_desc(sa + k * 32, p.sbo_bytes, p.layout_type);
+            const uint64_t bd = umma_desc(sb + k * 32, p.sbo_bytes, p.layout_type);
+            umma_f16(d_tmem, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
+          if (kb == p.k_blocks - 1) umma_commit(tfull_bar(acc));
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int w_l = row % p.bw;
+    const int h_l = (row / p.bw) % p.bh;
+    const int n_l = row / (p.bw * p.bh);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int wb = mt % p.tiles_w; mt /= p.tiles_w;
+      const int hb = mt % p.tiles_h; mt /= p.tiles_h;
+      const int nb = mt;
+      const int ow = wb * p.bw + w_l, oh = hb * p.bh + h_l, on = nb * p.bn + n_l;
+      const bool valid = row < p.rows && ow < p.W_out && oh < p.H_out && on < p.N;
+      const long pix = (static_cast<long>(on) * p.H_out + oh) * p.W_out + ow;
+      long rpix = pix;
+      if (p.res && p.res_up2)
+        rpix = (static_cast<long>(on) * p.res_H + (oh >> 1)) * p.res_W + (ow >> 1);
+
+      mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.N_tile;
+      for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
+        uint32_t v[16];
+        __syncwarp();                       // tcgen05.ld is warp-collective (.sync.aligned)
+        tmem_ld16(taddr + c0, v);
+        const int cbase = nt * p.N_tile + c0;
+        if (!valid || cbase >= p.cout_store) continue;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int c = cbase + g * 8;
+          if (c >= p.cout_store) break;
+          float y[8];
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.shift + c + 4));
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float t = fmaf(__uint_as_float(v[g * 8 + j]), sc[j], sh[j]);
+            const float sl = (p.act == ACT_PRELU) ? __ldg(p.slope + c + j) : 0.f;
+            y[j] = apply_act(t, p.act, sl);
+          }
+          if (p.res) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res + rpix * p.res_cs +
+                                                                  p.res_coff + c));
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(rh[j]);
+              y[2 * j] += f.x;
+              y[2 * j + 1] += f.y;
+            }
+          }
+          if (p.out_f32) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.out_cs + p.out_coff + c);
+            o[0] = make_float4(y[0], y[1], y[2], y[3]);
+            o[1] = make_float4(y[4], y[5], y[6], y[7]);
+          } else {
+            uint4 ov;
+            __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oh2[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+            *reinterpret_cast<uint4*>(p.out + pix * p.out_cs + p.out_coff + c) = ov;
+          }
+          if (p.out2) {
+            uint4 ov;
+            __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a0 = fmaf(y[2 * j], __ldg(p.scale2 + c + 2 * j), __ldg(p.shift2 + c + 2 * j));
+              const float a1 = fmaf(y[2 * j + 1], __ldg(p.scale2 + c + 2 * j + 1),
+                                    __ldg(p.shift2 + c + 2 * j + 1));
+              oh2[j] = __floats2half2_rn(a0, a1);
+            }
+            *reinterpret_cast<uint4*>(p.out2 + pix * p.out2_cs + p.out2_coff + c) = ov;
+          }
+        }
+      }
+      // Release the accumulator back to the MMA warp.
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(p.tmem_cols) : "memory");
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    TR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q));
+    TR_CHECK(q == cudaDriverEntryPointSuccess && ptr, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+int* tc_error_flag() {
+  static int* flag = nullptr;
+  if (!flag) {
+    TR_CUDA(cudaMalloc(&flag, sizeof(int)));
+    TR_CUDA(cudaMemset(flag, 0, sizeof(int)));
+  }
+  return flag;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    TR_CUDA(cudaGetDevice(&dev));
+    TR_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+}  // namespace
+
+struct ConvTcPlan {
+  CUtensorMap tmA, tmB;
+  TcParams p;
+  int grid;
+  uint32_t smem;
+  double flops;
+};
+
+bool conv_tc_eligible(const ConvArgs& a) {
+  if (a.cin_pad % 16 || a.cout_pad % 16 || a.cout_store % 8) return false;
+  if (a.stride != 1 && a.stride != 2) return false;
+  if (a.stride == 2 && ((a.in.H | a.in.W) & 1)) return false;
+  if (a.in.cs % 8 || a.in.coff % 8 || a.out.cs % 8 || a.out.coff % 8) return false;
+  if (a.cin_pad > 64 && a.cin_pad % 64) return false;
+  if (a.cin_pad != 16 && a.cin_pad != 32 && a.cin_pad % 64) return false;
+  if (a.cout_pad > 256 && a.cout_pad % 256) return false;
+  return true;
+}
+
+ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
+  TR_CHECK(conv_tc_eligible(a), "convolution not eligible for the tcgen05 path");
+  auto* plan = new ConvTcPlan();
+  TcParams& p = plan->p;
+  p = TcParams{};
+  p.N = a.in.N; p.H_out = a.H_out; p.W_out = a.W_out;
+  p.kh = a.kh; p.kw = a.kw; p.pad = a.pad; p.stride = a.stride;
+  p.cin_pad = a.cin_pad;
+  p.KC = a.cin_pad >= 64 ? 64 : a.cin_pad;
+  p.kchunks = a.cin_pad / p.KC;
+  p.k_blocks = a.kh * a.kw * p.kchunks;
+  p.in_coff = a.in.coff; p.in_cs = a.in.cs;
+  p.N_tile = a.cout_pad > 256 ? 256 : a.cout_pad;
+  p.n_tiles = a.cout_pad / p.N_tile;
+
+  // Pick the pixel box {bw, bh, bn} (<= 128 rows) that wastes the fewest MMA rows.
+  double best = -1.0;
+  for (int bw = 1; bw <= std::min(p.W_out, 128); ++bw) {
+    for (int bh = 1; bh <= std::min(p.H_out, 128 / bw); ++bh) {
+      for (int bn = 1; bn <= std::min(p.N, 128 / (bw * bh)); ++bn) {
+        const double tiles = double(ceil_div(p.W_out, bw)) * ceil_div(p.H_out, bh) * ceil_div(p.N, bn);
+        double eff = double(p.W_out) * p.H_out * p.N / (tiles * 128.0);
+        eff += 1e-6 * bw;      // prefer long contiguous runs on ties
+        if (eff > best) { best = eff; p.bw = bw; p.bh = bh; p.bn = bn; }
+      }
+    }
+  }
+  p.rows = p.bw * p.bh * p.bn;
+  p.tiles_w = ceil_div(p.W_out, p.bw);
+  p.tiles_h = ceil_div(p.H_out, p.bh);
+  p.tiles_n = ceil_div(p.N, p.bn);
+  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+
+  p.a_bytes = round_up(128 * p.KC * 2, 1024);         // MMA always reads 128 rows
+  p.b_bytes = round_up(p.N_tile * p.KC * 2, 1024);
+  p.stage_bytes = p.a_bytes + p.b_bytes;
+  p.stages = std::min(kMaxStages, int(kSmemBudget / p.stage_bytes));
+  p.stages = std::max(2, std::min(p.stages, p.k_blocks + 1));
+  p.sbo_bytes = 8u * p.KC * 2u;
+  CUtensorMapSwizzle swz;
+  if (p.KC == 64) { p.layout_type = 2; swz = CU_TENSOR_MAP_SWIZZLE_128B; }
+  else if (p.KC == 32) { p.layout_type = 4; swz = CU_TENSOR_MAP_SWIZZLE_64B; }
+  else { p.layout_type = 6; swz = CU_TENSOR_MAP_SWIZZLE_32B; }
+  // kind::f16 instruction descriptor: D=f32, A=B=f16, K-major, N>>3, M>>4.
+  p.idesc = (1u << 4) | (uint32_t(p.N_tile >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+  uint32_t cols = 32;
+  while (cols < uint32_t(2 * p.N_tile)) cols <<= 1;
+  p.tmem_cols = cols;
+
+  p.scale = a.scale; p.shift = a.shift; p.slope = a.slope;
+  p.scale2 = a.scale2; p.shift2 = a.shift2;
+  p.act = a.act;
+  p.out = a.out.ptr; p.out_cs = a.out.cs; p.out_coff = a.out.coff; p.cout_store = a.cout_store;
+  p.out2 = a.out2.ptr; p.out2_cs = a.out2.cs; p.out2_coff = a.out2.coff;
+  p.res = a.res.ptr; p.res_cs = a.res.cs; p.res_coff = a.res.coff; p.res_up2 = a.res_up2;
+  p.res_H = a.res.H; p.res_W = a.res.W;
+  p.out_f32 = a.out_f32;
+  p.err = tc_error_flag();
+  TR_CHECK(a.act != ACT_PRELU || a.slope, "PReLU needs slopes");
+  TR_CHECK(!a.out2.ptr || (a.scale2 && a.shift2), "second output needs scale2/shift2");
+
+  // ---- tensor maps
+  auto encode = encode_fn();
+  const cuuint64_t cs = a.in.cs, W = a.in.W, H = a.in.H, N = a.in.N;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  if (a.stride == 1) {
+    gdim[0] = cs; gdim[1] = W; gdim[2] = H; gdim[3] = N; gdim[4] = 1;
+    gstr[0] = cs * 2; gstr[1] = W * cs * 2; gstr[2] = H * W * cs * 2; gstr[3] = N * H * W * cs * 2;
+    box[0] = p.KC; box[1] = p.bw; box[2] = p.bh; box[3] = p.bn; box[4] = 1;
+  } else {
+    gdim[0] = 2 * cs; gdim[1] = W / 2; gdim[2] = 2; gdim[3] = H / 2; gdim[4] = N;
+    gstr[0] = 2 * cs * 2; gstr[1] = W * cs * 2; gstr[2] = 2 * W * cs * 2; gstr[3] = H * W * cs * 2;
+    box[0] = p.KC; box[1] = p.bw; box[2] = 1; box[3] = p.bh; box[4] = p.bn;
+  }
+  CUresult r = encode(&plan->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, a.in.ptr, gdim, gstr, box,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: " + std::to_string(int(r)));
+  const cuuint64_t ktot = cuuint64_t(a.kh) * a.kw * a.cin_pad;
+  cuuint64_t wdim[2] = {ktot, cuuint64_t(a.cout_pad)};
+  cuuint64_t wstr[1] = {ktot * 2};
+  cuuint32_t wbox[2] = {cuuint32_t(p.KC), cuuint32_t(p.N_tile)};
+  r = encode(&plan->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(a.w), wdim, wstr,
+             wbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: " + std::to_string(int(r)));
+
+  plan->grid = std::min(p.total_tiles, num_sms());
+  plan->smem = p.stages * p.stage_bytes + 1024 /*alignment*/ + 8 * (2 * kMaxStages + 4) + 16;
+  plan->flops = 2.0 * p.N * p.H_out * p.W_out * double(a.cout_pad) * a.kh * a.kw * a.cin_pad;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TR_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
+    attr_set = true;
+  }
+  return plan;
+}
+
+void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
+
+double conv_tc_plan_flops(const ConvTcPlan* p) { return p->flops; }
+
+void conv_tc_launch(const ConvTcPlan* plan, cudaStream_t s) {
+  conv_tc_kernel<<<plan->grid, kThreads, plan->smem, s>>>(plan->tmA, plan->tmB, plan->p);
+  TR_CUDA(cudaGetLastError());
+}
+
+}  // namespace trb

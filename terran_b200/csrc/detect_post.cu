@@ -1,0 +1,283 @@
+// RetinaFace post-processing on the GPU, batched over images:
+//   score threshold -> candidate keys -> descending sort (stable by anchor
+//   index) -> anchor/bbox/landmark decode -> greedy NMS -> survivors.
+// Replaces the per-image Python loop of the reference
+// (terran/face/detection/retinaface/wrapper.py:154-236, anchors.py:7-51) and
+// torchvision.ops.nms.  Compiled with -fmad=false: every fp32 product and sum is
+// rounded separately, exactly like the numpy oracle (oracle/detect.py), and the
+// IoU is compared against the threshold as a double like torchvision's CPU nms.
+#include "detect_post.cuh"
+
+namespace trb {
+
+namespace {
+
+constexpr int kSelThreads = 512;
+constexpr int kSmemKeys = 4096;
+
+struct Level { int stride, fh, fw, off; };
+
+struct DetParams {
+  DetHeads heads;
+  int N, H, W;
+  Level lv[3];
+  int A;           // anchors per image
+  int capP;        // power-of-two key capacity per image (>= A)
+  float thr;
+  double nms_thr;
+  int max_det;
+  unsigned long long* keys;   // [N][capP]
+  int* counts;                // [N] candidate counts
+  float* sbox;                // [N][A][4] decoded boxes in sorted order
+  int* kept;                  // [N][A] kept positions
+  // outputs
+  int* out_count;             // [N] survivors (may exceed max_det: truncated rows)
+  int* out_cand;              // [N] candidates
+  float* out_det;             // [N][max_det][16]
+};
+
+__device__ __forceinline__ void locate(const DetParams& p, int idx, int& l, int& pos, int& a) {
+  l = idx >= p.lv[2].off ? 2 : (idx >= p.lv[1].off ? 1 : 0);
+  const int local = idx - p.lv[l].off;
+  a = local & 1;
+  pos = local >> 1;
+}
+
+__device__ __forceinline__ float head_score(const DetParams& p, int n, int l, int pos, int a) {
+  const int hw = p.lv[l].fh * p.lv[l].fw;
+  if (p.heads.fused) {
+    const float* px = p.heads.cls[l] + (static_cast<long>(n) * hw + pos) * 32;
+    const float l0 = px[a], l1 = px[2 + a];
+    const float m = fmaxf(l0, l1);
+    const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+    return e1 / (e0 + e1);
+  }
+  return p.heads.cls[l][(static_cast<long>(n) * 4 + 2 + a) * hw + pos];
+}
+
+__device__ __forceinline__ float head_bbox(const DetParams& p, int n, int l, int pos, int ch) {
+  const int hw = p.lv[l].fh * p.lv[l].fw;
+  if (p.heads.fused) return p.heads.cls[l][(static_cast<long>(n) * hw + pos) * 32 + 4 + ch];
+  return p.heads.bbox[l][(static_cast<long>(n) * 8 + ch) * hw + pos];
+}
+
+__device__ __forceinline__ float head_lmk(const DetParams& p, int n, int l, int pos, int ch) {
+  const int hw = p.lv[l].fh * p.lv[l].fw;
+  if (p.heads.fused) return p.heads.cls[l][(static_cast<long>(n) * hw + pos) * 32 + 12 + ch];
+  return p.heads.lmk[l][(static_cast<long>(n) * 20 + ch) * hw + pos];
+}
+
+// ---- 1. threshold scan: every anchor of every image, warp-aggregated append.
+__global__ void __launch_bounds__(256) det_scan_kernel(const DetParams p) {
+  const int n = blockIdx.y;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  bool pass = false;
+  float score = 0.f;
+  if (idx < p.A) {
+    int l, pos, a;
+    locate(p, idx, l, pos, a);
+    score = head_score(p, n, l, pos, a);
+    pass = score >= p.thr;
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+  if (!ballot) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(p.counts + n, __popc(ballot));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (pass) {
+    const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+    // ascending key order = descending score, then ascending anchor index
+    const unsigned long long key =
+        (static_cast<unsigned long long>(~__float_as_uint(score)) << 32) | static_cast<unsigned>(idx);
+    p.keys[static_cast<long>(n) * p.capP + slot] = key;
+  }
+}
+
+__device__ void bitonic_sort(unsigned long long* k, int P) {
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = k[lo], b = k[hi];
+        if ((a > b) == up) { k[lo] = b; k[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float iou_f(const float4 a, const float4 b) {
+  const float area_a = (a.z - a.x) * (a.w - a.y);
+  const float area_b = (b.z - b.x) * (b.w - b.y);
+  const float w = fmaxf(0.f, fminf(a.z, b.z) - fmaxf(a.x, b.x));
+  const float h = fmaxf(0.f, fminf(a.w, b.w) - fmaxf(a.y, b.y));
+  const float inter = w * h;
+  return inter / (area_a + area_b - inter);
+}
+
+// ---- 2. one block per image: sort, decode, blocked greedy NMS, output.
+__global__ void __launch_bounds__(kSelThreads) det_select_kernel(const DetParams p) {
+  __shared__ unsigned long long skeys[kSmemKeys];
+  __shared__ unsigned long long chunk_mask[64];
+  __shared__ unsigned long long alive_s;
+  __shared__ int kept_n_s;
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int K = min(p.counts[n], p.A);
+  unsigned long long* gkeys = p.keys + static_cast<long>(n) * p.capP;
+  int P = 1;
+  while (P < K) P <<= 1;
+  unsigned long long* keys = gkeys;
+  if (P <= kSmemKeys) {
+    for (int i = tid; i < P; i += kSelThreads) skeys[i] = i < K ? gkeys[i] : ~0ull;
+    keys = skeys;
+  } else {
+    for (int i = K + tid; i < P; i += kSelThreads) gkeys[i] = ~0ull;
+  }
+  __syncthreads();
+  if (K > 1) bitonic_sort(keys, P);
+
+  // decode boxes of the sorted candidates
+  float4* sbox = reinterpret_cast<float4*>(p.sbox) + static_cast<long>(n) * p.A;
+  for (int i = tid; i < K; i += kSelThreads) {
+    const int idx = static_cast<int>(keys[i] & 0xffffffffull);
+    int l, pos, a;
+    locate(p, idx, l, pos, a);
+    const Level lv = p.lv[l];
+    const int h = pos / lv.fw, w = pos % lv.fw;
+    const float lo = p.heads.anchor_lo[l][a], hi = p.heads.anchor_hi[l][a];
+    const float x1 = lo + static_cast<float>(w * lv.stride), y1 = lo + static_cast<float>(h * lv.stride);
+    const float x2 = hi + static_cast<float>(w * lv.stride), y2 = hi + static_cast<float>(h * lv.stride);
+    const float aw = x2 - x1 + 1.f, ah = y2 - y1 + 1.f;
+    const float cx = x1 + 0.5f * (aw - 1.f), cy = y1 + 0.5f * (ah - 1.f);
+    const float d0 = head_bbox(p, n, l, pos, a * 4 + 0), d1 = head_bbox(p, n, l, pos, a * 4 + 1);
+    const float d2 = head_bbox(p, n, l, pos, a * 4 + 2), d3 = head_bbox(p, n, l, pos, a * 4 + 3);
+    const float pcx = d0 * aw + cx, pcy = d1 * ah + cy;
+    // correctly rounded fp32 exp (see oracle/detect.py exp_f32)
+    const float pw = static_cast<float>(exp(static_cast<double>(d2))) * aw;
+    const float ph = static_cast<float>(exp(static_cast<double>(d3))) * ah;
+    sbox[i] = make_float4(pcx - 0.5f * (pw - 1.f), pcy - 0.5f * (ph - 1.f),
+                          pcx + 0.5f * (pw - 1.f), pcy + 0.5f * (ph - 1.f));
+  }
+  if (tid == 0) kept_n_s = 0;
+  __syncthreads();
+
+  int* kept = p.kept + static_cast<long>(n) * p.A;
+  for (int base = 0; base < K; base += 64) {
+    const int m = min(64, K - base);
+    if (tid < 64) chunk_mask[tid] = 0ull;
+    if (tid == 0) alive_s = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+    __syncthreads();
+    const int kept_n = kept_n_s;
+    // A: suppress chunk members overlapping an already kept box
+    for (int t = tid; t < m * kept_n; t += kSelThreads) {
+      const int c = t % m, k = t / m;
+      const float ovr = iou_f(sbox[kept[k]], sbox[base + c]);
+      if (static_cast<double>(ovr) > p.nms_thr) atomicAnd(&alive_s, ~(1ull << c));
+    }
+    // B: pairwise overlaps inside the chunk (a < b)
+    for (int t = tid; t < m * m; t += kSelThreads) {
+      const int a = t / m, b = t % m;
+      if (a < b) {
+        const float ovr = iou_f(sbox[base + a], sbox[base + b]);
+        if (static_cast<double>(ovr) > p.nms_thr) atomicOr(&chunk_mask[a], 1ull << b);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long alive = alive_s;
+      int kn = kept_n;
+      for (int a = 0; a < m; ++a) {
+        if ((alive >> a) & 1ull) {
+          kept[kn++] = base + a;
+          alive &= ~chunk_mask[a];
+        }
+      }
+      kept_n_s = kn;
+    }
+    __syncthreads();
+  }
+
+  // output survivors in score-descending order
+  const int S = kept_n_s;
+  if (tid == 0) { p.out_count[n] = S; p.out_cand[n] = K; }
+  float* out = p.out_det + static_cast<long>(n) * p.max_det * 16;
+  for (int i = tid; i < min(S, p.max_det); i += kSelThreads) {
+    const int pos_sorted = kept[i];
+    const unsigned long long key = keys[pos_sorted];
+    const int idx = static_cast<int>(key & 0xffffffffull);
+    const float score = __uint_as_float(~static_cast<unsigned>(key >> 32));
+    int l, pos, a;
+    locate(p, idx, l, pos, a);
+    const Level lv = p.lv[l];
+    const int h = pos / lv.fw, w = pos % lv.fw;
+    const float lo = p.heads.anchor_lo[l][a], hi = p.heads.anchor_hi[l][a];
+    const float x1 = lo + static_cast<float>(w * lv.stride), y1 = lo + static_cast<float>(h * lv.stride);
+    const float x2 = hi + static_cast<float>(w * lv.stride), y2 = hi + static_cast<float>(h * lv.stride);
+    const float aw = x2 - x1 + 1.f, ah = y2 - y1 + 1.f;
+    const float cx = x1 + 0.5f * (aw - 1.f), cy = y1 + 0.5f * (ah - 1.f);
+    float* o = out + static_cast<long>(i) * 16;
+    const float4 b = sbox[pos_sorted];
+    o[0] = score; o[1] = b.x; o[2] = b.y; o[3] = b.z; o[4] = b.w;
+    for (int q = 0; q < 5; ++q) {
+      o[5 + 2 * q] = head_lmk(p, n, l, pos, a * 10 + 2 * q) * aw + cx;
+      o[6 + 2 * q] = head_lmk(p, n, l, pos, a * 10 + 2 * q + 1) * ah + cy;
+    }
+    o[15] = __int_as_float(idx);
+  }
+}
+
+}  // namespace
+
+size_t detect_workspace_bytes(int N, int H, int W) {
+  int A = 0;
+  for (int s : {32, 16, 8}) A += ceil_div(H, s) * ceil_div(W, s) * 2;
+  int capP = 1;
+  while (capP < A) capP <<= 1;
+  size_t b = 0;
+  b += size_t(N) * capP * 8;        // keys
+  b += size_t(N) * 4;               // counts
+  b += size_t(N) * A * 16;          // sorted boxes
+  b += size_t(N) * A * 4;           // kept
+  return b + 1024;
+}
+
+void detect_post_launch(const DetHeads& heads, int N, int H, int W, float thr, double nms_thr,
+                        int max_det, void* workspace, int* out_count, int* out_cand,
+                        float* out_det, cudaStream_t s) {
+  if (N == 0) return;
+  DetParams p{};
+  p.heads = heads;
+  p.N = N; p.H = H; p.W = W;
+  int off = 0, i = 0;
+  for (int st : {32, 16, 8}) {
+    p.lv[i].stride = st;
+    p.lv[i].fh = ceil_div(H, st);
+    p.lv[i].fw = ceil_div(W, st);
+    p.lv[i].off = off;
+    off += p.lv[i].fh * p.lv[i].fw * 2;
+    ++i;
+  }
+  p.A = off;
+  p.capP = 1;
+  while (p.capP < p.A) p.capP <<= 1;
+  p.thr = thr; p.nms_thr = nms_thr; p.max_det = max_det;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  p.keys = reinterpret_cast<unsigned long long*>(ws); ws += size_t(N) * p.capP * 8;
+  p.sbox = reinterpret_cast<float*>(ws); ws += size_t(N) * p.A * 16;
+  p.kept = reinterpret_cast<int*>(ws); ws += size_t(N) * p.A * 4;
+  p.counts = reinterpret_cast<int*>(ws);
+  p.out_count = out_count; p.out_cand = out_cand; p.out_det = out_det;
+  TR_CUDA(cudaMemsetAsync(p.counts, 0, size_t(N) * 4, s));
+  dim3 grid(ceil_div(p.A, 256), N);
+  det_scan_kernel<<<grid, 256, 0, s>>>(p);
+  TR_CUDA(cudaGetLastError());
+  det_select_kernel<<<N, kSelThreads, 0, s>>>(p);
+  TR_CUDA(cudaGetLastError());
+}
+
+}  // namespace trb

@@ -1,0 +1,43 @@
+// RetinaFace / OpenPose post-processing entry points (host side).
+#pragma once
+#include "common.cuh"
+
+namespace trb {
+
+// Head tensors of the three pyramid levels, index 0 = stride 32, 1 = 16, 2 = 8.
+//  fused == 0: reference layout, NCHW fp32: cls (N,4,h,w) already soft-maxed,
+//              bbox (N,8,h,w), lmk (N,20,h,w).
+//  fused == 1: cls[l] points at an NHWC fp32 tensor of 32 channels
+//              [4 class logits | 8 bbox | 20 landmark]; soft-max done in-kernel.
+struct DetHeads {
+  const float* cls[3];
+  const float* bbox[3];
+  const float* lmk[3];
+  int fused;
+  float anchor_lo[3][2];
+  float anchor_hi[3][2];
+};
+
+size_t detect_workspace_bytes(int N, int H, int W);
+void detect_post_launch(const DetHeads& heads, int N, int H, int W, float thr, double nms_thr,
+                        int max_det, void* workspace, int* out_count, int* out_cand,
+                        float* out_det, cudaStream_t s);
+
+// ---- OpenPose parse
+constexpr int kPeakCap = 512;     // peaks per (frame, part)
+constexpr int kCandCap = 4096;    // accepted pairs per (frame, limb)
+constexpr int kHumanCap = 128;    // humans per frame
+
+struct PoseOut {
+  int* count;        // [N] humans after filtering
+  int* keypoints;    // [N][kHumanCap][18][3] int32 (x, y, present)
+  double* score;     // [N][kHumanCap]
+  int* status;       // [N] overflow bits: 1 peaks, 2 candidates, 4 humans
+};
+
+size_t pose_workspace_bytes(int N);
+void pose_parse_launch(const float* paf, const float* heat, int N, int h, int w, double scale,
+                       void* workspace, const PoseOut& out, cudaStream_t s);
+void bicubic_table_host(float out[32]);
+
+}  // namespace trb

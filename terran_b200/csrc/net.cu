@@ -1,0 +1,522 @@
+// Layer-program executor and the C ABI (include/terran_b200.h).
+//
+// A net is built once from a Python-side description (terran_b200/weights.py);
+// per input shape the executor infers every buffer's dims, allocates the
+// activation buffers, builds the TMA tensor maps / launch geometry of each op
+// (a "plan", cached by (N,H,W)) and then a run is a plain sequence of kernel
+// launches on the caller's stream.
+#include <map>
+#include <memory>
+#include <tuple>
+#include <vector>
+
+#include "../../include/terran_b200.h"
+#include "detect_post.cuh"
+
+namespace trb {
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Buf {
+  void* ptr = nullptr;
+  int N = 0, H = 0, W = 0, C = 0;
+  bool f32 = false;
+  bool alias = false;
+  bool sized = false;
+};
+
+struct PreparedOp {
+  tr_op_desc d;
+  double flops = 0;          // algorithmic (un-padded) flops of this op
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ConvArgs conv;
+  ConvTcPlan* tc = nullptr;
+  StemArgs stem;
+  DwArgs dw;
+  View vin, vout;
+};
+
+struct Plan {
+  std::vector<Buf> bufs;
+  std::vector<PreparedOp> ops;
+  double tc_flops = 0;
+  int tc_launches = 0, launches = 0;
+  int N = 0, H = 0, W = 0;
+  ~Plan() {
+    for (auto& o : ops) {
+      if (o.tc) conv_tc_plan_destroy(o.tc);
+      if (o.e0) cudaEventDestroy(o.e0);
+      if (o.e1) cudaEventDestroy(o.e1);
+    }
+    for (auto& b : bufs)
+      if (b.ptr && !b.alias) cudaFree(b.ptr);
+  }
+};
+
+}  // namespace
+
+}  // namespace trb
+
+using namespace trb;
+
+struct tr_net {
+  std::vector<tr_buffer_desc> buffers;
+  std::vector<tr_op_desc> ops;
+  uint8_t* weights = nullptr;   // device copy of the blob
+  size_t weight_bytes = 0;
+  int force_direct = 0;
+  int profile = 0;
+  std::map<std::tuple<int, int, int, int>, std::unique_ptr<Plan>> plans;
+  Plan* last = nullptr;
+  ~tr_net() {
+    plans.clear();
+    if (weights) cudaFree(weights);
+  }
+};
+
+namespace trb {
+namespace {
+
+template <class T>
+const T* blob_ptr(const tr_net* net, int64_t off) {
+  if (off < 0) return nullptr;
+  TR_CHECK(size_t(off) < net->weight_bytes && off % 16 == 0, "bad blob offset");
+  return reinterpret_cast<const T*>(net->weights + off);
+}
+
+View make_view(const Buf& b, int coff, int C) {
+  View v;
+  v.ptr = static_cast<__half*>(b.ptr);
+  v.N = b.N; v.H = b.H; v.W = b.W; v.cs = b.C; v.coff = coff; v.C = C;
+  return v;
+}
+
+void set_dims(Buf& b, int N, int H, int W, const char* what) {
+  if (b.sized) {
+    TR_CHECK(b.N == N && b.H == H && b.W == W,
+             std::string("buffer written with inconsistent dims by ") + what);
+    return;
+  }
+  b.N = N; b.H = H; b.W = W; b.sized = true;
+}
+
+Plan* build_plan(tr_net* net, int N, int H, int W) {
+  auto plan = std::make_unique<Plan>();
+  plan->N = N; plan->H = H; plan->W = W;
+  plan->bufs.resize(net->buffers.size());
+  for (size_t i = 0; i < net->buffers.size(); ++i) {
+    plan->bufs[i].C = net->buffers[i].channels;
+    plan->bufs[i].f32 = net->buffers[i].is_f32 != 0;
+    TR_CHECK(plan->bufs[i].C % 8 == 0, "buffer channels must be a multiple of 8");
+  }
+  auto& B = plan->bufs;
+  // ---- pass 1: shape inference
+  for (const tr_op_desc& d : net->ops) {
+    int iH, iW, iN;
+    if (d.in < 0) { iN = N; iH = H; iW = W; }
+    else {
+      TR_CHECK(B[d.in].sized, "op reads a buffer no earlier op wrote");
+      iN = B[d.in].N; iH = B[d.in].H; iW = B[d.in].W;
+    }
+    switch (d.type) {
+      case TR_OP_STEM:
+      case TR_OP_CONV:
+      case TR_OP_DWCONV: {
+        const int oH = (iH + 2 * d.pad - d.k) / d.stride + 1, oW = (iW + 2 * d.pad - d.k) / d.stride + 1;
+        TR_CHECK(oH > 0 && oW > 0, "image too small for the network");
+        set_dims(B[d.out], iN, oH, oW, "conv");
+        if (d.out2 >= 0) set_dims(B[d.out2], iN, oH, oW, "conv out2");
+        break;
+      }
+      case TR_OP_MAXPOOL:
+        TR_CHECK(iH >= 2 && iW >= 2, "image too small for the network");
+        set_dims(B[d.out], iN, iH / 2, iW / 2, "maxpool");
+        break;
+      case TR_OP_COPY:
+        set_dims(B[d.out], iN, iH, iW, "copy");
+        break;
+      case TR_OP_VIEW: {
+        TR_CHECK(B[d.out].C == iH * iW * B[d.in].C, "flatten view channel mismatch");
+        set_dims(B[d.out], iN, 1, 1, "view");
+        B[d.out].alias = true;
+        break;
+      }
+      default: fail("unknown op type");
+    }
+  }
+  // ---- pass 2: allocate
+  for (auto& b : B) {
+    if (!b.sized || b.alias) continue;
+    const size_t bytes = size_t(b.N) * b.H * b.W * b.C * (b.f32 ? 4 : 2);
+    TR_CUDA(cudaMalloc(&b.ptr, bytes + 256));
+    // Padding channels (and slices no op writes) must read as zero.
+    TR_CUDA(cudaMemset(b.ptr, 0, bytes + 256));
+  }
+  for (const tr_op_desc& d : net->ops)
+    if (d.type == TR_OP_VIEW) B[d.out].ptr = B[d.in].ptr;
+  // ---- pass 3: prepare launches
+  for (const tr_op_desc& d : net->ops) {
+    PreparedOp po{};
+    po.d = d;
+    switch (d.type) {
+      case TR_OP_STEM: {
+        StemArgs& a = po.stem;
+        a = StemArgs{};
+        a.N = N; a.H = H; a.W = W;
+        a.in_scale = d.in_scale; a.in_shift = d.in_shift;
+        a.out = make_view(B[d.out], d.out_coff, d.out_c);
+        if (d.out2 >= 0) a.out2 = make_view(B[d.out2], d.out2_coff, d.out_c);
+        a.w = blob_ptr<float>(net, d.w_off);
+        a.scale = blob_ptr<float>(net, d.scale_off); a.shift = blob_ptr<float>(net, d.shift_off);
+        a.slope = blob_ptr<float>(net, d.slope_off);
+        a.scale2 = blob_ptr<float>(net, d.scale2_off); a.shift2 = blob_ptr<float>(net, d.shift2_off);
+        a.cout = d.out_c; a.stride = d.stride; a.act = d.act;
+        TR_CHECK(d.k == 3 && d.pad == 1, "stem is 3x3 pad 1");
+        TR_CHECK(!B[d.out].f32, "stem output is fp16");
+        break;
+      }
+      case TR_OP_CONV: {
+        ConvArgs& a = po.conv;
+        a = ConvArgs{};
+        a.in = make_view(B[d.in], d.in_coff, d.in_c);
+        a.out = make_view(B[d.out], d.out_coff, d.out_c);
+        if (B[d.out].f32) a.out_f32 = static_cast<float*>(B[d.out].ptr);
+        if (d.out2 >= 0) a.out2 = make_view(B[d.out2], d.out2_coff, d.out_c);
+        if (d.res >= 0) {
+          a.res = make_view(B[d.res], d.res_coff, d.out_c);
+          a.res_up2 = d.res_up2;
+          if (d.res_up2)
+            TR_CHECK((B[d.out].H + 1) / 2 <= B[d.res].H && (B[d.out].W + 1) / 2 <= B[d.res].W,
+                     "upsampled residual too small");
+          else
+            TR_CHECK(B[d.res].H == B[d.out].H && B[d.res].W == B[d.out].W, "residual dims");
+        }
+        a.w = blob_ptr<__half>(net, d.w_off);
+        a.scale = blob_ptr<float>(net, d.scale_off); a.shift = blob_ptr<float>(net, d.shift_off);
+        a.slope = blob_ptr<float>(net, d.slope_off);
+        a.scale2 = blob_ptr<float>(net, d.scale2_off); a.shift2 = blob_ptr<float>(net, d.shift2_off);
+        a.cout_pad = d.cout_pad; a.cout_store = d.out_c; a.cin_pad = d.in_c;
+        a.kh = a.kw = d.k; a.stride = d.stride; a.pad = d.pad; a.act = d.act;
+        a.H_out = B[d.out].H; a.W_out = B[d.out].W;
+        TR_CHECK(d.in_coff + d.in_c <= B[d.in].C && d.out_coff + d.out_c <= B[d.out].C,
+                 "channel slice out of range");
+        po.flops = 2.0 * B[d.out].N * a.H_out * a.W_out * double(d.cout_real) * d.k * d.k * d.cin_real;
+        const bool use_tc = !net->force_direct && !d.force_direct && conv_tc_eligible(a);
+        if (use_tc) {
+          po.tc = conv_tc_plan_create(a);
+          plan->tc_flops += po.flops;
+          plan->tc_launches++;
+        }
+        break;
+      }
+      case TR_OP_DWCONV: {
+        DwArgs& a = po.dw;
+        a.in = make_view(B[d.in], d.in_coff, d.in_c);
+        a.out = make_view(B[d.out], d.out_coff, d.out_c);
+        a.w = blob_ptr<float>(net, d.w_off);
+        a.scale = blob_ptr<float>(net, d.scale_off); a.shift = blob_ptr<float>(net, d.shift_off);
+        a.stride = d.stride;
+        TR_CHECK(d.k == 3 && d.pad == 1 && d.act == TR_ACT_RELU, "depthwise op is 3x3 pad 1 + ReLU");
+        break;
+      }
+      case TR_OP_MAXPOOL:
+      case TR_OP_COPY:
+        po.vin = make_view(B[d.in], d.in_coff, d.in_c);
+        po.vout = make_view(B[d.out], d.out_coff, d.out_c);
+        break;
+      case TR_OP_VIEW:
+        break;
+    }
+    if (d.type != TR_OP_VIEW) plan->launches++;
+    plan->ops.push_back(po);
+  }
+  Plan* raw = plan.get();
+  if (net->plans.size() >= 4) net->plans.clear();   // bounded cache
+  net->plans[std::make_tuple(N, H, W, net->force_direct)] = std::move(plan);
+  return raw;
+}
+
+void run_plan(Plan* plan, const uint8_t* image, int64_t sn, int64_t sh, int64_t sw, int64_t sc,
+              cudaStream_t s, bool profile) {
+  for (auto& po : plan->ops) {
+    if (profile && po.d.type != TR_OP_VIEW) {
+      if (!po.e0) { TR_CUDA(cudaEventCreate(&po.e0)); TR_CUDA(cudaEventCreate(&po.e1)); }
+      TR_CUDA(cudaEventRecord(po.e0, s));
+    }
+    switch (po.d.type) {
+      case TR_OP_STEM: {
+        StemArgs a = po.stem;
+        a.in = image; a.sn = sn; a.sh = sh; a.sw = sw; a.sc = sc;
+        stem_launch(a, s);
+        break;
+      }
+      case TR_OP_CONV:
+        if (po.tc) conv_tc_launch(po.tc, s);
+        else conv_direct_launch(po.conv, s);
+        break;
+      case TR_OP_DWCONV: dwconv_launch(po.dw, s); break;
+      case TR_OP_MAXPOOL: maxpool2_launch(po.vin, po.vout, s); break;
+      case TR_OP_COPY: copy_slice_launch(po.vin, po.vout, s); break;
+      default: break;
+    }
+    if (profile && po.d.type != TR_OP_VIEW) TR_CUDA(cudaEventRecord(po.e1, s));
+  }
+}
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return 1;
+  }
+}
+
+const float kAnchorLo[3][2] = {{-248.f, -120.f}, {-56.f, -24.f}, {-8.f, 0.f}};
+const float kAnchorHi[3][2] = {{263.f, 135.f}, {71.f, 39.f}, {23.f, 15.f}};
+
+void fill_anchor_refs(DetHeads& h) {
+  for (int l = 0; l < 3; ++l)
+    for (int a = 0; a < 2; ++a) { h.anchor_lo[l][a] = kAnchorLo[l][a]; h.anchor_hi[l][a] = kAnchorHi[l][a]; }
+}
+
+}  // namespace
+}  // namespace trb
+
+extern "C" {
+
+int tr_version(void) { return 100; }
+
+const char* tr_last_error(void) { return g_last_error.c_str(); }
+
+int tr_init(int device) {
+  return guarded([&] {
+    TR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TR_CUDA(cudaGetDeviceProperties(&prop, device));
+    TR_CHECK(prop.major == 10, "terran_b200 needs an sm_100 (Blackwell B200) device, found sm_" +
+                                   std::to_string(prop.major) + std::to_string(prop.minor));
+  });
+}
+
+int tr_net_create(const tr_buffer_desc* buffers, int n_buffers, const tr_op_desc* ops, int n_ops,
+                  const void* weights_host, size_t weight_bytes, tr_net** out) {
+  return guarded([&] {
+    auto net = std::make_unique<tr_net>();
+    net->buffers.assign(buffers, buffers + n_buffers);
+    net->ops.assign(ops, ops + n_ops);
+    for (const auto& d : net->ops) {
+      TR_CHECK(d.out >= 0 && d.out < n_buffers && d.in < n_buffers, "op buffer id out of range");
+      TR_CHECK(d.out2 < n_buffers && d.res < n_buffers, "op buffer id out of range");
+    }
+    net->weight_bytes = weight_bytes;
+    TR_CUDA(cudaMalloc(&net->weights, weight_bytes + 256));
+    TR_CUDA(cudaMemcpy(net->weights, weights_host, weight_bytes, cudaMemcpyHostToDevice));
+    *out = net.release();
+  });
+}
+
+void tr_net_destroy(tr_net* net) { delete net; }
+
+int tr_net_set_mode(tr_net* net, int force_direct) {
+  return guarded([&] { net->force_direct = force_direct ? 1 : 0; });
+}
+
+int tr_net_run(tr_net* net, const uint8_t* image_dev, int N, int H, int W, int64_t stride_n,
+               int64_t stride_h, int64_t stride_w, int64_t stride_c, void* stream) {
+  return guarded([&] {
+    TR_CHECK(N > 0 && H > 0 && W > 0, "empty batch");
+    auto it = net->plans.find(std::make_tuple(N, H, W, net->force_direct));
+    Plan* plan = it != net->plans.end() ? it->second.get() : build_plan(net, N, H, W);
+    net->last = plan;
+    run_plan(plan, image_dev, stride_n, stride_h, stride_w, stride_c,
+             static_cast<cudaStream_t>(stream), net->profile != 0);
+  });
+}
+
+int tr_net_buffer(tr_net* net, int buffer, void** ptr, int* N, int* H, int* W, int* channels) {
+  return guarded([&] {
+    TR_CHECK(net->last, "no run yet");
+    TR_CHECK(buffer >= 0 && size_t(buffer) < net->last->bufs.size(), "buffer id");
+    const Buf& b = net->last->bufs[buffer];
+    *ptr = b.ptr; *N = b.N; *H = b.H; *W = b.W; *channels = b.C;
+  });
+}
+
+int tr_net_export_nchw(tr_net* net, int buffer, int coff, int C, float* out_dev, void* stream) {
+  return guarded([&] {
+    TR_CHECK(net->last, "no run yet");
+    const Buf& b = net->last->bufs.at(buffer);
+    TR_CHECK(!b.f32 && coff + C <= b.C, "export slice");
+    export_nchw_launch(make_view(b, coff, C), C, out_dev, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int tr_net_export_nchw_f32(tr_net* net, int buffer, int coff, int C, float* out_dev,
+                           int softmax_pairs, void* stream) {
+  return guarded([&] {
+    TR_CHECK(net->last, "no run yet");
+    const Buf& b = net->last->bufs.at(buffer);
+    TR_CHECK(b.f32 && coff + C <= b.C, "export slice");
+    TR_CHECK(!softmax_pairs || C == 4, "pair softmax is over the 4 class channels");
+    export_nchw_f32_launch(static_cast<const float*>(b.ptr), b.N, b.H, b.W, b.C, coff, C, out_dev,
+                           softmax_pairs, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int tr_net_stats(tr_net* net, double* tc_flops, int* tc_launches, int* total_launches) {
+  return guarded([&] {
+    TR_CHECK(net->last, "no run yet");
+    *tc_flops = net->last->tc_flops;
+    *tc_launches = net->last->tc_launches;
+    *total_launches = net->last->launches;
+  });
+}
+
+int tr_net_set_profile(tr_net* net, int enable) {
+  return guarded([&] { net->profile = enable ? 1 : 0; });
+}
+
+int tr_net_profile(tr_net* net, float* ms, int32_t* is_tc, double* flops, int cap, int* n_ops) {
+  return guarded([&] {
+    TR_CHECK(net->last, "no run yet");
+    int n = 0;
+    for (auto& po : net->last->ops) {
+      if (po.d.type == TR_OP_VIEW) continue;
+      TR_CHECK(po.e0 && po.e1, "profiling was not enabled for the last run");
+      TR_CUDA(cudaEventSynchronize(po.e1));
+      if (n < cap) {
+        TR_CUDA(cudaEventElapsedTime(ms + n, po.e0, po.e1));
+        is_tc[n] = po.tc ? 1 : 0;
+        flops[n] = po.flops;
+      }
+      ++n;
+    }
+    *n_ops = n;
+  });
+}
+
+int tr_conv2d(const void* in_dev, int N, int H, int W, int in_cs, int in_coff, int cin_pad,
+              const void* w_dev, const float* scale_dev, const float* shift_dev,
+              const float* slope_dev, int cout_pad, int cout_store, int k, int stride, int pad,
+              int act, const void* res_dev, int res_cs, int res_up2, void* out_dev, int out_cs,
+              int out_coff, int out_is_f32, int use_tc, int repeat, float* ms, void* stream) {
+  return guarded([&] {
+    ConvArgs a{};
+    a.in.ptr = static_cast<__half*>(const_cast<void*>(in_dev));
+    a.in.N = N; a.in.H = H; a.in.W = W; a.in.cs = in_cs; a.in.coff = in_coff; a.in.C = cin_pad;
+    a.H_out = (H + 2 * pad - k) / stride + 1;
+    a.W_out = (W + 2 * pad - k) / stride + 1;
+    a.out.ptr = static_cast<__half*>(out_dev);
+    a.out.N = N; a.out.H = a.H_out; a.out.W = a.W_out; a.out.cs = out_cs; a.out.coff = out_coff;
+    a.out.C = cout_store;
+    if (out_is_f32) a.out_f32 = static_cast<float*>(out_dev);
+    if (res_dev) {
+      a.res.ptr = static_cast<__half*>(const_cast<void*>(res_dev));
+      a.res.N = N; a.res.cs = res_cs; a.res.coff = 0; a.res.C = cout_store;
+      a.res.H = res_up2 ? (a.H_out + 1) / 2 : a.H_out;
+      a.res.W = res_up2 ? (a.W_out + 1) / 2 : a.W_out;
+      a.res_up2 = res_up2;
+    }
+    a.w = static_cast<const __half*>(w_dev);
+    a.scale = scale_dev; a.shift = shift_dev; a.slope = slope_dev;
+    a.cout_pad = cout_pad; a.cout_store = cout_store; a.cin_pad = cin_pad;
+    a.kh = a.kw = k; a.stride = stride; a.pad = pad; a.act = act;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ConvTcPlan* plan = nullptr;
+    if (use_tc) plan = conv_tc_plan_create(a);
+    cudaEvent_t e0, e1;
+    TR_CUDA(cudaEventCreate(&e0));
+    TR_CUDA(cudaEventCreate(&e1));
+    auto once = [&] { if (plan) conv_tc_launch(plan, s); else conv_direct_launch(a, s); };
+    once();
+    TR_CUDA(cudaEventRecord(e0, s));
+    for (int i = 0; i < repeat; ++i) once();
+    TR_CUDA(cudaEventRecord(e1, s));
+    cudaError_t err = cudaStreamSynchronize(s);
+    if (plan) conv_tc_plan_destroy(plan);
+    TR_CUDA(err);
+    float t = 0.f;
+    TR_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = repeat > 0 ? t / repeat : 0.f;
+  });
+}
+
+size_t tr_detect_workspace_bytes(int N, int H, int W) { return detect_workspace_bytes(N, H, W); }
+
+int tr_retinaface_decode_nms(const float* const* heads9_dev, int N, int H, int W, float threshold,
+                             double nms_threshold, int max_det, void* workspace_dev,
+                             int32_t* out_count_dev, int32_t* out_candidates_dev,
+                             float* out_det_dev, void* stream) {
+  return guarded([&] {
+    DetHeads h{};
+    for (int l = 0; l < 3; ++l) {
+      h.cls[l] = heads9_dev[3 * l]; h.bbox[l] = heads9_dev[3 * l + 1]; h.lmk[l] = heads9_dev[3 * l + 2];
+    }
+    h.fused = 0;
+    fill_anchor_refs(h);
+    detect_post_launch(h, N, H, W, threshold, nms_threshold, max_det, workspace_dev, out_count_dev,
+                       out_candidates_dev, out_det_dev, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int tr_retinaface_detect(tr_net* net, const int* head_buffers3, float threshold,
+                         double nms_threshold, int max_det, void* workspace_dev,
+                         int32_t* out_count_dev, int32_t* out_candidates_dev, float* out_det_dev,
+                         void* stream) {
+  return guarded([&] {
+    TR_CHECK(net->last, "no run yet");
+    DetHeads h{};
+    int N = 0;
+    for (int l = 0; l < 3; ++l) {
+      const Buf& b = net->last->bufs.at(head_buffers3[l]);
+      TR_CHECK(b.f32 && b.C == 32, "fused head buffers are fp32 with 32 channels");
+      h.cls[l] = static_cast<const float*>(b.ptr);
+      N = b.N;
+    }
+    h.fused = 1;
+    fill_anchor_refs(h);
+    const int H = net->last->H, W = net->last->W;   // image dims of the last run
+    for (int l = 0; l < 3; ++l) {
+      const int st = l == 0 ? 32 : (l == 1 ? 16 : 8);
+      const Buf& b = net->last->bufs.at(head_buffers3[l]);
+      TR_CHECK(b.H == ceil_div(H, st) && b.W == ceil_div(W, st),
+               "head dims do not match ceil(H/stride): " + std::to_string(b.H) + "x" + std::to_string(b.W));
+    }
+    detect_post_launch(h, N, H, W, threshold, nms_threshold, max_det, workspace_dev, out_count_dev,
+                       out_candidates_dev, out_det_dev, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int tr_l2_normalize(const float* in_dev, float* out_dev, int N, int D, void* stream) {
+  return guarded([&] { l2_normalize_launch(in_dev, out_dev, N, D, static_cast<cudaStream_t>(stream)); });
+}
+
+size_t tr_pose_workspace_bytes(int N) { return pose_workspace_bytes(N); }
+
+int tr_openpose_parse(const float* paf_dev, const float* heat_dev, int N, int h, int w, double scale,
+                      void* workspace_dev, int32_t* out_count_dev, int32_t* out_keypoints_dev,
+                      double* out_score_dev, int32_t* out_status_dev, void* stream) {
+  return guarded([&] {
+    PoseOut o{out_count_dev, out_keypoints_dev, out_score_dev, out_status_dev};
+    pose_parse_launch(paf_dev, heat_dev, N, h, w, scale, workspace_dev, o,
+                      static_cast<cudaStream_t>(stream));
+  });
+}
+
+void tr_bicubic_table(float out32[32]) { bicubic_table_host(out32); }
+
+int tr_resize_bilinear_u8(const uint8_t* src_dev, int N, int H, int W, uint8_t* dst_dev, int h,
+                          int w, void* stream) {
+  return guarded([&] {
+    resize_bilinear_u8_launch(src_dev, N, H, W, dst_dev, h, w, static_cast<cudaStream_t>(stream));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+"""RetinaFace (mnet) model class — the plugin the ``Detection`` wrapper calls.
+
+Same protocol as the reference's ``RetinaFace`` class
+(``terran/face/detection/retinaface/wrapper.py:92-238``): ``cls(device=...)``
+and ``call(images, threshold=0.5) -> list[list[dict]]`` with float32 ``bbox``
+(4,), ``landmarks`` (5,2) and ``score``.  The network forward, anchor decode,
+threshold, sort and NMS all run in the native library; one D2H copy per batch
+replaces the reference's three per image.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from terran_b200 import _native as nat
+from terran_b200.checkpoint import get_checkpoint_path
+from terran_b200.defaults import cuda_index, default_device
+from terran_b200.frames import to_device_u8
+from terran_b200.weights import Net, retinaface_program
+
+CLASS_PATH = 'terran_b200.face.detection.retinaface.RetinaFace'
+
+
+def load_state_dict():
+    return torch.load(get_checkpoint_path(CLASS_PATH), map_location='cpu')
+
+
+class RetinaFace:
+
+    def __init__(self, device=default_device, nms_threshold=0.4, state_dict=None):
+        self.device = device
+        self.device_index = cuda_index(device)
+        self.nms_threshold = nms_threshold
+        self.feature_strides = [32, 16, 8]
+        if state_dict is None:
+            state_dict = load_state_dict()
+        program, self.roles = retinaface_program(state_dict)
+        with torch.cuda.device(self.device_index):
+            self.net = Net(program, self.device_index)
+        self._ws = None
+        self.last_candidates = None
+
+    # -- stages, exposed for the parity tests --------------------------------
+    def forward(self, frames):
+        """frames: CUDA uint8 (N,H,W,3) RGB.  Runs the conv stack."""
+        N, H, W, _ = frames.shape
+        # model channel order is BGR: start at channel 2, walk backwards
+        self.net.run(frames, N, H, W, (H * W * 3, W * 3, 3, -1), ptr_offset=2)
+
+    def heads(self, frames):
+        """The reference module's 9 outputs (s32,s16,s8 x prob/bbox/landmark) as
+        NCHW fp32 CUDA tensors — for parity against ``RetinaFace.forward``."""
+        self.forward(frames)
+        out = []
+        for buf in self.roles['heads']:
+            out.append(self.net.export_nchw_f32(buf, 0, 4, softmax_pairs=True))
+            out.append(self.net.export_nchw_f32(buf, 4, 8))
+            out.append(self.net.export_nchw_f32(buf, 12, 20))
+        return out
+
+    def _workspace(self, N, H, W):
+        need = nat.lib().tr_detect_workspace_bytes(N, H, W)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=f'cuda:{self.device_index}')
+        return self._ws
+
+    def detect_device(self, frames, threshold=0.5, max_det=512):
+        """Forward + post-processing, results left on the device.
+        Returns (count (N,), candidates (N,), det (N,max_det,16))."""
+        N, H, W, _ = frames.shape
+        self.forward(frames)
+        dev = frames.device
+        ws = self._workspace(N, H, W)
+        while True:
+            count = torch.empty(N, dtype=torch.int32, device=dev)
+            cand = torch.empty(N, dtype=torch.int32, device=dev)
+            det = torch.empty((N, max_det, 16), dtype=torch.float32, device=dev)
+            heads = (C.c_int * 3)(*self.roles['heads'])
+            nat.check(nat.lib().tr_retinaface_detect(
+                self.net.handle, heads, float(threshold), float(self.nms_threshold), max_det,
+                C.c_void_p(ws.data_ptr()), C.c_void_p(count.data_ptr()),
+                C.c_void_p(cand.data_ptr()), C.c_void_p(det.data_ptr()),
+                nat.current_stream_ptr()))
+            top = int(count.max().item()) if N else 0
+            if top <= max_det:
+                return count, cand, det
+            max_det = top            # rare: more survivors than rows; redo the select
+
+    def call(self, images, threshold=0.5):
+        """Run the detection.  ``images`` is a (N,H,W,3) uint8 RGB array
+        (numpy, or a CUDA tensor to skip the upload)."""
+        with torch.cuda.device(self.device_index):
+            frames = to_device_u8(images, self.device_index)
+            count, cand, det = self.detect_device(frames, threshold)
+            counts = count.cpu().numpy()
+            self.last_candidates = cand.cpu().numpy()
+            top = int(counts.max()) if len(counts) else 0
+            rows = det[:, :max(top, 1)].cpu().numpy()
+        return unpack_detections(counts, rows)
+
+
+def unpack_detections(counts, rows):
+    """(N,) counts + (N,R,16) rows -> the reference's list of lists of dicts."""
+    batch = []
+    for n, k in enumerate(counts):
+        r = rows[n, :k]
+        batch.append([
+            {'bbox': r[i, 1:5].copy(), 'landmarks': r[i, 5:15].reshape(5, 2).copy(),
+             'score': r[i, 0]}
+            for i in range(k)
+        ])
+    return batch
+
+
+def decode_nms(heads, H, W, threshold=0.5, nms_threshold=0.4, max_det=None):
+    """Stage-level entry: the reference's 9 head tensors (torch CUDA fp32 NCHW,
+    class scores already soft-maxed) -> (counts, candidates, rows, indices)."""
+    N = heads[0].shape[0]
+    dev = heads[0].device
+    nat.init(dev.index or 0)
+    heads = [h.contiguous().float() for h in heads]
+    A = sum(int(h.shape[2] * h.shape[3] * 2) for h in heads[::3])
+    max_det = A if max_det is None else max_det
+    ws = torch.empty(nat.lib().tr_detect_workspace_bytes(N, H, W), dtype=torch.uint8, device=dev)
+    count = torch.empty(N, dtype=torch.int32, device=dev)
+    cand = torch.empty(N, dtype=torch.int32, device=dev)
+    det = torch.empty((N, max_det, 16), dtype=torch.float32, device=dev)
+    ptrs = (C.c_void_p * 9)(*[h.data_ptr() for h in heads])
+    nat.check(nat.lib().tr_retinaface_decode_nms(
+        ptrs, N, H, W, float(threshold), float(nms_threshold), max_det,
+        C.c_void_p(ws.data_ptr()), C.c_void_p(count.data_ptr()), C.c_void_p(cand.data_ptr()),
+        C.c_void_p(det.data_ptr()), nat.current_stream_ptr()))
+    counts = count.cpu().numpy()
+    rows = det.cpu().numpy()
+    idx = rows[..., 15].copy().view(np.int32)
+    return counts, cand.cpu().numpy(), rows, idx

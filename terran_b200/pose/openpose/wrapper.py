@@ -1,0 +1,101 @@
+"""OpenPose (2017 body model) — the plugin ``Estimation`` calls.
+
+Same protocol as the reference's ``OpenPose`` class
+(``terran/pose/openpose/wrapper.py:166-485``): ``cls(device=..., short_side=184)``
+and ``call(images (N,H,W,3) uint8) -> list[list[{'keypoints': int32 (18,3),
+'score': float64}]]``.  Resize, VGG/PAF forward, the x8 bicubic up-sampling,
+peak extraction, PAF line integrals, greedy limb matching and human assembly
+all run in the native library; one D2H copy of the assembled humans per batch
+replaces the reference's per-candidate ``.cpu()`` calls.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from terran_b200 import _native as nat
+from terran_b200.checkpoint import get_checkpoint_path
+from terran_b200.defaults import cuda_index, default_device
+from terran_b200.frames import resize_short_side, to_device_u8
+from terran_b200.weights import Net, openpose_program
+
+CLASS_PATH = 'terran_b200.pose.openpose.OpenPose'
+
+
+def parse_device(paf, heat, scale, workspace=None):
+    """Stage-level entry: network maps (CUDA fp32 NCHW, paf (N,38,h,w), heat
+    (N,19,h,w)) -> (count, keypoints, score, status) CUDA tensors."""
+    N, _, h, w = paf.shape
+    dev = paf.device
+    nat.init(dev.index or 0)
+    paf, heat = paf.contiguous().float(), heat.contiguous().float()
+    need = nat.lib().tr_pose_workspace_bytes(N)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    count = torch.empty(N, dtype=torch.int32, device=dev)
+    kps = torch.empty((N, nat.TR_HUMAN_CAP, 18, 3), dtype=torch.int32, device=dev)
+    score = torch.empty((N, nat.TR_HUMAN_CAP), dtype=torch.float64, device=dev)
+    status = torch.empty(N, dtype=torch.int32, device=dev)
+    nat.check(nat.lib().tr_openpose_parse(
+        C.c_void_p(paf.data_ptr()), C.c_void_p(heat.data_ptr()), N, h, w, float(scale),
+        C.c_void_p(workspace.data_ptr()), C.c_void_p(count.data_ptr()), C.c_void_p(kps.data_ptr()),
+        C.c_void_p(score.data_ptr()), C.c_void_p(status.data_ptr()), nat.current_stream_ptr()))
+    return count, kps, score, status, workspace
+
+
+def unpack_poses(count, kps, score, status):
+    count, status = count.cpu().numpy(), status.cpu().numpy()
+    if status.any():
+        bad = int(np.flatnonzero(status)[0])
+        raise nat.NativeError(
+            f'pose parse capacity exceeded on frame {bad} (status {int(status[bad])}: '
+            f'1 = more than {nat.TR_PEAK_CAP} peaks of one part, 2 = more than '
+            f'{nat.TR_CAND_CAP} limb candidates, 4 = more than {nat.TR_HUMAN_CAP} humans)')
+    top = int(count.max()) if len(count) else 0
+    kps = kps[:, :max(top, 1)].cpu().numpy()
+    score = score[:, :max(top, 1)].cpu().numpy()
+    return [
+        [{'keypoints': kps[n, i].copy(), 'score': score[n, i]} for i in range(k)]
+        for n, k in enumerate(count)
+    ]
+
+
+class OpenPose:
+
+    def __init__(self, device=default_device, short_side=184, state_dict=None):
+        self.device = device
+        self.device_index = cuda_index(device)
+        self.short_side = short_side
+        self.downsampling_ratio = 8
+        self.keypoint_threshold = 0.1
+        self.thresh_2 = 0.05
+        self.human_threshold = 0.4
+        if state_dict is None:
+            state_dict = torch.load(get_checkpoint_path(CLASS_PATH), map_location='cpu')
+        program, self.roles = openpose_program(state_dict)
+        with torch.cuda.device(self.device_index):
+            self.net = Net(program, self.device_index)
+        self._ws = None
+
+    # -- device stages --------------------------------------------------------
+    def maps(self, resized):
+        """resized: CUDA uint8 (N,h,w,3) RGB at network resolution.  Returns the
+        reference module's outputs (paf (N,38,h/8,w/8), heat (N,19,...)) fp32."""
+        N, H, W, _ = resized.shape
+        self.net.run(resized, N, H, W, (H * W * 3, W * 3, 3, 1))
+        r = self.roles
+        return (self.net.export_nchw(r['maps'], r['paf_coff'], 38),
+                self.net.export_nchw(r['maps'], r['heat_coff'], 19))
+
+    def estimate_device(self, frames):
+        resized, scale = resize_short_side(frames, self.short_side)
+        paf, heat = self.maps(resized)
+        count, kps, score, status, self._ws = parse_device(paf, heat, scale, self._ws)
+        return count, kps, score, status
+
+    def call(self, images):
+        """Pose estimation on a (N,H,W,3) uint8 RGB batch (numpy or CUDA tensor)."""
+        with torch.cuda.device(self.device_index):
+            frames = to_device_u8(images, self.device_index)
+            out = self.estimate_device(frames)
+            return unpack_poses(*out)

@@ -1,0 +1,427 @@
+"""Weight ingestion: reference ``state_dict`` -> layer program + packed blob.
+
+Reads the checkpoint key layout of the reference models (SURVEY.md Appendix C;
+``retinaface/model.py``, ``arcface/model.py``, ``openpose/model.py``), folds
+every BatchNorm that FOLLOWS a convolution into an fp32 per-channel
+scale/shift applied in the kernel epilogue, repacks filters to the
+``[cout][kh][kw][cin]`` fp16 layout the tcgen05 kernel's TMA descriptors
+expect, and emits the op list the native executor (``csrc/net.cu``) runs.
+
+A BatchNorm that PRECEDES a zero-padded convolution (ArcFace ``Unit.body[0]``,
+and the ``(x-127.5)*0.0078125`` input affine) cannot be folded into that
+convolution — padding is applied after the affine — so it is applied by the
+producer instead: the previous convolution's epilogue emits a second,
+normalised tensor (``out2``), and the u8 stem kernels apply the input affine to
+in-bounds taps only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .synth import ARCFACE_CHANNELS, ARCFACE_UNITS, OPENPOSE_TRUNK, RETINAFACE_SCALES, \
+    openpose_stage_layers
+
+
+def _r(x, m):
+    return (x + m - 1) // m * m
+
+
+class Program:
+    """Builder for the (buffers, ops, blob) triple ``tr_net_create`` takes."""
+
+    def __init__(self):
+        self.blob = bytearray()
+        self.buffers = []
+        self.ops = []
+
+    # -- blob
+    def add(self, arr, dtype):
+        arr = np.ascontiguousarray(np.asarray(arr, dtype=dtype))
+        pad = (-len(self.blob)) % 16
+        self.blob += b'\0' * pad
+        off = len(self.blob)
+        self.blob += arr.tobytes()
+        return off
+
+    def add_vec(self, t, n_pad):
+        if t is None:
+            return -1
+        v = np.zeros(n_pad, np.float32)
+        t = np.asarray(t, np.float32)
+        v[:len(t)] = t
+        return self.add(v, np.float32)
+
+    # -- buffers
+    def buffer(self, channels, f32=False):
+        self.buffers.append((int(channels), int(f32)))
+        return len(self.buffers) - 1
+
+    # -- ops
+    def _op(self, **kw):
+        d = dict(type=0, in_=-1, in_coff=0, in_c=0, out=-1, out_coff=0, out_c=0, out2=-1,
+                 out2_coff=0, res=-1, res_coff=0, res_up2=0, k=1, stride=1, pad=0, act=0,
+                 cout_pad=0, cin_real=0, cout_real=0, force_direct=0, w_off=-1, scale_off=-1, shift_off=-1, slope_off=-1,
+                 scale2_off=-1, shift2_off=-1, in_scale=1.0, in_shift=0.0)
+        d.update(kw)
+        self.ops.append(nat.OpDesc(**d))
+
+    def conv(self, w, scale, shift, in_, out, *, in_coff=0, in_map=None, cin_pad=None,
+             out_coff=0, k=None, stride=1, pad=None, act=nat.TR_ACT_NONE, slope=None,
+             res=-1, res_coff=0, res_up2=0, out2=-1, scale2=None, shift2=None,
+             force_direct=0):
+        """w: (cout, cin, k, k) fp32 tensor.  ``in_map[c]`` is the position of
+        reference input channel c inside the (padded) input view."""
+        w = w.detach().float().numpy()
+        cout, cin, kh, kw_ = w.shape
+        k = kh if k is None else k
+        pad = k // 2 if pad is None else pad
+        if cin_pad is None:
+            cin_pad = _r(cin, 8) if cin <= 8 else _r(cin, 16)
+        in_map = np.arange(cin) if in_map is None else np.asarray(in_map)
+        cout_pad = _r(cout, 16)
+        packed = np.zeros((cout_pad, kh, kw_, cin_pad), np.float16)
+        packed[:cout, :, :, in_map] = w.transpose(0, 2, 3, 1).astype(np.float16)
+        self._op(type=nat.TR_OP_CONV, in_=in_, in_coff=in_coff, in_c=cin_pad, out=out,
+                 out_coff=out_coff, out_c=_r(cout, 8), out2=out2, res=res, res_coff=res_coff,
+                 res_up2=res_up2, k=k, stride=stride, pad=pad, act=act, cout_pad=cout_pad,
+                 cin_real=cin, cout_real=cout, force_direct=force_direct,
+                 w_off=self.add(packed, np.float16),
+                 scale_off=self.add_vec(scale, cout_pad), shift_off=self.add_vec(shift, cout_pad),
+                 slope_off=self.add_vec(slope, cout_pad),
+                 scale2_off=self.add_vec(scale2, cout_pad), shift2_off=self.add_vec(shift2, cout_pad))
+
+    def stem(self, w, scale, shift, out, *, stride, act, slope=None, in_scale=1.0, in_shift=0.0,
+             out2=-1, scale2=None, shift2=None):
+        w = w.detach().float().numpy()            # (cout, 3, 3, 3) -> [cout][kh][kw][c]
+        cout = w.shape[0]
+        self._op(type=nat.TR_OP_STEM, out=out, out_c=cout, out2=out2, k=3, stride=stride, pad=1,
+                 act=act, cout_pad=cout, in_scale=in_scale, in_shift=in_shift,
+                 w_off=self.add(w.transpose(0, 2, 3, 1), np.float32),
+                 scale_off=self.add_vec(scale, cout), shift_off=self.add_vec(shift, cout),
+                 slope_off=self.add_vec(slope, cout),
+                 scale2_off=self.add_vec(scale2, cout), shift2_off=self.add_vec(shift2, cout))
+
+    def dwconv(self, w, scale, shift, in_, out, *, stride):
+        w = w.detach().float().numpy()            # (C, 1, 3, 3) -> [kh][kw][C]
+        c = w.shape[0]
+        self._op(type=nat.TR_OP_DWCONV, in_=in_, in_c=c, out=out, out_c=c, k=3, stride=stride,
+                 pad=1, act=nat.TR_ACT_RELU, cout_pad=c,
+                 w_off=self.add(w[:, 0].transpose(1, 2, 0), np.float32),
+                 scale_off=self.add_vec(scale, c), shift_off=self.add_vec(shift, c))
+
+    def maxpool(self, in_, out, channels):
+        self._op(type=nat.TR_OP_MAXPOOL, in_=in_, in_c=channels, out=out, out_c=channels, k=2,
+                 stride=2)
+
+    def copy(self, in_, in_coff, out, out_coff, channels):
+        self._op(type=nat.TR_OP_COPY, in_=in_, in_coff=in_coff, in_c=channels, out=out,
+                 out_coff=out_coff, out_c=channels)
+
+    def view(self, in_, out):
+        self._op(type=nat.TR_OP_VIEW, in_=in_, out=out)
+
+
+def bn_fold(sd, prefix, eps, conv_bias=None):
+    """(scale, shift) of BN(conv + bias) as an affine of the conv output."""
+    g, b = sd[prefix + '.weight'].double(), sd[prefix + '.bias'].double()
+    m, v = sd[prefix + '.running_mean'].double(), sd[prefix + '.running_var'].double()
+    scale = g / torch.sqrt(v + eps)
+    bias = conv_bias.double() if conv_bias is not None else 0.0
+    shift = b + (bias - m) * scale
+    return scale.float().numpy(), shift.float().numpy()
+
+
+# ------------------------------------------------------------------ RetinaFace
+
+def retinaface_program(sd):
+    """Program + roles for reference ``RetinaFace`` (retinaface/model.py:319-341).
+    The stem reads the frame in MODEL channel order (BGR); callers with RGB
+    memory pass a pointer to channel 2 and a channel stride of -1."""
+    P = Program()
+    relu = nat.TR_ACT_RELU
+
+    def cbr(pc, pb, in_, out, eps, **kw):
+        s, t = bn_fold(sd, pb, eps, sd.get(pc + '.bias'))
+        P.conv(sd[pc + '.weight'], s, t, in_, out, act=relu, **kw)
+
+    b = P.buffer(8)
+    s, t = bn_fold(sd, 'base.first_conv_block.1', 1e-5)
+    P.stem(sd['base.first_conv_block.0.weight'], s, t, b, stride=2, act=relu)
+    x = P.buffer(8)
+    s, t = bn_fold(sd, 'base.first_conv_block.4', 1e-5)
+    P.dwconv(sd['base.first_conv_block.3.weight'], s, t, b, x, stride=1)
+
+    def sep_block(prefix, x, cout, stride):
+        conv = P.buffer(cout)
+        cbr(prefix + '.conv_block.0', prefix + '.conv_block.1', x, conv, 1e-5)
+        sep = P.buffer(cout)
+        s, t = bn_fold(sd, prefix + '.sep_block.1', 1e-5)
+        P.dwconv(sd[prefix + '.sep_block.0.weight'], s, t, conv, sep, stride=stride)
+        return conv, sep
+
+    taps = []
+    for si, blocks in enumerate(RETINAFACE_SCALES):
+        for bi, (_cin, cout, stride) in enumerate(blocks):
+            conv, x = sep_block(f'base.scales.{si}.{bi}', x, cout, stride)
+        taps.append(conv)
+    _, x = sep_block('base.final_conv.0', x, 256, 1)
+    c32 = P.buffer(256)
+    cbr('base.final_conv.1', 'base.final_conv.2', x, c32, 1e-5)
+    c8, c16 = taps
+
+    e = 2e-5
+    p32 = P.buffer(64)
+    cbr('refiner.conv_stride32.0', 'refiner.conv_stride32.1', c32, p32, e)
+    p16 = P.buffer(64)
+    cbr('refiner.conv_stride16.0', 'refiner.conv_stride16.1', c16, p16, e, res=p32, res_up2=1)
+    a16 = P.buffer(64)
+    cbr('refiner.aggr_stride16.0', 'refiner.aggr_stride16.1', p16, a16, e)
+    p8 = P.buffer(64)
+    cbr('refiner.conv_stride8.0', 'refiner.conv_stride8.1', c8, p8, e, res=a16, res_up2=1)
+    a8 = P.buffer(64)
+    cbr('refiner.aggr_stride8.0', 'refiner.aggr_stride8.1', p8, a8, e)
+
+    heads, ctxs = {}, {}
+    for stride, feat in ((8, a8), (16, a16), (32, p32)):
+        p = f'refiner.context_stride{stride}'
+        ctx = P.buffer(64)
+        red = P.buffer(16)
+        tmp = P.buffer(16)
+        cbr(p + '.context_3x3.0', p + '.context_3x3.1', feat, ctx, e, out_coff=0)
+        cbr(p + '.dimension_reducer.0', p + '.dimension_reducer.1', feat, red, e)
+        cbr(p + '.context_5x5.0', p + '.context_5x5.1', red, ctx, e, out_coff=32)
+        cbr(p + '.context_7x7.0', p + '.context_7x7.1', red, tmp, e)
+        cbr(p + '.context_7x7.3', p + '.context_7x7.4', tmp, ctx, e, out_coff=48)
+        # fused head: [4 class logits | 8 bbox | 20 landmark] -> fp32
+        w = torch.cat([sd[f'outputs.cls_stride{stride}.weight'],
+                       sd[f'outputs.bbox_stride{stride}.weight'],
+                       sd[f'outputs.landmark_stride{stride}.weight']], 0)
+        bias = torch.cat([sd[f'outputs.cls_stride{stride}.bias'],
+                          sd[f'outputs.bbox_stride{stride}.bias'],
+                          sd[f'outputs.landmark_stride{stride}.bias']], 0)
+        head = P.buffer(32, f32=True)
+        P.conv(w, np.ones(32, np.float32), bias.float().numpy(), ctx, head)
+        heads[stride] = head
+        ctxs[stride] = ctx
+    roles = {'heads': [heads[32], heads[16], heads[8]], 'context': ctxs}
+    return P, roles
+
+
+# --------------------------------------------------------------------- ArcFace
+
+def arcface_program(sd, units=ARCFACE_UNITS):
+    """Program for reference ``FaceResNet100`` (arcface/model.py:38-97).  Input
+    in model channel order (BGR)."""
+    P = Program()
+    e = 2e-5
+
+    def pre_affine(prefix):
+        """BN applied to a tensor before a padded conv, as (scale, shift)."""
+        return bn_fold(sd, prefix, e)
+
+    C0 = ARCFACE_CHANNELS[0]
+    x = P.buffer(C0)
+    xn = P.buffer(C0)
+    s, t = bn_fold(sd, 'initial_layer.1', e)
+    s2, t2 = pre_affine('stages.0.0.body.0')
+    P.stem(sd['initial_layer.0.weight'], s, t, x, stride=1, act=nat.TR_ACT_PRELU,
+           slope=sd['initial_layer.2.weight'].float().numpy(),
+           in_scale=0.0078125, in_shift=-127.5 * 0.0078125, out2=xn, scale2=s2, shift2=t2)
+
+    n_stages = len(units)
+    for si, n_units in enumerate(units):
+        cout = ARCFACE_CHANNELS[si + 1]
+        y_full = P.buffer(cout)      # conv1 output of the strided first unit (full res)
+        y = P.buffer(cout)
+        sc = P.buffer(cout)
+        xs = [P.buffer(cout), P.buffer(cout)]
+        xns = [P.buffer(cout), P.buffer(cout)]
+        for u in range(n_units):
+            p = f'stages.{si}.{u}'
+            stride = 2 if u == 0 else 1
+            s, t = bn_fold(sd, p + '.body.2', e)
+            yb = y_full if u == 0 else y
+            P.conv(sd[p + '.body.1.weight'], s, t, xn, yb, act=nat.TR_ACT_PRELU,
+                   slope=sd[p + '.body.3.weight'].float().numpy())
+            if u == 0:
+                s, t = bn_fold(sd, p + '.shortcut.1', e)
+                P.conv(sd[p + '.shortcut.0.weight'], s, t, x, sc, stride=2)
+                res = sc
+            else:
+                res = x
+            last = (si == n_stages - 1 and u == n_units - 1)
+            x_new, xn_new = xs[u & 1], xns[u & 1]
+            s, t = bn_fold(sd, p + '.body.5', e)
+            if last:
+                P.conv(sd[p + '.body.4.weight'], s, t, yb, x_new, stride=stride, res=res)
+            else:
+                nxt = f'stages.{si}.{u + 1}' if u + 1 < n_units else f'stages.{si + 1}.0'
+                s2, t2 = pre_affine(nxt + '.body.0')
+                P.conv(sd[p + '.body.4.weight'], s, t, yb, x_new, stride=stride, res=res,
+                       out2=xn_new, scale2=s2, shift2=t2)
+            x, xn = x_new, xn_new
+
+    # final_layer: BN2d (no padding follows -> folded into the FC exactly),
+    # Flatten in (C,H,W) order -> permuted to our (H,W,C), Linear, BN1d.
+    Cl = ARCFACE_CHANNELS[len(units)]
+    s0, t0 = (v.astype(np.float64) for v in bn_fold(sd, 'final_layer.0', e))
+    W = sd['final_layer.3.weight'].double().numpy()
+    hw = W.shape[1] // Cl
+    side = int(round(hw ** 0.5))
+    W = W.reshape(512, Cl, side, side)
+    bias = sd['final_layer.3.bias'].double().numpy() + (W * t0[None, :, None, None]).sum((1, 2, 3))
+    Wf = (W * s0[None, :, None, None]).transpose(0, 2, 3, 1).reshape(512, hw * Cl, 1, 1)
+    g = sd['final_layer.4.weight'].double().numpy()
+    b = sd['final_layer.4.bias'].double().numpy()
+    m = sd['final_layer.4.running_mean'].double().numpy()
+    v = sd['final_layer.4.running_var'].double().numpy()
+    scale = g / np.sqrt(v + e)
+    shift = b + (bias - m) * scale
+    flat = P.buffer(hw * Cl)
+    P.view(x, flat)
+    emb = P.buffer(512, f32=True)
+    P.conv(torch.from_numpy(Wf.astype(np.float32)), scale.astype(np.float32),
+           shift.astype(np.float32), flat, emb, k=1, pad=0)
+    return P, {'embedding': emb}
+
+
+# -------------------------------------------------------------------- OpenPose
+
+#: position of reference concat channel c (cat[PAF 38, heat 19, trunk 128]) in
+#: the padded 192-channel buffer [PAF 0..37 | pad | heat 40..58 | pad | trunk 64..191]
+OPENPOSE_CAT_MAP = np.concatenate([np.arange(38), 40 + np.arange(19), 64 + np.arange(128)])
+
+
+def openpose_program(sd):
+    """Program for reference ``BodyPoseModel`` (openpose/model.py:27-141).  The
+    frame is read as stored (RGB, no flip: wrapper.py:116-122)."""
+    P = Program()
+    relu = nat.TR_ACT_RELU
+
+    def one(cout):
+        return np.ones(cout, np.float32)
+
+    cat = [P.buffer(192), P.buffer(192)]
+    x = None
+    ch = 3
+    items = list(OPENPOSE_TRUNK)
+    for i, item in enumerate(items):
+        if item == 'P':
+            y = P.buffer(ch)
+            P.maxpool(x, y, ch)
+            x = y
+            continue
+        name, cin, cout, _k = item
+        w, b = sd[f'model0.{name}.weight'], sd[f'model0.{name}.bias'].float().numpy()
+        if cin == 3:
+            y = P.buffer(cout)
+            # reference: x.astype(f32) / 255.0 - 0.5 (wrapper.py:116-122)
+            P.stem(w, one(cout), b, y, stride=1, act=relu, in_scale=1.0 / 255.0, in_shift=-0.5)
+        elif i == len(items) - 1:
+            P.conv(w, one(cout), b, x, cat[0], out_coff=64, act=relu)
+            P.copy(cat[0], 64, cat[1], 64, 128)
+            y = None
+        else:
+            y = P.buffer(cout)
+            P.conv(w, one(cout), b, x, y, act=relu)
+        x, ch = y, cout
+
+    for stage in range(1, 7):
+        src = cat[0] if stage == 1 else cat[stage % 2]
+        dst = cat[0] if stage == 1 else cat[(stage + 1) % 2]
+        for branch in (1, 2):
+            layers = openpose_stage_layers(stage, branch)
+            x = src
+            tmp = [P.buffer(128), P.buffer(128)]
+            for li, (name, cin, cout, k, has_relu) in enumerate(layers):
+                pfx = f'model{stage}_{branch}.{name}'
+                w, b = sd[pfx + '.weight'], sd[pfx + '.bias'].float().numpy()
+                act = relu if has_relu else nat.TR_ACT_NONE
+                kw = {}
+                if li == 0:
+                    if stage == 1:
+                        kw = dict(in_coff=64)
+                    else:
+                        kw = dict(in_map=OPENPOSE_CAT_MAP, cin_pad=192)
+                if li == len(layers) - 1:
+                    P.conv(w, one(cout), b, x, dst, out_coff=0 if branch == 1 else 40, act=act, **kw)
+                else:
+                    y = P.buffer(cout) if cout != 128 else tmp[li & 1]
+                    P.conv(w, one(cout), b, x, y, act=act, **kw)
+                    x = y
+    return P, {'maps': cat[(6 + 1) % 2], 'paf_coff': 0, 'heat_coff': 40}
+
+
+# ----------------------------------------------------------------------- Net
+
+class Net:
+    """A compiled layer program living on one CUDA device."""
+
+    def __init__(self, program, device_index=0):
+        nat.init(device_index)
+        self.program = program
+        bufs = (nat.BufferDesc * len(program.buffers))(*[
+            nat.BufferDesc(c, f) for c, f in program.buffers])
+        ops = (nat.OpDesc * len(program.ops))(*program.ops)
+        blob = bytes(program.blob)
+        handle = C.c_void_p()
+        nat.check(nat.lib().tr_net_create(bufs, len(program.buffers), ops, len(program.ops),
+                                          blob, len(blob), C.byref(handle)))
+        self.handle = handle
+        self.weight_bytes = len(blob)
+
+    def __del__(self):
+        h, self.handle = getattr(self, 'handle', None), None
+        if h:
+            try:
+                nat.lib().tr_net_destroy(h)
+            except Exception:
+                pass
+
+    def set_force_direct(self, flag):
+        nat.check(nat.lib().tr_net_set_mode(self.handle, int(bool(flag))))
+
+    def run(self, image, N, H, W, strides, ptr_offset=0):
+        """image: torch uint8 CUDA tensor; strides = element strides (n,h,w,c)."""
+        sn, sh, sw, sc = (int(v) for v in strides)
+        nat.check(nat.lib().tr_net_run(self.handle, C.c_void_p(image.data_ptr() + ptr_offset),
+                                       N, H, W, sn, sh, sw, sc, nat.current_stream_ptr()))
+
+    def buffer_info(self, buf):
+        ptr = C.c_void_p()
+        n, h, w, c = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        nat.check(nat.lib().tr_net_buffer(self.handle, buf, C.byref(ptr), C.byref(n), C.byref(h),
+                                          C.byref(w), C.byref(c)))
+        return ptr.value, n.value, h.value, w.value, c.value
+
+    def export_nchw(self, buf, coff, channels):
+        _, n, h, w, _ = self.buffer_info(buf)
+        out = torch.empty((n, channels, h, w), dtype=torch.float32, device='cuda')
+        nat.check(nat.lib().tr_net_export_nchw(self.handle, buf, coff, channels,
+                                               C.c_void_p(out.data_ptr()), nat.current_stream_ptr()))
+        return out
+
+    def export_nchw_f32(self, buf, coff, channels, softmax_pairs=False):
+        _, n, h, w, _ = self.buffer_info(buf)
+        out = torch.empty((n, channels, h, w), dtype=torch.float32, device='cuda')
+        nat.check(nat.lib().tr_net_export_nchw_f32(
+            self.handle, buf, coff, channels, C.c_void_p(out.data_ptr()), int(softmax_pairs),
+            nat.current_stream_ptr()))
+        return out
+
+    def set_profile(self, flag):
+        nat.check(nat.lib().tr_net_set_profile(self.handle, int(bool(flag))))
+
+    def profile(self):
+        """Per-op (ms, is_tc, algorithmic flops) of the last profiled run."""
+        cap = len(self.program.ops)
+        ms, tc, fl, n = (C.c_float * cap)(), (C.c_int32 * cap)(), (C.c_double * cap)(), C.c_int()
+        nat.check(nat.lib().tr_net_profile(self.handle, ms, tc, fl, cap, C.byref(n)))
+        return [(ms[i], bool(tc[i]), fl[i]) for i in range(n.value)]
+
+    def stats(self):
+        fl, tc, tot = C.c_double(), C.c_int(), C.c_int()
+        nat.check(nat.lib().tr_net_stats(self.handle, C.byref(fl), C.byref(tc), C.byref(tot)))
+        return {'tc_flops': fl.value, 'tc_launches': tc.value, 'launches': tot.value}

@@ -1,0 +1,191 @@
+"""GPU: the three conv stacks and the public wrappers against the fp32 oracle
+(oracle/nets.py == the reference nn.Modules, see tests/test_oracle_golden.py).
+
+Stated tolerances (fp16 activations/weights, fp32 accumulation; SURVEY.md
+section 8(d)): RetinaFace class probabilities |d| <= 5e-3 away from saturation
+(the synthetic class head has a x30 gain, so logits are compared at 0.25),
+bbox/landmark deltas <= 4e-3; ArcFace normalised embedding cosine >= 0.9999 and
+max |d| <= 5e-3; OpenPose maps <= 4e-3.  Integer outputs are compared at stage
+level (tests/test_gpu_post.py); end to end they are compared as sets."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import detect, nets, pose
+from terran_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def retina():
+    from terran_b200.face.detection.retinaface import RetinaFace
+    sd = synth.retinaface_state_dict()
+    return RetinaFace(device=torch.device('cuda'), state_dict=sd), sd
+
+
+@pytest.fixture(scope='module')
+def arc():
+    from terran_b200.face.recognition.arcface import ArcFace
+    sd = synth.arcface_state_dict()
+    return ArcFace(device=torch.device('cuda'), state_dict=sd), sd
+
+
+@pytest.fixture(scope='module')
+def opose():
+    from terran_b200.pose.openpose import OpenPose
+    sd = synth.openpose_state_dict()
+    return OpenPose(device=torch.device('cuda'), state_dict=sd), sd
+
+
+def oracle_heads(sd, frames):
+    x = torch.from_numpy(frames.astype(np.float32)).permute(0, 3, 1, 2).flip(1)
+    return [h.numpy() for h in nets.retinaface_forward(sd, x)]
+
+
+def logit(p):
+    p = np.clip(p.astype(np.float64), 1e-7, 1 - 1e-7)
+    return np.log(p / (1 - p))
+
+
+@pytest.mark.parametrize('mode', ['direct', 'tcgen05'])
+@pytest.mark.parametrize('shape', [(2, 75, 109), (1, 416, 416)])
+def test_retinaface_heads(native, retina, shape, mode):
+    model, sd = retina
+    model.net.set_force_direct(mode == 'direct')
+    try:
+        N, H, W = shape
+        frames = np.random.default_rng(11).integers(0, 256, (N, H, W, 3), dtype=np.uint8)
+        got = [t.cpu().numpy() for t in model.heads(torch.from_numpy(frames).cuda())]
+        want = oracle_heads(sd, frames)
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert a.shape == b.shape, (i, a.shape, b.shape)
+            if i % 3 == 0:
+                assert np.abs(logit(a) - logit(b)).max() < 0.25, (i, np.abs(logit(a) - logit(b)).max())
+            else:
+                assert np.abs(a - b).max() < 4e-3, (i, np.abs(a - b).max())
+    finally:
+        model.net.set_force_direct(False)
+
+
+def match_fraction(got, want):
+    """Fraction of reference detections with an identical-anchor detection."""
+    if not want:
+        return 1.0
+    keys = {tuple(np.round(f['bbox']).astype(int)) for f in got}
+    hit = sum(tuple(np.round(f['bbox']).astype(int)) in keys for f in want)
+    return hit / len(want)
+
+
+def test_retinaface_call_end_to_end(native, retina, golden):
+    """RetinaFace.call on the frames the reference itself processed (fixture)."""
+    model, sd = retina
+    g = golden('retinaface_call.npz')
+    out = model.call(g['images'])
+    assert len(out) == 3
+    for n, faces in enumerate(out):
+        ref = [{'bbox': b} for b in g[f'bbox{n}']]
+        assert match_fraction(faces, ref) >= 0.8, (n, len(faces), len(ref))
+        assert abs(len(faces) - len(ref)) <= max(3, len(ref) // 5)
+        assert faces[0]['bbox'].dtype == np.float32 and faces[0]['landmarks'].shape == (5, 2)
+
+
+def test_detection_wrapper(native, retina, golden):
+    """Detection()(640x640 image): BASELINE config 1 through the public API."""
+    from terran_b200.face.detection import Detection
+    model, sd = retina
+    det = Detection(device=torch.device('cuda'), lazy=True)
+    det.model = model
+    img = np.random.default_rng(0).integers(0, 256, (640, 640, 3), dtype=np.uint8)
+    g = golden('retinaface_detection_640.npz')
+    faces = det(img)
+    ref = [{'bbox': b} for b in g['bbox']]
+    assert match_fraction(faces, ref) >= 0.8
+    assert faces[0]['bbox'].dtype == np.int32 and faces[0]['landmarks'].dtype == np.int32
+    # device resize and host cv2 resize give the same answer
+    det.device_resize = False
+    faces_host = det(img)
+    assert len(faces_host) == len(faces)
+    for a, b in zip(faces, faces_host):
+        np.testing.assert_array_equal(a['bbox'], b['bbox'])
+    # list input with different sizes -> pad-merge path
+    det.device_resize = True
+    out = det([img, img[:400, :500]])
+    assert len(out) == 2 and len(out[0]) > 0
+
+
+@pytest.mark.parametrize('mode', ['direct', 'tcgen05'])
+def test_arcface_embedding(native, arc, golden, mode):
+    model, sd = arc
+    model.net.set_force_direct(mode == 'direct')
+    try:
+        g = golden('arcface_embed.npz')
+        crops = torch.from_numpy(g['crops']).cuda()
+        raw = model.embed_device(crops, normalise=False).cpu().numpy()
+        emb = model.embed_device(crops).cpu().numpy()
+    finally:
+        model.net.set_force_direct(False)
+    want = g['normalised']
+    cos = (emb * want).sum(1)
+    assert cos.min() >= 0.9999, cos
+    assert np.abs(emb - want).max() <= 5e-3
+    assert np.abs(raw - g['raw']).max() <= 0.05 * np.abs(g['raw']).max()
+    np.testing.assert_allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)
+
+
+def test_recognition_wrapper(native, arc, golden):
+    from terran_b200.face.recognition import Recognition
+    model, _ = arc
+    rec = Recognition(device=torch.device('cuda'), lazy=True)
+    rec.model = model
+    g = golden('arcface_embed.npz')
+    out = rec(list(g['crops']))
+    assert out.shape == (3, 512) and out.dtype == np.float32
+    assert ((out * g['normalised']).sum(1) >= 0.9999).all()
+    # reference model-input layout (NCHW BGR) gives the same embedding
+    chw = torch.from_numpy(np.ascontiguousarray(g['crops'].transpose(0, 3, 1, 2)[:, ::-1])).cuda()
+    alt = model.embed_device(chw, layout='nchw_bgr').cpu().numpy()
+    np.testing.assert_allclose(alt, out, atol=1e-6)
+    with pytest.raises(ValueError):
+        rec(list(g['crops']), [[]])
+    empty = rec(list(g['crops']), [[], [], []])
+    assert [e.shape for e in empty] == [(0, 512)] * 3
+
+
+@pytest.mark.parametrize('mode', ['direct', 'tcgen05'])
+def test_openpose_maps(native, opose, golden, mode):
+    model, sd = opose
+    model.net.set_force_direct(mode == 'direct')
+    try:
+        g = golden('openpose_forward.npz')
+        x = g['x']                                              # (2,3,56,72) in [-0.5,0.5]
+        frames = np.round((x + 0.5) * 255).astype(np.uint8).transpose(0, 2, 3, 1)
+        paf, heat = model.maps(torch.from_numpy(np.ascontiguousarray(frames)).cuda())
+    finally:
+        model.net.set_force_direct(False)
+    assert np.abs(paf.cpu().numpy() - g['paf']).max() <= 4e-3
+    assert np.abs(heat.cpu().numpy() - g['heat']).max() <= 4e-3
+
+
+def test_estimation_wrapper(native, opose):
+    """Estimation on 720p noise frames: runs end to end through the public API
+    (random weights give no peaks above 0.1 -> no humans, like the reference)."""
+    from terran_b200.pose import Estimation
+    model, sd = opose
+    est = Estimation(device=torch.device('cuda'), lazy=True)
+    est.model = model
+    frames = np.random.default_rng(2).integers(0, 256, (2, 720, 1280, 3), dtype=np.uint8)
+    out = est(frames)
+    assert len(out) == 2
+    x = torch.from_numpy(frames[:1]).cuda()
+    from terran_b200.frames import resize_short_side
+    resized, scale = resize_short_side(x, 184)
+    assert tuple(resized.shape) == (1, 184, 327, 3)
+    paf, heat = model.maps(resized)
+    assert tuple(paf.shape) == (1, 38, 23, 40) and tuple(heat.shape) == (1, 19, 23, 40)
+    xin = (resized.cpu().numpy().transpose(0, 3, 1, 2).astype(np.float32) / 255.0 - 0.5)
+    paf_ref, heat_ref = nets.openpose_forward(sd, torch.from_numpy(xin))
+    assert np.abs(paf.cpu().numpy() - paf_ref.numpy()).max() <= 4e-3
+    assert np.abs(heat.cpu().numpy() - heat_ref.numpy()).max() <= 4e-3
+    want = pose.parse(paf_ref.numpy(), heat_ref.numpy(), scale)
+    assert [len(p) for p in out[:1]] == [len(w) for w in want]

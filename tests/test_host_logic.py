@@ -1,0 +1,262 @@
+"""CPU: host-side logic — registry, batching, weight packing, the C-ABI library
+(loads, exports every declared symbol), and the multi-process sharding helpers
+over gloo (world_size 2)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import ROOT
+
+
+# ----------------------------------------------------------------- C ABI / build
+
+def test_library_exports_every_declared_symbol(native):
+    header = open(os.path.join(ROOT, 'include', 'terran_b200.h')).read()
+    declared = set(re.findall(r'\b(tr_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(native.SYMBOLS), declared ^ set(native.SYMBOLS)
+    lib = native.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.tr_version() == 100
+
+
+def test_op_desc_layout_matches_header(native):
+    """ctypes struct layout == the C struct (field order and sizes)."""
+    header = open(os.path.join(ROOT, 'include', 'terran_b200.h')).read()
+    body = re.search(r'typedef struct tr_op_desc \{(.*?)\} tr_op_desc;', header, re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.split(None, 1)
+        fields += [(n.strip(), ctype) for n in names.split(',')]
+    want = [(n.rstrip('_'), {'int32_t': C.c_int32, 'int64_t': C.c_int64, 'float': C.c_float}[t])
+            for n, t in fields]
+    got = [(n.rstrip('_'), t) for n, t in native.OpDesc._fields_]
+    assert got == want
+    assert C.sizeof(native.OpDesc) == 20 * 4 + 6 * 8 + 2 * 4
+
+
+def test_no_gpu_calls_fail_loudly(native):
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(native.NativeError):
+        native.check(native.lib().tr_init(0))
+    from terran_b200.face.detection.retinaface import RetinaFace
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        RetinaFace(device=torch.device('cpu'), state_dict={})
+
+
+def test_bicubic_table_matches_oracle(native):
+    from oracle import pose
+    tab = (C.c_float * 32)()
+    native.lib().tr_bicubic_table(tab)
+    np.testing.assert_array_equal(np.array(tab, np.float32).reshape(8, 4), pose.bicubic_table())
+
+
+def test_sources_build_for_sm100a():
+    from terran_b200 import build
+    src = open(os.path.join(ROOT, 'terran_b200', 'build.py')).read()
+    assert 'arch=compute_100a,code=sm_100a' in src and '-lineinfo' in src
+    assert os.path.exists(build.build())
+
+
+# ------------------------------------------------------------------- registry
+
+def test_registry_resolves_classes(tmp_path, monkeypatch):
+    monkeypatch.setenv('TERRAN_HOME', str(tmp_path))
+    from terran_b200 import checkpoint as ck
+    from terran_b200.face.detection.retinaface import RetinaFace
+    from terran_b200.pose.openpose import OpenPose
+    assert ck.get_class_for_checkpoint('face-detection', None) is RetinaFace
+    assert ck.get_class_for_checkpoint('pose-estimation', 'gpu-realtime') is OpenPose
+    with pytest.raises(ValueError, match='Checkpoint not found'):
+        ck.get_class_for_checkpoint('face-detection', 'nope')
+    with pytest.raises(ValueError):
+        ck.get_checkpoint_path('terran_b200.pose.openpose.OpenPose')       # not on disk
+    (tmp_path / 'checkpoints').mkdir(exist_ok=True)
+    (tmp_path / 'checkpoints' / '11a769ad.pth').write_bytes(b'x')
+    assert ck.get_checkpoint_path('terran_b200.pose.openpose.OpenPose').name == '11a769ad.pth'
+    assert (tmp_path / 'checkpoints').exists()
+
+
+def test_public_surface():
+    import terran_b200
+    from terran_b200.pose import Keypoint
+    for name in ('face_detection', 'extract_features', 'pose_estimation', 'Detection',
+                 'Recognition', 'Estimation', 'default_device'):
+        assert hasattr(terran_b200, name)
+    assert repr(terran_b200.face_detection) == '<Detection(RetinaFace)>'
+    assert repr(terran_b200.extract_features) == '<Recognition(ArcFace)>'
+    assert repr(terran_b200.pose_estimation) == '<Estimation(OpenPose)>'
+    assert Keypoint.NOSE.value == 0 and Keypoint.L_EAR.value == 17 and len(Keypoint) == 18
+
+
+# ------------------------------------------------------------------- batching
+
+def test_pad_merge_matches_reference_rules():
+    from terran_b200.batching import PadMerge
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in ((10, 20), (13, 17), (8, 8))]
+    batch, off = PadMerge().merge(imgs)
+    assert batch.shape == (3, 13, 20, 3)
+    # extra rows/cols: ceil before, floor after
+    np.testing.assert_array_equal(off, [[0, 2], [2, 0], [6, 3]])
+    for im, (left, top), b in zip(imgs, off, batch):
+        np.testing.assert_array_equal(b[top:top + im.shape[0], left:left + im.shape[1]], im)
+        assert b.sum() == im.sum()
+    arr = np.zeros((2, 4, 4, 3), np.uint8)
+    assert PadMerge('bogus').merge(arr)[1] is None          # arrays pass through unchecked
+    with pytest.raises(NotImplementedError):
+        PadMerge('crop').merge(imgs)
+    with pytest.raises(ValueError):
+        PadMerge('bogus').merge(imgs)
+
+    faces = [[{'bbox': np.array([5, 6, 9, 12], np.float32),
+               'landmarks': np.arange(10, dtype=np.float32).reshape(5, 2), 'score': np.float32(.9)}]] * 3
+    out = PadMerge().unpad_faces(faces, off)
+    np.testing.assert_array_equal(out[1][0]['bbox'], [3, 6, 7, 12])
+    assert out[1][0]['bbox'].dtype == np.float32 and out[1][0]['landmarks'].dtype == np.float64
+    poses = [[{'keypoints': np.array([[7, 9, 1], [0, 0, 0]] * 9, np.int32), 'score': 0.5}]] * 3
+    kp = PadMerge().unpad_poses(poses, off)[2][0]['keypoints']
+    np.testing.assert_array_equal(kp[0], [1, 6, 1])
+    np.testing.assert_array_equal(kp[1], [0, 0, 0])          # absent joints stay zero
+
+
+def test_round_faces_half_to_even():
+    from terran_b200.batching import round_faces
+    f = {'bbox': np.array([0.5, 1.5, 2.5, -0.5], np.float32) * np.float32(0.5),
+         'landmarks': np.zeros((5, 2), np.float32), 'score': np.float32(1)}
+    out = round_faces([[f]], 0.5)
+    np.testing.assert_array_equal(out[0][0]['bbox'], [0, 2, 2, 0])
+    assert out[0][0]['bbox'].dtype == np.int32
+
+
+def test_resized_dims_follow_reference():
+    from terran_b200.frames import resized_dims
+    assert resized_dims(1080, 1920, 416)[:2] == (416, 739)
+    assert resized_dims(720, 1280, 184)[:2] == (184, 327)
+    assert resized_dims(640, 640, 416)[:2] == (416, 416)
+    assert abs(resized_dims(1080, 1920, 416)[2] - 0.385185) < 1e-6
+
+
+# ------------------------------------------------------------- weight packing
+
+def test_bn_fold_is_exact_affine():
+    from terran_b200.weights import bn_fold
+    g = torch.Generator().manual_seed(0)
+    sd = {'bn.weight': torch.rand(6, generator=g) + 0.5, 'bn.bias': torch.randn(6, generator=g),
+          'bn.running_mean': torch.randn(6, generator=g), 'bn.running_var': torch.rand(6, generator=g) + 0.5}
+    bias = torch.randn(6, generator=g)
+    s, t = bn_fold(sd, 'bn', 2e-5, bias)
+    y = torch.randn(4, 6, 3, 3, generator=g)
+    want = torch.nn.functional.batch_norm(y + bias.view(1, -1, 1, 1), sd['bn.running_mean'],
+                                          sd['bn.running_var'], sd['bn.weight'], sd['bn.bias'],
+                                          False, 0.0, 2e-5)
+    got = y * torch.from_numpy(s).view(1, -1, 1, 1) + torch.from_numpy(t).view(1, -1, 1, 1)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), atol=1e-5)
+
+
+def test_programs_cover_every_checkpoint_tensor():
+    """Every conv / linear weight of the reference state_dicts lands in the
+    packed blob exactly once (op counts per architecture)."""
+    from terran_b200 import _native as nat, synth, weights
+    P, roles = weights.retinaface_program(synth.retinaface_state_dict())
+    kinds = [op.type for op in P.ops]
+    assert kinds.count(nat.TR_OP_STEM) == 1 and kinds.count(nat.TR_OP_DWCONV) == 13
+    # 56 convs = 1 stem + 13 depthwise + 33 dense + 9 heads fused into 3
+    assert kinds.count(nat.TR_OP_CONV) == 56 - 1 - 13 - 9 + 3
+    assert len(roles['heads']) == 3
+    P, _ = weights.openpose_program(synth.openpose_state_dict())
+    kinds = [op.type for op in P.ops]
+    assert kinds.count(nat.TR_OP_CONV) + kinds.count(nat.TR_OP_STEM) == 92
+    assert kinds.count(nat.TR_OP_MAXPOOL) == 3
+    small = (1, 1, 1, 1)
+    P, _ = weights.arcface_program(synth.arcface_state_dict(units=small), units=small)
+    kinds = [op.type for op in P.ops]
+    # stem + per unit (2 convs + shortcut for first units) + FC
+    assert kinds.count(nat.TR_OP_CONV) == 4 * 3 + 1 and kinds.count(nat.TR_OP_VIEW) == 1
+    # concat-channel remap for the 7x7 stage convs
+    m = weights.OPENPOSE_CAT_MAP
+    assert len(m) == 185 and m[37] == 37 and m[38] == 40 and m[56] == 58 and m[57] == 64 and m[-1] == 191
+
+
+def test_umeyama_recovers_similarity():
+    from terran_b200.face.recognition.arcface.wrapper import umeyama_similarity, LANDMARK_TEMPLATE
+    th, s, t = 0.3, 1.7, np.array([5.0, -3.0])
+    R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    src = LANDMARK_TEMPLATE.astype(np.float64)
+    dst = (s * (R @ src.T)).T + t
+    T = umeyama_similarity(src, dst)
+    np.testing.assert_allclose(T[:2, :2], s * R, atol=1e-9)
+    np.testing.assert_allclose(T[:2, 2], t, atol=1e-9)
+
+
+# -------------------------------------------------------------- multi-process
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch
+import torch.distributed as dist
+from terran_b200 import parallel, synth
+rank, world, _ = parallel.init_from_env(backend='gloo')
+assert world == 2
+# 1. weight broadcast: rank 1 starts from nothing
+sd = synth.retinaface_state_dict() if rank == 0 else None
+sd = parallel.broadcast_state_dict(sd, src=0)
+ref = synth.retinaface_state_dict()
+assert list(sd) == list(ref)
+for k in ref:
+    assert sd[k].dtype == ref[k].dtype and torch.equal(sd[k], ref[k]), k
+# 2. frame sharding: a pure per-frame function, sharded == unsharded
+frames = np.arange(7 * 3, dtype=np.float32).reshape(7, 3)
+def call(batch):        # stand-in for a model call: variable number of rows per frame
+    return [np.full((int(f[0]) % 4, 16), f.sum(), np.float32) for f in batch]
+lo, hi, res = parallel.sharded_call(call, frames)
+assert (lo, hi) == parallel.shard_range(7, rank, 2)
+counts = [len(r) for r in res]
+rows = np.concatenate(res) if res else np.zeros((0, 16), np.float32)
+out = parallel.gather_rows(counts, rows, dst=0)
+if rank == 0:
+    want = call(frames)
+    assert len(out) == 7
+    for a, b in zip(out, want):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    print('GATHER_OK')
+else:
+    assert out is None
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_broadcast_and_gather(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='', OMP_NUM_THREADS='1')
+    r = subprocess.run(
+        [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+         '--master-addr', '127.0.0.1', '--master-port', '29731', str(script)],
+        capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'GATHER_OK' in r.stdout
+
+
+def test_shard_range_partitions():
+    from terran_b200.parallel import shard_range
+    for n in (0, 1, 7, 32, 33):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,178 @@
+"""CPU: the oracle restatements against the golden fixtures that
+``oracle/make_golden.py`` produced by running the UNMODIFIED reference
+(``/root/reference``) on the same seeded inputs and synthetic checkpoints."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import detect, nets, pose
+from terran_b200 import synth
+
+
+@pytest.fixture(scope='module')
+def retina_sd():
+    return synth.retinaface_state_dict()
+
+
+def test_retinaface_forward_matches_reference(golden, retina_sd):
+    g = golden('retinaface_forward.npz')
+    x = torch.from_numpy(g['x'].astype(np.float32))
+    heads = nets.retinaface_forward(retina_sd, x)
+    assert len(heads) == 9
+    for i, h in enumerate(heads):
+        np.testing.assert_allclose(h.numpy(), g[f'head{i}'], rtol=0, atol=2e-5)
+
+
+def test_anchor_reference_closed_form():
+    # generate_anchors(base 16, ratio 1, scales ...) of anchors.py:75-134
+    assert detect.anchor_refs_from_settings(16, (32, 16)) == detect.ANCHOR_REFS[32]
+    assert detect.anchor_refs_from_settings(16, (8, 4)) == detect.ANCHOR_REFS[16]
+    assert detect.anchor_refs_from_settings(16, (2, 1)) == detect.ANCHOR_REFS[8]
+    a = detect.anchors_for(16, 2, 3)
+    assert a.shape == (12, 4)
+    np.testing.assert_array_equal(a[0], [-56, -56, 71, 71])
+    np.testing.assert_array_equal(a[1], [-24, -24, 39, 39])
+    np.testing.assert_array_equal(a[2], [-40, -56, 87, 71])      # w = 1
+    np.testing.assert_array_equal(a[6], [-56, -40, 71, 87])      # h = 1
+
+
+def test_retinaface_call_matches_reference(golden):
+    """decode + threshold + sort + NMS on the reference's own head tensors:
+    identical survivor sets and order, scores bit-equal, boxes within the 1-ulp
+    exp() difference (torch's SLEEF exp vs the correctly rounded oracle exp)."""
+    g = golden('retinaface_call.npz')
+    heads = [g[f'head{i}'] for i in range(9)]
+    H, W = g['images'].shape[1:3]
+    out = detect.model_call(heads, H, W)
+    assert len(out) == g['images'].shape[0]
+    for i, faces in enumerate(out):
+        ref_scores = g[f'score{i}']
+        assert len(faces) == len(ref_scores) > 0
+        np.testing.assert_array_equal(np.array([f['score'] for f in faces]), ref_scores)
+        np.testing.assert_allclose(np.stack([f['bbox'] for f in faces]), g[f'bbox{i}'],
+                                   rtol=0, atol=2e-4)
+        np.testing.assert_allclose(np.stack([f['landmarks'] for f in faces]), g[f'landmarks{i}'],
+                                   rtol=0, atol=2e-4)
+
+
+def test_retinaface_full_pipeline_from_pixels(golden, retina_sd):
+    """uint8 frames -> oracle network -> oracle post-processing equals the
+    reference's RetinaFace.call output."""
+    g = golden('retinaface_call.npz')
+    images = g['images']
+    x = torch.from_numpy(images.astype(np.float32)).permute(0, 3, 1, 2).flip(1)
+    heads = [h.numpy() for h in nets.retinaface_forward(retina_sd, x)]
+    out = detect.model_call(heads, *images.shape[1:3])
+    for i, faces in enumerate(out):
+        np.testing.assert_array_equal(np.array([f['score'] for f in faces]), g[f'score{i}'])
+
+
+def test_detection_640_end_to_end(golden, retina_sd):
+    """BASELINE config 1: Detection()(one 640x640 image) through cv2 resize,
+    network, post-processing, rescale + round (int32 outputs exact)."""
+    import cv2
+    g = golden('retinaface_detection_640.npz')
+    img = np.random.default_rng(0).integers(0, 256, (640, 640, 3), dtype=np.uint8)
+    scale = 416 / 640
+    small = cv2.resize(img, (int(640 * scale), int(640 * scale)), interpolation=cv2.INTER_LINEAR)
+    x = torch.from_numpy(small[None].astype(np.float32)).permute(0, 3, 1, 2).flip(1)
+    heads = [h.numpy() for h in nets.retinaface_forward(retina_sd, x)]
+    faces = detect.resize_out(detect.model_call(heads, 416, 416), scale)[0]
+    assert len(faces) == len(g['score'])
+    np.testing.assert_array_equal(np.stack([f['bbox'] for f in faces]), g['bbox'])
+    np.testing.assert_array_equal(np.stack([f['landmarks'] for f in faces]), g['landmarks'])
+    np.testing.assert_array_equal(np.array([f['score'] for f in faces]), g['score'])
+    assert faces[0]['bbox'].dtype == np.int32
+
+
+def test_nms_matches_torchvision():
+    """The oracle NMS against torchvision.ops.nms (the reference's dependency),
+    including the IoU == threshold edge (suppressed only when strictly greater
+    as a double)."""
+    from torchvision.ops import nms as tv_nms
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        n = 300
+        xy = rng.uniform(0, 200, (n, 2)).astype(np.float32)
+        wh = rng.uniform(5, 80, (n, 2)).astype(np.float32)
+        boxes = np.concatenate([xy, xy + wh], 1)
+        scores = rng.permutation(n).astype(np.float32) / n
+        order = np.argsort(-scores, kind='stable')
+        keep = order[detect.nms(boxes[order], 0.4)]
+        ref = tv_nms(torch.from_numpy(boxes), torch.from_numpy(scores), 0.4).numpy()
+        np.testing.assert_array_equal(keep, ref)
+
+
+def test_nms_edge_cases():
+    assert len(detect.nms(np.zeros((0, 4), np.float32), 0.4)) == 0
+    one = np.array([[0, 0, 10, 10]], np.float32)
+    np.testing.assert_array_equal(detect.nms(one, 0.4), [0])
+    # identical boxes: IoU 1 -> second suppressed; degenerate zero-area boxes: IoU nan -> kept
+    same = np.array([[0, 0, 10, 10], [0, 0, 10, 10]], np.float32)
+    np.testing.assert_array_equal(detect.nms(same, 0.4), [0])
+    degenerate = np.array([[5, 5, 5, 5], [5, 5, 5, 5]], np.float32)
+    np.testing.assert_array_equal(detect.nms(degenerate, 0.4), [0, 1])
+
+
+def test_arcface_matches_reference(golden):
+    g = golden('arcface_embed.npz')
+    sd = synth.arcface_state_dict()
+    crops = g['crops']
+    x = torch.from_numpy(crops.transpose(0, 3, 1, 2)[:, ::-1].astype(np.float32).copy())
+    raw = nets.arcface_forward(sd, x).numpy()
+    np.testing.assert_allclose(raw, g['raw'], rtol=0, atol=1e-4)
+    norm = np.sqrt((raw ** 2).sum(1, keepdims=True))
+    norm[norm == 0] = 1
+    np.testing.assert_allclose(raw / norm, g['normalised'], rtol=0, atol=1e-6)
+
+
+def test_openpose_forward_matches_reference(golden):
+    g = golden('openpose_forward.npz')
+    sd = synth.openpose_state_dict()
+    paf, heat = nets.openpose_forward(sd, torch.from_numpy(g['x']))
+    np.testing.assert_allclose(paf.numpy(), g['paf'], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(heat.numpy(), g['heat'], rtol=0, atol=1e-5)
+    # quirk: the final heat-map layer keeps its ReLU (openpose/model.py:38)
+    assert heat.min() >= 0 and paf.min() < 0
+
+
+def test_bicubic_matches_torch():
+    t = torch.from_numpy(np.random.default_rng(3).random((1, 4, 9, 13)).astype(np.float32))
+    ref = torch.nn.functional.interpolate(t, scale_factor=8, mode='bicubic',
+                                          align_corners=False)[0].numpy()
+    np.testing.assert_allclose(pose.bicubic_up8(t[0].numpy()), ref, rtol=0, atol=1e-6)
+    tab = pose.bicubic_table()
+    np.testing.assert_allclose(tab.sum(1), 1.0, atol=1e-6)
+
+
+def test_openpose_parse_matches_reference(golden):
+    """24 synthetic scenes through the reference's OpenPose.call (stub network):
+    identical keypoint integers and human counts, scores to 1e-5."""
+    g = golden('openpose_parse.npz')
+    scale = 184 / 720
+    total = 0
+    for k, seed in enumerate(g['seeds']):
+        paf, heat = pose.synthetic_scene(int(seed))
+        np.testing.assert_allclose([paf.astype(np.float64).sum(), heat.astype(np.float64).sum()],
+                                   g[f'mapsum{k}'], rtol=1e-12)
+        if k < 4:
+            np.testing.assert_array_equal(paf, g[f'paf{k}'].astype(np.float32))
+            np.testing.assert_array_equal(heat, g[f'heat{k}'].astype(np.float32))
+        humans = pose.parse_frame(paf, heat, scale)
+        assert len(humans) == len(g[f'score{k}'])
+        if humans:
+            np.testing.assert_array_equal(np.stack([h['keypoints'] for h in humans]), g[f'kp{k}'])
+            np.testing.assert_allclose([h['score'] for h in humans], g[f'score{k}'], atol=1e-5)
+        total += len(humans)
+    assert total > 50
+
+
+def test_openpose_parse_edge_cases():
+    z_paf, z_heat = np.zeros((38, 6, 7), np.float32), np.zeros((19, 6, 7), np.float32)
+    assert pose.parse_frame(z_paf, z_heat, 1.0) == []          # no peaks at all
+    # one isolated joint: a peak but no limb -> no human
+    h = z_heat.copy()
+    h[0, 3, 3] = 1.0
+    assert pose.parse_frame(z_paf, h, 1.0) == []
+    # zero-length pair (same location for src/dst part) -> NaN score, rejected
+    assert pose.segment_points(5, 5) == [5] * 10
