@@ -1,0 +1,324 @@
+"""Headline benchmark: frames/sec end-to-end (detect + pose) on synthetic 1080p
+frame batches, one process per GPU, frames sharded across ranks (weak scaling:
+every rank processes its own batch; no collective on the per-frame step).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the CPU path (oracle port), host cores
+
+One step = one pass of RetinaFace face detection (short side 416) and OpenPose
+pose estimation (short side 184) over one batch of 32 synthetic 1080p frames,
+resize and post-processing included.  ``value`` is timed with the frames already
+resident in HBM (results stay on the device); ``e2e`` goes through the public
+callables with the frames in pinned HOST memory, H2D and result D2H inside the
+timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault('TERRAN_HOME', os.path.join(ROOT, '.pytest_cache', 'terran_home'))
+os.makedirs(os.environ['TERRAN_HOME'], exist_ok=True)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BATCH = 32
+FRAME_HW = (1080, 1920)
+METRIC = 'frames/sec end-to-end (detect+pose) on 1080p synthetic batch'
+WORKLOAD = ('RetinaFace face_detection (short side 416) + OpenPose pose_estimation '
+            '(short side 184) on 1080p synthetic frames, batch=32 per GPU')
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {'hbm_gbs': p['hbm_gbs'], 'bf16_tflops': p['bf16_tflops'],
+                'bf16_tflops_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0,
+            'source': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# --------------------------------------------------------------- reference arm
+
+def cpu_pipeline_frames(frames, sd_det, sd_pose):
+    """The reference's CPU path for detect + pose, restated (oracle port): host
+    cv2 resize, fp32 torch convolutions on all host threads, numpy/Python
+    post-processing.  Returns (n_faces, n_humans)."""
+    import cv2
+    from oracle import detect, nets, pose
+    H, W = frames.shape[1:3]
+    s_det, s_pose = 416 / min(H, W), 184 / min(H, W)
+    small = np.stack([cv2.resize(f, (int(W * s_det), int(H * s_det)),
+                                 interpolation=cv2.INTER_LINEAR) for f in frames])
+    x = torch.from_numpy(small.astype(np.float32)).permute(0, 3, 1, 2).flip(1)
+    heads = [h.numpy() for h in nets.retinaface_forward(sd_det, x)]
+    faces = detect.resize_out(detect.model_call(heads, *small.shape[1:3]), s_det)
+    small = np.stack([cv2.resize(f, (int(W * s_pose), int(H * s_pose)),
+                                 interpolation=cv2.INTER_LINEAR) for f in frames])
+    x = torch.from_numpy(small.transpose(0, 3, 1, 2).astype(np.float32) / 255.0 - 0.5)
+    paf, heat = nets.openpose_forward(sd_pose, x)
+    humans = pose.parse(paf.numpy(), heat.numpy(), s_pose)
+    return sum(len(f) for f in faces), sum(len(h) for h in humans)
+
+
+def time_cpu_pipeline(sample_frames, steps, warmup):
+    from terran_b200 import synth
+    sd_det, sd_pose = synth.retinaface_state_dict(), synth.openpose_state_dict()
+    frames = np.random.default_rng(0).integers(0, 256, (sample_frames,) + FRAME_HW + (3,),
+                                               dtype=np.uint8)
+    for _ in range(warmup):
+        cpu_pipeline_frames(frames, sd_det, sd_pose)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pipeline_frames(frames, sd_det, sd_pose)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_frames / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on the box's host cores, rank 0 only."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = 4
+    fps, dt = time_cpu_pipeline(sample, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'frames_per_step': sample,
+                   'note': 'bounded sample of the same workload on host cores'},
+        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{sample} synthetic 1080p frames per step (detect+pose), '
+                                   f'oracle port of the reference CPU path, torch {cores} threads'},
+        'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------- our arm
+
+def run_ours(args):
+    from terran_b200 import parallel, synth
+    from terran_b200.face.detection import Detection
+    from terran_b200.face.detection.retinaface import RetinaFace
+    from terran_b200.pose import Estimation
+    from terran_b200.pose.openpose import OpenPose
+
+    rank, world, local = parallel.init_from_env()
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    import torch.distributed as dist
+
+    # Weights: generated on rank 0, ONE broadcast to the other ranks at init.
+    sd_det = parallel.broadcast_state_dict(synth.retinaface_state_dict() if rank == 0 else None)
+    sd_pose = parallel.broadcast_state_dict(synth.openpose_state_dict() if rank == 0 else None)
+    det_model = RetinaFace(device=dev, state_dict=sd_det)
+    pose_model = OpenPose(device=dev, state_dict=sd_pose)
+    detection = Detection(device=dev, lazy=True)
+    detection.model = det_model
+    estimation = Estimation(device=dev, lazy=True)
+    estimation.model = pose_model
+
+    H, W = FRAME_HW
+    host = torch.from_numpy(np.random.default_rng(rank).integers(
+        0, 256, (BATCH, H, W, 3), dtype=np.uint8)).pin_memory()
+    frames = host.to(dev)              # 199 MB > 126 MB L2: every step streams from HBM
+
+    def device_step():
+        from terran_b200.frames import resize_short_side
+        small, _ = resize_short_side(frames, 416)
+        out_d = det_model.detect_device(small)
+        out_p = pose_model.estimate_device(frames)
+        return out_d, out_p
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+
+    # ---- value: device-resident, CUDA events on the launch stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out_d, out_p = device_step()
+        e1.record()
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * BATCH * args.steps / (ms_total / 1e3)
+
+    # ---- e2e: public API, frames in pinned host memory, results back on host
+    def e2e_step():
+        d = host.to(dev, non_blocking=True)
+        faces = detection(d)
+        poses = estimation(d)
+        return faces, poses
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        faces, poses = e2e_step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = world * BATCH * args.steps / float(dt.item())
+    d2h = 0
+    for f in faces:
+        d2h += len(f) * 16 * 4
+    d2h += 2 * BATCH * 4 + BATCH * 4 * 2 + sum(len(p) for p in poses) * (54 * 4 + 8)
+
+    # ---- roofline of the dominant kernel (conv_tc_kernel): per-op CUDA events
+    tc_ms = tc_flops = all_ms = 0.0
+    tc_launch = 0
+    for net in (det_model.net, pose_model.net):
+        net.set_profile(True)
+    for _ in range(args.steps):
+        device_step()
+        for net in (det_model.net, pose_model.net):
+            for op_ms, is_tc, flops in net.profile():
+                all_ms += op_ms
+                if is_tc:
+                    tc_ms += op_ms
+                    tc_flops += flops
+                    tc_launch += 1
+    for net in (det_model.net, pose_model.net):
+        net.set_profile(False)
+    peaks = measured_peaks()
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0
+    launches_per_step = (det_model.net.stats()['launches'] + pose_model.net.stats()['launches']
+                         + 2       # resize x2
+                         + 2 + 1   # detect scan/select (+ memset not counted)
+                         + 2       # paf/heat export
+                         + 4)      # pose peaks/sort/limbs/assemble
+
+    if rank != 0:
+        return
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'frames_per_gpu': BATCH,
+                   'frame': '1080x1920x3 u8', 'parallelism': f'frame-sharded dp{world}',
+                   'l2': 'inputs (199 MB of frames per step) larger than the 126 MB L2',
+                   'weights': 'synthetic seeded (terran_b200/synth.py)'},
+        'clocks': clocks.summary(),
+        'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': BATCH * H * W * 3,
+                'd2h_bytes_per_step': int(d2h)},
+        'gpu_launches': int(launches_per_step * args.steps),
+        'roofline': {
+            'kernel': 'conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches of a step)',
+            'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops_sustained'],
+            'unit': 'TFLOP/s', 'frac': achieved / peaks['bf16_tflops_sustained'],
+            'peak_source': peaks['source'] + ' (sustained: kernel timed inside a long step)',
+            'traffic': None,
+            'share_of_step': tc_ms / all_ms if all_ms else None,
+            'launches_per_step': tc_launch // max(args.steps, 1),
+            'algorithmic_gflop_per_step': tc_flops / max(args.steps, 1) / 1e9,
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        fps, _ = time_cpu_pipeline(4, 1, 1)
+        line['cpu_baseline'] = {
+            'value': fps, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '4 synthetic 1080p frames (detect+pose), oracle port of the reference '
+                      'CPU path, 1 warm-up + 1 timed pass'}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -24,6 +24,10 @@ for step in "$@"; do
     smoke)   run smoke 900 python __graft_entry__.py --smoke ;;
     bench)   run bench 1200 python bench.py ;;
     benchref) run benchref 1200 python bench.py --impl reference --steps 2 --warmup 1 ;;
+    ncu_list) run ncu_list 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv \
+                --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline ;;
+    ncu_full) run ncu_full 1500 ncu --set full --clock-control none --import-source on -k regex:conv_tc \
+                -s 100 -c 3 -f -o gpurun_out/prof_conv_tc python bench.py --steps 1 --warmup 1 --no-cpu-baseline ;;
     *)       run custom 1200 bash -c "$step" ;;
   esac
 done

@@ -318,20 +318,25 @@ resize_u8_kernel(const uint8_t* src, int N, int H, int W, uint8_t* dst, int h, i
   const int ox = idx % w;
   const int oy = (idx / w) % h;
   const int n = idx / (static_cast<long>(w) * h);
-  auto tap = [](int o, double scale, int n_src, int& i0, int& i1, int& a0, int& a1) {
+  // OpenCV clamps index AND fraction along x, but along y only clips the row
+  // index when fetching rows (the weights keep the unclamped fraction).
+  auto tap = [](int o, double scale, int n_src, bool clamp_weights, int& i0, int& i1, int& a0,
+                int& a1) {
     float f = static_cast<float>((o + 0.5) * scale - 0.5);
     int s = static_cast<int>(floorf(f));
     f -= s;
-    if (s < 0) { s = 0; f = 0.f; }
-    if (s >= n_src - 1) { s = n_src - 1; f = 0.f; }
-    i0 = s;
-    i1 = min(s + 1, n_src - 1);
+    if (clamp_weights) {
+      if (s < 0) { s = 0; f = 0.f; }
+      if (s >= n_src - 1) { s = n_src - 1; f = 0.f; }
+    }
+    i0 = min(max(s, 0), n_src - 1);
+    i1 = min(max(s + 1, 0), n_src - 1);
     a1 = static_cast<int>(rintf(f * 2048.f));
     a0 = static_cast<int>(rintf((1.f - f) * 2048.f));
   };
   int x0, x1, ax0, ax1, y0, y1, ay0, ay1;
-  tap(ox, sx_d, W, x0, x1, ax0, ax1);
-  tap(oy, sy_d, H, y0, y1, ay0, ay1);
+  tap(ox, sx_d, W, true, x0, x1, ax0, ax1);
+  tap(oy, sy_d, H, false, y0, y1, ay0, ay1);
   const uint8_t* r0 = src + (static_cast<long>(n) * H + y0) * W * 3;
   const uint8_t* r1 = src + (static_cast<long>(n) * H + y1) * W * 3;
   uint8_t* o = dst + idx * 3;
@@ -418,7 +423,7 @@ void resize_bilinear_u8_launch(const uint8_t* src, int N, int H, int W, uint8_t*
                                int w, cudaStream_t s) {
   const long total = static_cast<long>(N) * h * w;
   resize_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
-      src, N, H, W, dst, h, w, double(H) / h, double(W) / w);
+      src, N, H, W, dst, h, w, 1.0 / (double(h) / H), 1.0 / (double(w) / W));  // OpenCV: 1/inv_scale
   TR_CUDA(cudaGetLastError());
 }
 

@@ -216,4 +216,9 @@ def openpose_state_dict(seed=7):
                 last = i == len(layers) - 1
                 conv(f'model{stage}_{branch}.{name}', cin, cout, k,
                      gain=0.5 if last else math.sqrt(2.0))
+    # Final heat-map layer: damped and shifted so that, on noise frames, only a
+    # few up-sampled maxima clear the 0.1 peak threshold (tens of peaks on one
+    # or two parts, like a real frame) instead of ~150 per part.
+    sd['model6_2.Mconv7_stage6_L2.weight'] *= 0.4
+    sd['model6_2.Mconv7_stage6_L2.bias'] = sd['model6_2.Mconv7_stage6_L2.bias'] * 0.4 - 0.05
     return sd

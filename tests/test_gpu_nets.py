@@ -61,7 +61,11 @@ def test_retinaface_heads(native, retina, shape, mode):
         for i, (a, b) in enumerate(zip(got, want)):
             assert a.shape == b.shape, (i, a.shape, b.shape)
             if i % 3 == 0:
-                assert np.abs(logit(a) - logit(b)).max() < 0.25, (i, np.abs(logit(a) - logit(b)).max())
+                assert np.abs(a - b).max() < 2e-2, (i, np.abs(a - b).max())
+                live = (np.abs(logit(a)) < 8) & (np.abs(logit(b)) < 8)   # away from fp32 saturation
+                assert live.any()
+                d = np.abs(logit(a) - logit(b))[live].max()
+                assert d < 0.25, (i, d)
             else:
                 assert np.abs(a - b).max() < 4e-3, (i, np.abs(a - b).max())
     finally:

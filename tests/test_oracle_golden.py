@@ -85,6 +85,20 @@ def test_detection_640_end_to_end(golden, retina_sd):
     assert faces[0]['bbox'].dtype == np.int32
 
 
+def test_resize_oracle_matches_cv2():
+    """The integer restatement of cv2.resize(INTER_LINEAR) on uint8 (the
+    reference's host resize) — down- and up-scaling, odd sizes."""
+    import cv2
+    from oracle import resize
+    rng = np.random.default_rng(0)
+    for (H, W), short in (((1080, 1920), 416), ((720, 1280), 184), ((640, 640), 416),
+                          ((333, 517), 416), ((97, 61), 184), ((50, 70), 416), ((1200, 777), 300)):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        got, scale = resize.resize_short_side(img, short)
+        want = cv2.resize(img, (int(W * scale), int(H * scale)), interpolation=cv2.INTER_LINEAR)
+        np.testing.assert_array_equal(got, want, err_msg=f'{H}x{W}->{short}')
+
+
 def test_nms_matches_torchvision():
     """The oracle NMS against torchvision.ops.nms (the reference's dependency),
     including the IoU == threshold edge (suppressed only when strictly greater
