@@ -104,6 +104,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   }
 }
 
+// One lane of the (converged) warp, chosen by the hardware.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
                                             int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -126,7 +139,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes,
                                               uint32_t layout_type) {
   uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);          // start address
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);          // start address (0 = template)
   d |= static_cast<uint64_t>(1) << 16;                          // LBO (unused: swizzled K-major)
   d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;             // 8-row group stride
   d |= static_cast<uint64_t>(1) << 46;                          // descriptor version (sm_100)
@@ -208,38 +221,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);     // provably warp-uniform
 
   const int taps = p.kh * p.kw;
 
+  // The producer and MMA loops run with the WHOLE warp converged and every
+  // operand warp-uniform; one elected lane issues the TMA / tcgen05 instructions.
+  // (Issuing from inside an `if (lane == 0)` region makes the compiler wrap each
+  // uniform-datapath instruction in a divergence "waterfall" loop — measured at
+  // ~240 cycles per tcgen05.mma, 4x the MMA's own execution time.)
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        int mt = tile / p.n_tiles;
-        const int wb = mt % p.tiles_w; mt /= p.tiles_w;
-        const int hb = mt % p.tiles_h; mt /= p.tiles_h;
-        const int nb = mt;
-        const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = nb * p.bn;
-        for (int tap = 0; tap < taps; ++tap) {
-          const int r = tap / p.kw, s = tap % p.kw;
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = p.rows * p.KC * 2 + p.N_tile * p.KC * 2;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int wb = mt % p.tiles_w; mt /= p.tiles_w;
+      const int hb = mt % p.tiles_h; mt /= p.tiles_h;
+      const int nb = mt;
+      const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = nb * p.bn;
+      int tap = 0;
+      for (int r = 0; r < p.kh; ++r) {
+        for (int s = 0; s < p.kw; ++s, ++tap) {
+          // input-space coordinates of this tap
+          int c_base = p.in_coff, cw, ch, c2, c3, c4;
+          if (p.stride == 1) {
+            cw = w0 + s - p.pad; ch = h0 + r - p.pad; c3 = n0; c4 = 0; c2 = ch;
+          } else {
+            const int oy = r - p.pad, ox = s - p.pad;
+            const int py = oy & 1, px = ox & 1;
+            c_base += px * p.in_cs;
+            cw = w0 + ((ox - px) >> 1); c2 = py; c3 = h0 + ((oy - py) >> 1); c4 = n0;
+          }
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
             const uint32_t sa = base + stage * p.stage_bytes;
-            const uint32_t sb = sa + p.a_bytes;
-            mbar_expect_tx(full_bar(stage), p.rows * p.KC * 2 + p.N_tile * p.KC * 2);
-            const int c = p.in_coff + kc * p.KC;
-            if (p.stride == 1) {
-              tma_load_5d(sa, &tmA, full_bar(stage), c, w0 + s - p.pad, h0 + r - p.pad, n0, 0);
-            } else {
-              const int oy = r - p.pad, ox = s - p.pad;
-              const int py = oy & 1, px = ox & 1;
-              tma_load_5d(sa, &tmA, full_bar(stage), px * p.in_cs + c, w0 + ((ox - px) >> 1), py,
-                          h0 + ((oy - py) >> 1), n0);
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(stage), tx_bytes);
+              tma_load_5d(sa, &tmA, full_bar(stage), c_base + kc * p.KC, cw, c2, c3, c4);
+              tma_load_2d(sa + p.a_bytes, &tmB, full_bar(stage), tap * p.cin_pad + kc * p.KC,
+                          nt * p.N_tile);
             }
-            tma_load_2d(sb, &tmB, full_bar(stage), tap * p.cin_pad + kc * p.KC, nt * p.N_tile);
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -247,31 +272,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      const int ksteps = p.KC / 16;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    const int ksteps = p.KC / 16;
+    const uint64_t desc_hi = umma_desc(0, p.sbo_bytes, p.layout_type);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_base + acc * p.N_tile;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase, p.err, 3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + acc * p.N_tile;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase, p.err, 3);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = base + stage * p.stage_bytes;
-          const uint32_t sb = sa + p.a_bytes;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = umma_desc(sa + k * 32, p.sbo_bytes, p.layout_type);
-            const uint64_t bd = umma_desc(sb + k * 32, p.sbo_bytes, p.layout_type);
-            umma_f16(d_tmem, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
+        const uint32_t sa = base + stage * p.stage_bytes;
+        const uint64_t ad = desc_hi | static_cast<uint64_t>((sa & 0x3FFFFu) >> 4);
+        const uint64_t bd = desc_hi | static_cast<uint64_t>(((sa + p.a_bytes) & 0x3FFFFu) >> 4);
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k)     // +32 bytes (2 x 16 B) per 16-element K step
+            umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));        // frees the smem slot when the MMAs retire
           if (kb == p.k_blocks - 1) umma_commit(tfull_bar(acc));
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
