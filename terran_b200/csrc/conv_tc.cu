@@ -11,13 +11,18 @@
 // convolutions view the input as {2C, W/2, 2, H/2, N} so a tap selects a
 // (row parity, column parity) plane and the window stays dense.
 //
-// Warp roles (192 threads, one CTA per SM, persistent over output tiles):
-//   warp 0      TMA producer (one elected lane)
-//   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2-5   epilogue: tcgen05.ld -> scale/shift/activation/residual -> HBM
+// Warp roles (320 threads, one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer  (whole warp converged, one elected lane issues)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (same)
+//   warps 2-9   epilogue: tcgen05.ld -> scale/shift/activation/residual -> HBM
+//               (two warps per TMEM lane quarter, alternating 16-column chunks)
 // Pipelines: smem ring (full/empty mbarriers) between TMA and MMA, and a
 // double-buffered TMEM accumulator (tmem_full/tmem_empty) between MMA and the
 // epilogue, so the epilogue of tile i overlaps the main loop of tile i+1.
+// One ring stage holds `sub` (A,B) k-blocks: the issue loops run on a single
+// warp whose per-iteration latency (~400 cycles of dependent instructions and
+// mbarrier round trips, measured) must stay below the MMA time queued per
+// iteration, so a stage carries >= 512 cycles of tensor work where smem allows.
 //
 // Replaces the cuDNN/ATen convolutions behind every nn.Conv2d of the
 // reference's models (retinaface/model.py, arcface/model.py, openpose/model.py).
@@ -25,15 +30,19 @@
 
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <vector>
 
 namespace trb {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 8;
-constexpr uint32_t kSmemBudget = 200 * 1024;
+constexpr int kMaxSub = 4;
+constexpr uint32_t kSmemBudget = 196 * 1024;
+constexpr int kMaxParamChannels = 1024;     // per-channel epilogue params staged in smem
 
 struct TcParams {
   int bw, bh, bn, rows;
@@ -43,11 +52,13 @@ struct TcParams {
   int kh, kw, pad, stride;
   int KC, kchunks, cin_pad;
   int in_coff, in_cs;
-  int k_blocks;
+  int k_blocks;            // taps * kchunks
+  int sub, iters;          // k-blocks per stage, stage iterations per tile
   int stages;
-  uint32_t a_bytes, b_bytes, stage_bytes;
+  uint32_t a_bytes, b_bytes, sub_bytes, stage_bytes;
   uint32_t sbo_bytes, layout_type, idesc;
   uint32_t tmem_cols;
+  int cout_pad;
   // epilogue
   const float* scale; const float* shift; const float* slope;
   const float* scale2; const float* shift2;
@@ -57,6 +68,7 @@ struct TcParams {
   const __half* res; int res_cs, res_coff, res_up2, res_H, res_W;
   float* out_f32;
   int* err;   // device flag set on a pipeline timeout
+  int debug;  // timing experiments only: 1 = skip TMA loads, 2 = skip MMAs (results are garbage)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -135,27 +147,28 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes,
-                                              uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);          // start address (0 = template)
-  d |= static_cast<uint64_t>(1) << 16;                          // LBO (unused: swizzled K-major)
-  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;             // 8-row group stride
-  d |= static_cast<uint64_t>(1) << 46;                          // descriptor version (sm_100)
-  d |= static_cast<uint64_t>(layout_type) << 61;                // swizzle mode
-  return d;
+// Upper 32 bits of the K-major shared-memory matrix descriptor
+// (cute::UMMA::SmemDescriptor): SBO [32,46), version=1 [46,48), layout [61,64).
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return (sbo_bytes >> 4) | (1u << 14) | (layout_type << 29);
+}
+// Lower 32 bits: start address >> 4 in [0,14), LBO (=1, unused for swizzled K-major) in [16,30).
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) {
+  return ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
 }
 
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                         uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
+                                         uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
       "}\n"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -164,7 +177,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+// Asynchronous TMEM load of 16 consecutive fp32 columns of this thread's lane;
+// tmem_ld_wait() must precede the first use of v.
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -172,22 +187,93 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
         "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float apply_act(float y, int act, float slope) {
-  if (act == ACT_RELU) return fmaxf(y, 0.f);
-  if (act == ACT_PRELU) return y >= 0.f ? y : y * slope;
-  return y;
+struct EpiCtx {
+  const float* sp;       // smem params: [5][cout_pad] scale, shift, slope, scale2, shift2
+  int cpad;
+  bool valid;
+  long pix, rpix;
+};
+
+// Scale/shift/activation/residual/store of 16 consecutive output channels.
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiCtx& e,
+                                               const uint32_t (&v)[16], int cbase) {
+  if (!e.valid || cbase >= p.cout_store) return;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int c = cbase + g * 8;
+    if (c >= p.cout_store) break;
+    float y[8];
+    const float4* sc4 = reinterpret_cast<const float4*>(e.sp + c);
+    const float4* sh4 = reinterpret_cast<const float4*>(e.sp + e.cpad + c);
+    const float4 s0 = sc4[0], s1 = sc4[1], b0 = sh4[0], b1 = sh4[1];
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = fmaf(__uint_as_float(v[g * 8 + j]), sc[j], sh[j]);
+    if (p.act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+    } else if (p.act == ACT_PRELU) {
+      const float4* sl4 = reinterpret_cast<const float4*>(e.sp + 2 * e.cpad + c);
+      const float4 l0 = sl4[0], l1 = sl4[1];
+      const float sl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = y[j] >= 0.f ? y[j] : y[j] * sl[j];
+    }
+    if (p.res) {
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res + e.rpix * p.res_cs +
+                                                            p.res_coff + c));
+      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(rh[j]);
+        y[2 * j] += f.x;
+        y[2 * j + 1] += f.y;
+      }
+    }
+    if (p.out_f32) {
+      float4* o = reinterpret_cast<float4*>(p.out_f32 + e.pix * p.out_cs + p.out_coff + c);
+      o[0] = make_float4(y[0], y[1], y[2], y[3]);
+      o[1] = make_float4(y[4], y[5], y[6], y[7]);
+    } else {
+      uint4 ov;
+      __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) oh2[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+      *reinterpret_cast<uint4*>(p.out + e.pix * p.out_cs + p.out_coff + c) = ov;
+    }
+    if (p.out2) {
+      const float4* a4 = reinterpret_cast<const float4*>(e.sp + 3 * e.cpad + c);
+      const float4* t4 = reinterpret_cast<const float4*>(e.sp + 4 * e.cpad + c);
+      const float4 a0 = a4[0], a1 = a4[1], t0 = t4[0], t1 = t4[1];
+      const float s2[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float h2[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+      uint4 ov;
+      __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        oh2[j] = __floats2half2_rn(fmaf(y[2 * j], s2[2 * j], h2[2 * j]),
+                                   fmaf(y[2 * j + 1], s2[2 * j + 1], h2[2 * j + 1]));
+      *reinterpret_cast<uint4*>(p.out2 + e.pix * p.out2_cs + p.out2_coff + c) = ov;
+    }
+  }
 }
 
+template <int KSTEPS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Manual 1024-byte alignment (SWIZZLE_128B atoms repeat every 1024 bytes).
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + p.stages * p.stage_bytes;
+  const uint32_t params_s = base + p.stages * p.stage_bytes;
+  const int cpad = p.cout_pad <= kMaxParamChannels ? p.cout_pad : 0;
+  const uint32_t bars = params_s + 5u * cpad * 4u;
   // barrier layout: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
@@ -207,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -216,14 +302,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                  ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp >= 2 && cpad) {
+    // Stage the per-channel epilogue parameters once per CTA.
+    float* sp = reinterpret_cast<float*>(smem_raw + (params_s - smem_u32(smem_raw)));
+    for (int i = threadIdx.x - 64; i < cpad; i += kThreads - 64) {
+      sp[i] = p.scale[i];
+      sp[cpad + i] = p.shift[i];
+      sp[2 * cpad + i] = p.slope ? p.slope[i] : 0.f;
+      sp[3 * cpad + i] = p.scale2 ? p.scale2[i] : 1.f;
+      sp[4 * cpad + i] = p.shift2 ? p.shift2[i] : 0.f;
+    }
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);     // provably warp-uniform
-
-  const int taps = p.kh * p.kw;
 
   // The producer and MMA loops run with the WHOLE warp converged and every
   // operand warp-uniform; one elected lane issues the TMA / tcgen05 instructions.
@@ -234,7 +329,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = p.rows * p.KC * 2 + p.N_tile * p.KC * 2;
+    const uint32_t sub_tx = p.rows * p.KC * 2 + p.N_tile * p.KC * 2;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
@@ -242,58 +337,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int hb = mt % p.tiles_h; mt /= p.tiles_h;
       const int nb = mt;
       const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = nb * p.bn;
-      int tap = 0;
-      for (int r = 0; r < p.kh; ++r) {
-        for (int s = 0; s < p.kw; ++s, ++tap) {
-          // input-space coordinates of this tap
-          int c_base = p.in_coff, cw, ch, c2, c3, c4;
-          if (p.stride == 1) {
-            cw = w0 + s - p.pad; ch = h0 + r - p.pad; c3 = n0; c4 = 0; c2 = ch;
-          } else {
-            const int oy = r - p.pad, ox = s - p.pad;
-            const int py = oy & 1, px = ox & 1;
-            c_base += px * p.in_cs;
-            cw = w0 + ((ox - px) >> 1); c2 = py; c3 = h0 + ((oy - py) >> 1); c4 = n0;
-          }
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
-            const uint32_t sa = base + stage * p.stage_bytes;
-            if (elect_one()) {
-              mbar_expect_tx(full_bar(stage), tx_bytes);
-              tma_load_5d(sa, &tmA, full_bar(stage), c_base + kc * p.KC, cw, c2, c3, c4);
-              tma_load_2d(sa + p.a_bytes, &tmB, full_bar(stage), tap * p.cin_pad + kc * p.KC,
-                          nt * p.N_tile);
+      int r = 0, s = 0, kc = 0, kb = 0;           // running (tap row, tap col, channel chunk)
+      for (int it = 0; it < p.iters; ++it) {
+        const int nsub = min(p.sub, p.k_blocks - kb);
+        mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
+        const uint32_t sa = base + stage * p.stage_bytes;
+        if (p.debug & 1) {
+          if (elect_one()) mbar_arrive(full_bar(stage));
+          kb += nsub;
+        } else {
+          if (elect_one()) mbar_expect_tx(full_bar(stage), sub_tx * nsub);
+          __syncwarp();
+          for (int j = 0; j < nsub; ++j, ++kb) {
+            int c0 = p.in_coff + kc * p.KC, c1, c2, c3, c4;
+            if (p.stride == 1) {
+              c1 = w0 + s - p.pad; c2 = h0 + r - p.pad; c3 = n0; c4 = 0;
+            } else {
+              const int oy = r - p.pad, ox = s - p.pad;
+              const int py = oy & 1, px = ox & 1;
+              c0 += px * p.in_cs;
+              c1 = w0 + ((ox - px) >> 1); c2 = py; c3 = h0 + ((oy - py) >> 1); c4 = n0;
             }
-            __syncwarp();
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            const uint32_t dst = sa + j * p.sub_bytes;
+            if (elect_one()) {
+              tma_load_5d(dst, &tmA, full_bar(stage), c0, c1, c2, c3, c4);
+              tma_load_2d(dst + p.a_bytes, &tmB, full_bar(stage),
+                          (r * p.kw + s) * p.cin_pad + kc * p.KC, nt * p.N_tile);
+            }
+            if (++kc == p.kchunks) { kc = 0; if (++s == p.kw) { s = 0; ++r; } }
           }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    const int ksteps = p.KC / 16;
-    const uint64_t desc_hi = umma_desc(0, p.sbo_bytes, p.layout_type);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1u;
+    int tile_it = 0;
+    const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
+    const uint32_t a_lo0 = umma_desc_lo(base);
+    const uint32_t stage_step = p.stage_bytes >> 4, sub_step = p.sub_bytes >> 4,
+                   b_off = p.a_bytes >> 4;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_it) {
+      const int acc = tile_it & 1;
+      const uint32_t acc_phase = (tile_it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + acc * p.N_tile;
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
+      int kb = 0;
+      uint32_t accumulate = 0;
+      for (int it = 0; it < p.iters; ++it) {
+        const int nsub = min(p.sub, p.k_blocks - kb);
+        kb += nsub;
         mbar_wait(full_bar(stage), phase, p.err, 3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = base + stage * p.stage_bytes;
-        const uint64_t ad = desc_hi | static_cast<uint64_t>((sa & 0x3FFFFu) >> 4);
-        const uint64_t bd = desc_hi | static_cast<uint64_t>(((sa + p.a_bytes) & 0x3FFFFu) >> 4);
         if (elect_one()) {
-          for (int k = 0; k < ksteps; ++k)     // +32 bytes (2 x 16 B) per 16-element K step
-            umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(empty_bar(stage));        // frees the smem slot when the MMAs retire
-          if (kb == p.k_blocks - 1) umma_commit(tfull_bar(acc));
+          uint32_t a_lo = a_lo0 + stage * stage_step;
+          if (!(p.debug & 2)) {
+            for (int j = 0; j < nsub; ++j, a_lo += sub_step) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {      // +32 B (2 x 16 B units) per K step
+                umma_f16(d_tmem, a_lo + 2 * k, a_lo + b_off + 2 * k, desc_hi, p.idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+          }
+          umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
+          if (it == p.iters - 1) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -301,88 +413,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---------------------------------------------------------------- epilogue
+    const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = ew >> 2;               // which 16-column chunks (even / odd) it takes
     const int row = q * 32 + lane;
     const int w_l = row % p.bw;
     const int h_l = (row / p.bw) % p.bh;
     const int n_l = row / (p.bw * p.bh);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1u;
+    const int nchunks = p.N_tile >> 4;
+    EpiCtx e;
+    e.cpad = cpad;
+    e.sp = reinterpret_cast<const float*>(smem_raw + (params_s - smem_u32(smem_raw)));
+    int tile_it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_it) {
+      const int acc = tile_it & 1;
+      const uint32_t acc_phase = (tile_it >> 1) & 1u;
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
       const int wb = mt % p.tiles_w; mt /= p.tiles_w;
       const int hb = mt % p.tiles_h; mt /= p.tiles_h;
       const int nb = mt;
       const int ow = wb * p.bw + w_l, oh = hb * p.bh + h_l, on = nb * p.bn + n_l;
-      const bool valid = row < p.rows && ow < p.W_out && oh < p.H_out && on < p.N;
-      const long pix = (static_cast<long>(on) * p.H_out + oh) * p.W_out + ow;
-      long rpix = pix;
+      e.valid = row < p.rows && ow < p.W_out && oh < p.H_out && on < p.N;
+      e.pix = (static_cast<long>(on) * p.H_out + oh) * p.W_out + ow;
+      e.rpix = e.pix;
       if (p.res && p.res_up2)
-        rpix = (static_cast<long>(on) * p.res_H + (oh >> 1)) * p.res_W + (ow >> 1);
+        e.rpix = (static_cast<long>(on) * p.res_H + (oh >> 1)) * p.res_W + (ow >> 1);
 
       mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.N_tile;
-      for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
-        uint32_t v[16];
-        __syncwarp();                       // tcgen05.ld is warp-collective (.sync.aligned)
-        tmem_ld16(taddr + c0, v);
-        const int cbase = nt * p.N_tile + c0;
-        if (!valid || cbase >= p.cout_store) continue;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int c = cbase + g * 8;
-          if (c >= p.cout_store) break;
-          float y[8];
-          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c));
-          const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c + 4));
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift + c));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.shift + c + 4));
-          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float t = fmaf(__uint_as_float(v[g * 8 + j]), sc[j], sh[j]);
-            const float sl = (p.act == ACT_PRELU) ? __ldg(p.slope + c + j) : 0.f;
-            y[j] = apply_act(t, p.act, sl);
-          }
-          if (p.res) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res + rpix * p.res_cs +
-                                                                  p.res_coff + c));
-            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(rh[j]);
-              y[2 * j] += f.x;
-              y[2 * j + 1] += f.y;
-            }
-          }
-          if (p.out_f32) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.out_cs + p.out_coff + c);
-            o[0] = make_float4(y[0], y[1], y[2], y[3]);
-            o[1] = make_float4(y[4], y[5], y[6], y[7]);
-          } else {
-            uint4 ov;
-            __half2* oh2 = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) oh2[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
-            *reinterpret_cast<uint4*>(p.out + pix * p.out_cs + p.out_coff + c) = ov;
-          }
-          if (p.out2) {
-            uint4 ov;
-            __half2* oh2 = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float a0 = fmaf(y[2 * j], __ldg(p.scale2 + c + 2 * j), __ldg(p.shift2 + c + 2 * j));
-              const float a1 = fmaf(y[2 * j + 1], __ldg(p.scale2 + c + 2 * j + 1),
-                                    __ldg(p.shift2 + c + 2 * j + 1));
-              oh2[j] = __floats2half2_rn(a0, a1);
-            }
-            *reinterpret_cast<uint4*>(p.out2 + pix * p.out2_cs + p.out2_coff + c) = ov;
-          }
-        }
+      const int cn0 = nt * p.N_tile;
+      // software-pipelined TMEM reads: chunk i+2 is in flight while chunk i is stored
+      uint32_t va[16], vb[16];
+      int c = half;
+      __syncwarp();
+      if (c < nchunks) tmem_ld16_async(taddr + c * 16, va);
+      while (c < nchunks) {
+        __syncwarp();                       // tcgen05.ld / wait::ld are warp-collective
+        tmem_ld_wait();
+        if (c + 2 < nchunks) tmem_ld16_async(taddr + (c + 2) * 16, vb);
+        epilogue_chunk(p, e, va, cn0 + c * 16);
+        c += 2;
+        if (c >= nchunks) break;
+        __syncwarp();
+        tmem_ld_wait();
+        if (c + 2 < nchunks) tmem_ld16_async(taddr + (c + 2) * 16, va);
+        epilogue_chunk(p, e, vb, cn0 + c * 16);
+        c += 2;
       }
       // Release the accumulator back to the MMA warp.
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -431,6 +509,19 @@ int num_sms() {
   return n;
 }
 
+using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const TcParams);
+
+KernelFn kernel_for(int kc) {
+  KernelFn fn = kc == 64 ? conv_tc_kernel<4> : (kc == 32 ? conv_tc_kernel<2> : conv_tc_kernel<1>);
+  static bool attr_set[3] = {false, false, false};
+  const int slot = kc == 64 ? 0 : (kc == 32 ? 1 : 2);
+  if (!attr_set[slot]) {
+    TR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[slot] = true;
+  }
+  return fn;
+}
+
 }  // namespace
 
 struct ConvTcPlan {
@@ -449,6 +540,7 @@ bool conv_tc_eligible(const ConvArgs& a) {
   if (a.cin_pad > 64 && a.cin_pad % 64) return false;
   if (a.cin_pad != 16 && a.cin_pad != 32 && a.cin_pad % 64) return false;
   if (a.cout_pad > 256 && a.cout_pad % 256) return false;
+  if (a.cout_pad > kMaxParamChannels) return false;
   return true;
 }
 
@@ -466,6 +558,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   p.in_coff = a.in.coff; p.in_cs = a.in.cs;
   p.N_tile = a.cout_pad > 256 ? 256 : a.cout_pad;
   p.n_tiles = a.cout_pad / p.N_tile;
+  p.cout_pad = a.cout_pad;
 
   // Pick the pixel box {bw, bh, bn} (<= 128 rows) that wastes the fewest MMA rows.
   double best = -1.0;
@@ -487,9 +580,18 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
 
   p.a_bytes = round_up(128 * p.KC * 2, 1024);         // MMA always reads 128 rows
   p.b_bytes = round_up(p.N_tile * p.KC * 2, 1024);
-  p.stage_bytes = p.a_bytes + p.b_bytes;
-  p.stages = std::min(kMaxStages, int(kSmemBudget / p.stage_bytes));
-  p.stages = std::max(2, std::min(p.stages, p.k_blocks + 1));
+  p.sub_bytes = p.a_bytes + p.b_bytes;
+  // k-blocks per ring stage: enough tensor work (>= ~512 cycles = 8 MMAs of N=128) to
+  // cover the single-warp issue latency, within ~64 KB per stage.
+  const int mma_cycles = (p.KC / 16) * std::max(p.N_tile / 2, 8);     // per k-block
+  auto clamp_sub = [&](int v) { return std::max(1, std::min(std::min(kMaxSub, v), p.k_blocks)); };
+  p.sub = clamp_sub(std::min(ceil_div(512, mma_cycles), int(65536 / p.sub_bytes)));
+  if (const char* s = getenv("TRB_TC_SUB")) p.sub = clamp_sub(atoi(s));
+  p.iters = ceil_div(p.k_blocks, p.sub);
+  p.stage_bytes = p.sub * p.sub_bytes;
+  const uint32_t param_bytes = 5u * p.cout_pad * 4u;
+  p.stages = std::min(kMaxStages, int((kSmemBudget - param_bytes) / p.stage_bytes));
+  p.stages = std::max(2, std::min(p.stages, p.iters + 1));
   p.sbo_bytes = 8u * p.KC * 2u;
   CUtensorMapSwizzle swz;
   if (p.KC == 64) { p.layout_type = 2; swz = CU_TENSOR_MAP_SWIZZLE_128B; }
@@ -510,6 +612,8 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   p.res_H = a.res.H; p.res_W = a.res.W;
   p.out_f32 = a.out_f32;
   p.err = tc_error_flag();
+  if (const char* dbg = getenv("TRB_TC_DEBUG")) p.debug = atoi(dbg);
+  TR_CHECK(a.scale && a.shift, "epilogue scale/shift are required");
   TR_CHECK(a.act != ACT_PRELU || a.slope, "PReLU needs slopes");
   TR_CHECK(!a.out2.ptr || (a.scale2 && a.shift2), "second output needs scale2/shift2");
 
@@ -541,14 +645,10 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: " + std::to_string(int(r)));
 
   plan->grid = std::min(p.total_tiles, num_sms());
-  plan->smem = p.stages * p.stage_bytes + 1024 /*alignment*/ + 8 * (2 * kMaxStages + 4) + 16;
+  plan->smem = p.stages * p.stage_bytes + param_bytes + 1024 /*alignment*/ +
+               8 * (2 * kMaxStages + 4) + 16;
   plan->flops = 2.0 * p.N * p.H_out * p.W_out * double(a.cout_pad) * a.kh * a.kw * a.cin_pad;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TR_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 227 * 1024));
-    attr_set = true;
-  }
+  kernel_for(p.KC);
   return plan;
 }
 
@@ -557,7 +657,7 @@ void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
 double conv_tc_plan_flops(const ConvTcPlan* p) { return p->flops; }
 
 void conv_tc_launch(const ConvTcPlan* plan, cudaStream_t s) {
-  conv_tc_kernel<<<plan->grid, kThreads, plan->smem, s>>>(plan->tmA, plan->tmB, plan->p);
+  kernel_for(plan->p.KC)<<<plan->grid, kThreads, plan->smem, s>>>(plan->tmA, plan->tmB, plan->p);
   TR_CUDA(cudaGetLastError());
 }
 
