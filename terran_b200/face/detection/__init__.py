@@ -67,9 +67,14 @@ class Detection:
             frames, offsets = self.merger.merge(resized)
             model = self._model()
 
-        faces = model.call(frames)
-        faces = self.merger.unpad_faces(faces, offsets)
-        faces = round_faces(faces, scales)
+        if offsets is None and not isinstance(scales, list) and hasattr(model, 'call_arrays'):
+            # one scale, no padding: rescale + round the whole batch at once
+            from terran_b200.face.detection.retinaface.wrapper import unpack_detections
+            faces = unpack_detections(*model.call_arrays(frames), scale=scales)
+        else:
+            faces = model.call(frames)
+            faces = self.merger.unpad_faces(faces, offsets)
+            faces = round_faces(faces, scales)
         return faces[0] if single else faces
 
 

@@ -86,30 +86,42 @@ class RetinaFace:
                 return count, cand, det
             max_det = top            # rare: more survivors than rows; redo the select
 
-    def call(self, images, threshold=0.5):
-        """Run the detection.  ``images`` is a (N,H,W,3) uint8 RGB array
-        (numpy, or a CUDA tensor to skip the upload)."""
+    def call_arrays(self, images, threshold=0.5):
+        """``call`` without the per-face dict building: (counts (N,), rows
+        (N,R,16) float32 on the host) — see ``unpack_detections``."""
         with torch.cuda.device(self.device_index):
             frames = to_device_u8(images, self.device_index)
             count, cand, det = self.detect_device(frames, threshold)
             counts = count.cpu().numpy()
-            self.last_candidates = cand.cpu().numpy()
+            self.last_candidates = cand
             top = int(counts.max()) if len(counts) else 0
             rows = det[:, :max(top, 1)].cpu().numpy()
-        return unpack_detections(counts, rows)
+        return counts, rows
+
+    def call(self, images, threshold=0.5):
+        """Run the detection.  ``images`` is a (N,H,W,3) uint8 RGB array
+        (numpy, or a CUDA tensor to skip the upload)."""
+        return unpack_detections(*self.call_arrays(images, threshold))
 
 
-def unpack_detections(counts, rows):
-    """(N,) counts + (N,R,16) rows -> the reference's list of lists of dicts."""
-    batch = []
-    for n, k in enumerate(counts):
-        r = rows[n, :k]
-        batch.append([
-            {'bbox': r[i, 1:5].copy(), 'landmarks': r[i, 5:15].reshape(5, 2).copy(),
-             'score': r[i, 0]}
-            for i in range(k)
-        ])
-    return batch
+def unpack_detections(counts, rows, scale=None):
+    """(N,) counts + (N,R,16) rows -> the reference's list of lists of dicts.
+    With ``scale`` the coordinates are mapped back to input pixels exactly like
+    ``Detection.resize_out`` (detection/__init__.py:59-84): float32 value /
+    python-float scale, round half to even, int32 — done once on the whole
+    batch instead of per face."""
+    scores = np.ascontiguousarray(rows[..., 0])
+    coords = rows[..., 1:15]
+    if scale is not None:
+        coords = np.around(coords / scale).astype(np.int32)
+    else:
+        coords = np.ascontiguousarray(coords)
+    boxes = coords[..., :4]
+    lmks = coords[..., 4:].reshape(coords.shape[0], coords.shape[1], 5, 2)
+    return [
+        [{'bbox': boxes[n, i], 'landmarks': lmks[n, i], 'score': scores[n, i]} for i in range(k)]
+        for n, k in enumerate(counts)
+    ]
 
 
 def decode_nms(heads, H, W, threshold=0.5, nms_threshold=0.4, max_det=None):

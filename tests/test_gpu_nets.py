@@ -171,6 +171,32 @@ def test_openpose_maps(native, opose, golden, mode):
     assert np.abs(heat.cpu().numpy() - g['heat']).max() <= 4e-3
 
 
+def test_streaming_pipeline_matches_sequential_calls(native, retina, opose):
+    """FrameFeeder + PerceptionPipeline (prefetched uploads, detect and pose on
+    two streams) return exactly what the plain sequential calls return."""
+    from terran_b200.face.detection import Detection
+    from terran_b200.pipeline import FrameFeeder, PerceptionPipeline
+    from terran_b200.pose import Estimation
+    det = Detection(device=torch.device('cuda'), lazy=True)
+    det.model = retina[0]
+    est = Estimation(device=torch.device('cuda'), lazy=True)
+    est.model = opose[0]
+    rng = np.random.default_rng(8)
+    batches = [rng.integers(0, 256, (3, 270, 480, 3), dtype=np.uint8) for _ in range(4)]
+    want = [(det(b), est(b)) for b in batches]
+    pipe = PerceptionPipeline(det, est, device=torch.device('cuda'))
+    got = [pipe(frames) for frames in FrameFeeder(batches, device=torch.device('cuda'))]
+    pipe.close()
+    assert len(got) == len(want)
+    for (f_got, p_got), (f_want, p_want) in zip(got, want):
+        assert [len(f) for f in f_got] == [len(f) for f in f_want]
+        for a, b in zip(sum(f_got, []), sum(f_want, [])):
+            np.testing.assert_array_equal(a['bbox'], b['bbox'])
+            np.testing.assert_array_equal(a['landmarks'], b['landmarks'])
+            assert a['score'] == b['score']
+        assert [len(p) for p in p_got] == [len(p) for p in p_want]
+
+
 def test_estimation_wrapper(native, opose):
     """Estimation on 720p noise frames: runs end to end through the public API
     (random weights give no peaks above 0.1 -> no humans, like the reference)."""
