@@ -114,64 +114,107 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) 
 
 // ------------------------------------------------------------------ u8 stems
 // 3x3, pad 1, 3 input channels read straight from the u8 frame (any strides,
-// any channel order: the BGR flip of the reference is folded into the packed
-// weights).  x' = x*in_scale + in_shift is applied to IN-BOUNDS taps only, so
+// any channel order: the BGR flip of the reference is a negative channel
+// stride).  x' = x*in_scale + in_shift is applied to IN-BOUNDS taps only, so
 // the zero padding sees zeros exactly like the reference (which pads after the
-// affine).  One thread = one output pixel, all COUT channels.
-template <int COUT>
+// affine).  Register-blocked: one thread = 4 consecutive output pixels x all
+// COUT channels (16 at a time), so each smem weight vector feeds 4 pixels.
+template <int COUT, int STRIDE>
 __global__ void __launch_bounds__(128) stem_kernel(const StemArgs a, int H_out, int W_out) {
-  __shared__ float sw[27 * COUT];
+  constexpr int PX = 4;
+  constexpr int COLS = (PX - 1) * STRIDE + 3;
+  constexpr int CB = COUT < 16 ? COUT : 16;          // couts per register block
+  __shared__ __align__(16) float sw[27 * COUT];
+  __shared__ float sp[5 * COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
-    // packed as [cout][kh][kw][c]; stored transposed [tap*3+c][cout] for broadcast reads
+    // packed as [cout][kh][kw][c]; stored transposed [tap*3+c][cout] for vector reads
     const int o = i / 27, t = i % 27;
     sw[t * COUT + o] = a.w[i];
   }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+    sp[i] = a.scale[i];
+    sp[COUT + i] = a.shift[i];
+    sp[2 * COUT + i] = a.slope ? a.slope[i] : 0.f;
+    sp[3 * COUT + i] = a.scale2 ? a.scale2[i] : 1.f;
+    sp[4 * COUT + i] = a.shift2 ? a.shift2[i] : 0.f;
+  }
   __syncthreads();
-  const long npix = static_cast<long>(a.N) * H_out * W_out;
-  const long pix = blockIdx.x * 128L + threadIdx.x;
-  if (pix >= npix) return;
-  const int ow = pix % W_out;
-  const int oh = (pix / W_out) % H_out;
-  const int on = pix / (static_cast<long>(W_out) * H_out);
-  float acc[COUT];
+  const int wq = (W_out + PX - 1) / PX;
+  const long nthreads = static_cast<long>(a.N) * H_out * wq;
+  const long tid = blockIdx.x * 128L + threadIdx.x;
+  if (tid >= nthreads) return;
+  const int ow0 = static_cast<int>(tid % wq) * PX;
+  const int oh = (tid / wq) % H_out;
+  const int on = tid / (static_cast<long>(wq) * H_out);
+
+  float x[3][COLS][3];
 #pragma unroll
-  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
   for (int r = 0; r < 3; ++r) {
-    const int ih = oh * a.stride + r - 1;
-    if (ih < 0 || ih >= a.H) continue;
-    for (int s = 0; s < 3; ++s) {
-      const int iw = ow * a.stride + s - 1;
-      if (iw < 0 || iw >= a.W) continue;
-      const uint8_t* ip = a.in + on * a.sn + ih * a.sh + iw * a.sw;
+    const int ih = oh * STRIDE + r - 1;
+    const bool rok = ih >= 0 && ih < a.H;
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const float x = fmaf(static_cast<float>(ip[ch * a.sc]), a.in_scale, a.in_shift);
-        const float* wrow = sw + ((r * 3 + s) * 3 + ch) * COUT;
+    for (int c = 0; c < COLS; ++c) {
+      const int iw = ow0 * STRIDE + c - 1;
+      const bool ok = rok && iw >= 0 && iw < a.W;
+      const uint8_t* ip = a.in + on * a.sn + (ok ? ih : 0) * a.sh + (ok ? iw : 0) * a.sw;
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(x, wrow[o], acc[o]);
-      }
+      for (int ch = 0; ch < 3; ++ch)
+        x[r][c][ch] = ok ? fmaf(static_cast<float>(ip[ch * a.sc]), a.in_scale, a.in_shift) : 0.f;
     }
   }
-  __half* op = a.out.ptr + pix * a.out.cs + a.out.coff;
-  __half* op2 = a.out2.ptr ? a.out2.ptr + pix * a.out2.cs + a.out2.coff : nullptr;
+  const long pix0 = (static_cast<long>(on) * H_out + oh) * W_out + ow0;
+#pragma unroll 1
+  for (int o0 = 0; o0 < COUT; o0 += CB) {
+    float acc[PX][CB];
 #pragma unroll
-  for (int o = 0; o < COUT; o += 8) {
-    uint4 ov, ov2;
-    __half2* h = reinterpret_cast<__half2*>(&ov);
-    __half2* h2 = reinterpret_cast<__half2*>(&ov2);
+    for (int p = 0; p < PX; ++p)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float y0 = fmaf(acc[o + 2 * j], a.scale[o + 2 * j], a.shift[o + 2 * j]);
-      float y1 = fmaf(acc[o + 2 * j + 1], a.scale[o + 2 * j + 1], a.shift[o + 2 * j + 1]);
-      y0 = act_f(y0, a.act, a.act == ACT_PRELU ? a.slope[o + 2 * j] : 0.f);
-      y1 = act_f(y1, a.act, a.act == ACT_PRELU ? a.slope[o + 2 * j + 1] : 0.f);
-      h[j] = __floats2half2_rn(y0, y1);
-      if (op2)
-        h2[j] = __floats2half2_rn(fmaf(y0, a.scale2[o + 2 * j], a.shift2[o + 2 * j]),
-                                  fmaf(y1, a.scale2[o + 2 * j + 1], a.shift2[o + 2 * j + 1]));
+      for (int j = 0; j < CB; ++j) acc[p][j] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float4* wv = reinterpret_cast<const float4*>(sw + ((r * 3 + s) * 3 + ch) * COUT + o0);
+          float w[CB];
+#pragma unroll
+          for (int j = 0; j < CB / 4; ++j) {
+            const float4 t = wv[j];
+            w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
+          }
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            const float xv = x[r][p * STRIDE + s][ch];
+#pragma unroll
+            for (int j = 0; j < CB; ++j) acc[p][j] = fmaf(xv, w[j], acc[p][j]);
+          }
+        }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      if (ow0 + p >= W_out) break;
+      __half* op = a.out.ptr + (pix0 + p) * a.out.cs + a.out.coff + o0;
+      __half* op2 = a.out2.ptr ? a.out2.ptr + (pix0 + p) * a.out2.cs + a.out2.coff + o0 : nullptr;
+#pragma unroll
+      for (int g = 0; g < CB; g += 8) {
+        uint4 ov, ov2;
+        __half2* h = reinterpret_cast<__half2*>(&ov);
+        __half2* h2 = reinterpret_cast<__half2*>(&ov2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = o0 + g + 2 * j;
+          float y0 = fmaf(acc[p][g + 2 * j], sp[c0], sp[COUT + c0]);
+          float y1 = fmaf(acc[p][g + 2 * j + 1], sp[c0 + 1], sp[COUT + c0 + 1]);
+          y0 = act_f(y0, a.act, sp[2 * COUT + c0]);
+          y1 = act_f(y1, a.act, sp[2 * COUT + c0 + 1]);
+          h[j] = __floats2half2_rn(y0, y1);
+          h2[j] = __floats2half2_rn(fmaf(y0, sp[3 * COUT + c0], sp[4 * COUT + c0]),
+                                    fmaf(y1, sp[3 * COUT + c0 + 1], sp[4 * COUT + c0 + 1]));
+        }
+        *reinterpret_cast<uint4*>(op + g) = ov;
+        if (op2) *reinterpret_cast<uint4*>(op2 + g) = ov2;
+      }
     }
-    *reinterpret_cast<uint4*>(op + o) = ov;
-    if (op2) *reinterpret_cast<uint4*>(op2 + o) = ov2;
   }
 }
 
@@ -371,11 +414,11 @@ void conv_direct_launch(const ConvArgs& a, cudaStream_t s) {
 
 void stem_launch(const StemArgs& a, cudaStream_t s) {
   const int H_out = (a.H + 2 - 3) / a.stride + 1, W_out = (a.W + 2 - 3) / a.stride + 1;
-  const long npix = static_cast<long>(a.N) * H_out * W_out;
-  const unsigned grid = static_cast<unsigned>((npix + 127) / 128);
-  if (a.cout == 8) stem_kernel<8><<<grid, 128, 0, s>>>(a, H_out, W_out);
-  else if (a.cout == 64) stem_kernel<64><<<grid, 128, 0, s>>>(a, H_out, W_out);
-  else fail("stem conv supports 8 or 64 output channels");
+  const long nthreads = static_cast<long>(a.N) * H_out * ((W_out + 3) / 4);
+  const unsigned grid = static_cast<unsigned>((nthreads + 127) / 128);
+  if (a.cout == 8 && a.stride == 2) stem_kernel<8, 2><<<grid, 128, 0, s>>>(a, H_out, W_out);
+  else if (a.cout == 64 && a.stride == 1) stem_kernel<64, 1><<<grid, 128, 0, s>>>(a, H_out, W_out);
+  else fail("stem conv supports (8 channels, stride 2) or (64 channels, stride 1)");
   TR_CUDA(cudaGetLastError());
 }
 

@@ -69,6 +69,10 @@ struct TcParams {
   float* out_f32;
   int* err;   // device flag set on a pipeline timeout
   int debug;  // timing experiments only: 1 = skip TMA loads, 2 = skip MMAs (results are garbage)
+  // halo mode: the input patch of a tile (+ filter halo) is loaded ONCE per channel chunk and
+  // every tap's A operand is a shifted UMMA descriptor into it.  1: tile 8w x 16h, 2: 16w x 8h.
+  int halo, halo_base_mode, taps, iters_kc;
+  uint32_t patch_bytes, patch_tx, ring_off;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -157,18 +161,19 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) {
   return ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
 }
 
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
-                                         uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                         uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       ".reg .b64 da, db;\n"
-      "mov.b64 da, {%1, %3};\n"
-      "mov.b64 db, {%2, %3};\n"
-      "setp.ne.b32 p, %5, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
       "}\n"
-      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -271,7 +276,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Manual 1024-byte alignment (SWIZZLE_128B atoms repeat every 1024 bytes).
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t params_s = base + p.stages * p.stage_bytes;
+  const uint32_t ring = base + p.ring_off;              // halo mode: two patch buffers come first
+  const uint32_t params_s = ring + p.stages * p.stage_bytes;
   const int cpad = p.cout_pad <= kMaxParamChannels ? p.cout_pad : 0;
   const uint32_t bars = params_s + 5u * cpad * 4u;
   // barrier layout: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tmem_ptr
@@ -280,6 +286,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
+  auto pfull_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 6 + b); };
+  auto pempty_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 8 + b); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -294,6 +302,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiWarps);
+      mbar_init(pfull_bar(a), 1);
+      mbar_init(pempty_bar(a), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -327,8 +337,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // ~240 cycles per tcgen05.mma, 4x the MMA's own execution time.)
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, pb = 0;
+    uint32_t phase = 0, pphase = 0;
     const uint32_t sub_tx = p.rows * p.KC * 2 + p.N_tile * p.KC * 2;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
@@ -337,11 +347,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int hb = mt % p.tiles_h; mt /= p.tiles_h;
       const int nb = mt;
       const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = nb * p.bn;
+      if (p.halo) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(pempty_bar(pb), pphase ^ 1u, p.err, 5);
+          if (elect_one()) {
+            mbar_expect_tx(pfull_bar(pb), p.patch_tx);
+            const int cw = w0 - p.pad, ch = h0 - p.pad;
+            tma_load_5d(base + pb * p.patch_bytes, &tmA, pfull_bar(pb), p.in_coff + kc * p.KC,
+                        p.halo == 1 ? cw : ch, p.halo == 1 ? ch : cw, n0, 0);
+          }
+          __syncwarp();
+          int tap = 0;
+          for (int it = 0; it < p.iters_kc; ++it) {
+            const int nsub = min(p.sub, p.taps - tap);
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
+            const uint32_t sb = ring + stage * p.stage_bytes;
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(stage), nsub * p.N_tile * p.KC * 2);
+              for (int j = 0; j < nsub; ++j)
+                tma_load_2d(sb + j * p.b_bytes, &tmB, full_bar(stage),
+                            (tap + j) * p.cin_pad + kc * p.KC, nt * p.N_tile);
+            }
+            __syncwarp();
+            tap += nsub;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          if (++pb == 2) { pb = 0; pphase ^= 1u; }
+        }
+        continue;
+      }
       int r = 0, s = 0, kc = 0, kb = 0;           // running (tap row, tap col, channel chunk)
       for (int it = 0; it < p.iters; ++it) {
         const int nsub = min(p.sub, p.k_blocks - kb);
         mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
-        const uint32_t sa = base + stage * p.stage_bytes;
+        const uint32_t sa = ring + stage * p.stage_bytes;
         if (p.debug & 1) {
           if (elect_one()) mbar_arrive(full_bar(stage));
           kb += nsub;
@@ -373,11 +412,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, pb = 0;
+    uint32_t phase = 0, pphase = 0;
     int tile_it = 0;
     const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
-    const uint32_t a_lo0 = umma_desc_lo(base);
+    const uint32_t halo_hi = umma_desc_hi(2048, p.layout_type);   // 16 patch rows per 8-row group step
+    const uint32_t a_lo0 = umma_desc_lo(ring);
     const uint32_t stage_step = p.stage_bytes >> 4, sub_step = p.sub_bytes >> 4,
                    b_off = p.a_bytes >> 4;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_it) {
@@ -388,6 +428,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t d_tmem = tmem_base + acc * p.N_tile;
       int kb = 0;
       uint32_t accumulate = 0;
+      if (p.halo) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(pfull_bar(pb), pphase, p.err, 6);
+          const uint32_t patch = base + pb * p.patch_bytes;
+          int tap = 0;
+          for (int it = 0; it < p.iters_kc; ++it) {
+            const int nsub = min(p.sub, p.taps - tap);
+            mbar_wait(full_bar(stage), phase, p.err, 3);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+              const uint32_t b_lo0 = a_lo0 + stage * stage_step;
+              for (int j = 0; j < nsub; ++j) {
+                const int t = tap + j, r = t / p.kw, s = t - r * p.kw;
+                const uint32_t rows_off = p.halo == 1 ? r * 16 + s : s * 16 + r;
+                const uint32_t a_start = patch + rows_off * 128u;
+                const uint32_t a_lo = umma_desc_lo(a_start);
+                const uint32_t a_hi = halo_hi | (p.halo_base_mode ? ((a_start >> 7) & 7u) << 17 : 0u);
+                const uint32_t b_lo = b_lo0 + j * (p.b_bytes >> 4);
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                  umma_f16(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, desc_hi, p.idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit(empty_bar(stage));
+              if (it == p.iters_kc - 1) {
+                umma_commit(pempty_bar(pb));
+                if (kc == p.kchunks - 1) umma_commit(tfull_bar(acc));
+              }
+            }
+            __syncwarp();
+            tap += nsub;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          if (++pb == 2) { pb = 0; pphase ^= 1u; }
+        }
+        continue;
+      }
       for (int it = 0; it < p.iters; ++it) {
         const int nsub = min(p.sub, p.k_blocks - kb);
         kb += nsub;
@@ -399,7 +477,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < nsub; ++j, a_lo += sub_step) {
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {      // +32 B (2 x 16 B units) per K step
-                umma_f16(d_tmem, a_lo + 2 * k, a_lo + b_off + 2 * k, desc_hi, p.idesc, accumulate);
+                umma_f16(d_tmem, a_lo + 2 * k, desc_hi, a_lo + b_off + 2 * k, desc_hi, p.idesc, accumulate);
                 accumulate = 1;
               }
             }
@@ -417,9 +495,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = ew >> 2;               // which 16-column chunks (even / odd) it takes
     const int row = q * 32 + lane;
-    const int w_l = row % p.bw;
-    const int h_l = (row / p.bw) % p.bh;
-    const int n_l = row / (p.bw * p.bh);
+    // halo == 2: MMA row m = (w_l, h_l) with h_l fastest (16w x 8h tile)
+    const int w_l = p.halo == 2 ? row >> 3 : row % p.bw;
+    const int h_l = p.halo == 2 ? row & 7 : (row / p.bw) % p.bh;
+    const int n_l = p.halo == 2 ? 0 : row / (p.bw * p.bh);
     const int nchunks = p.N_tile >> 4;
     EpiCtx e;
     e.cpad = cpad;
@@ -572,6 +651,31 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
       }
     }
   }
+  // Halo mode (stride-1 KxK, 64-channel chunks): tile 8x16 or 16x8 pixels, the input patch
+  // incl. filter halo is 16 pixels along the 8-pixel axis so an 8-row UMMA group never
+  // straddles a patch row and the group stride (SBO) is a whole swizzle repeat (2048 B).
+  p.taps = a.kh * a.kw;
+  {
+    int want = 0;                                   // 0 off, 1 / 2 forced orientation, 3 auto
+    if (const char* h = getenv("TRB_TC_HALO")) want = atoi(h);
+    const bool ok = a.stride == 1 && p.KC == 64 && a.kh == a.kw && a.kh >= 3 && a.pad == a.kh / 2 &&
+                    8 + 2 * a.pad <= 16;
+    if (want && ok) {
+      const long t1 = long(ceil_div(p.W_out, 8)) * ceil_div(p.H_out, 16) * p.N;
+      const long t2 = long(ceil_div(p.W_out, 16)) * ceil_div(p.H_out, 8) * p.N;
+      const long t0 = long(ceil_div(p.W_out, p.bw)) * ceil_div(p.H_out, p.bh) * ceil_div(p.N, p.bn);
+      int mode = want == 3 ? (t2 < t1 ? 2 : 1) : want;
+      const long th = mode == 1 ? t1 : t2;
+      const int sms = num_sms();
+      const bool worth = (a.cin_pad <= 128 || a.kh >= 5) &&
+                         ceil_div(int(th * p.n_tiles), sms) * 100 <= ceil_div(int(t0 * p.n_tiles), sms) * 115;
+      if (want != 3 || worth) {
+        p.halo = mode;
+        p.bw = mode == 1 ? 8 : 16; p.bh = mode == 1 ? 16 : 8; p.bn = 1;
+      }
+    }
+    if (const char* h = getenv("TRB_TC_HALO_BASE")) p.halo_base_mode = atoi(h);
+  }
   p.rows = p.bw * p.bh * p.bn;
   p.tiles_w = ceil_div(p.W_out, p.bw);
   p.tiles_h = ceil_div(p.H_out, p.bh);
@@ -580,18 +684,25 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
 
   p.a_bytes = round_up(128 * p.KC * 2, 1024);         // MMA always reads 128 rows
   p.b_bytes = round_up(p.N_tile * p.KC * 2, 1024);
-  p.sub_bytes = p.a_bytes + p.b_bytes;
+  p.sub_bytes = p.halo ? p.b_bytes : p.a_bytes + p.b_bytes;
   // k-blocks per ring stage: enough tensor work (>= ~512 cycles = 8 MMAs of N=128) to
   // cover the single-warp issue latency, within ~64 KB per stage.
   const int mma_cycles = (p.KC / 16) * std::max(p.N_tile / 2, 8);     // per k-block
-  auto clamp_sub = [&](int v) { return std::max(1, std::min(std::min(kMaxSub, v), p.k_blocks)); };
+  const int k_per_group = p.halo ? p.taps : p.k_blocks;
+  auto clamp_sub = [&](int v) { return std::max(1, std::min(std::min(kMaxSub, v), k_per_group)); };
   p.sub = clamp_sub(std::min(ceil_div(512, mma_cycles), int(65536 / p.sub_bytes)));
   if (const char* s = getenv("TRB_TC_SUB")) p.sub = clamp_sub(atoi(s));
   p.iters = ceil_div(p.k_blocks, p.sub);
+  p.iters_kc = ceil_div(p.taps, p.sub);
   p.stage_bytes = p.sub * p.sub_bytes;
   const uint32_t param_bytes = 5u * p.cout_pad * 4u;
-  p.stages = std::min(kMaxStages, int((kSmemBudget - param_bytes) / p.stage_bytes));
-  p.stages = std::max(2, std::min(p.stages, p.iters + 1));
+  if (p.halo) {
+    p.patch_tx = (16 + 2 * a.pad) * 16 * 128;
+    p.patch_bytes = round_up(p.patch_tx, 1024);
+    p.ring_off = 2 * p.patch_bytes;
+  }
+  p.stages = std::min(kMaxStages, int((kSmemBudget - param_bytes - p.ring_off) / p.stage_bytes));
+  p.stages = std::max(2, std::min(p.stages, (p.halo ? p.iters_kc * p.kchunks : p.iters) + 1));
   p.sbo_bytes = 8u * p.KC * 2u;
   CUtensorMapSwizzle swz;
   if (p.KC == 64) { p.layout_type = 2; swz = CU_TENSOR_MAP_SWIZZLE_128B; }
@@ -622,10 +733,15 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   const cuuint64_t cs = a.in.cs, W = a.in.W, H = a.in.H, N = a.in.N;
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
-  if (a.stride == 1) {
+  if (p.halo == 2) {        // dims (C, H, W, N): patch rows run along H
+    gdim[0] = cs; gdim[1] = H; gdim[2] = W; gdim[3] = N; gdim[4] = 1;
+    gstr[0] = W * cs * 2; gstr[1] = cs * 2; gstr[2] = H * W * cs * 2; gstr[3] = N * H * W * cs * 2;
+    box[0] = p.KC; box[1] = 16; box[2] = 16 + 2 * a.pad; box[3] = 1; box[4] = 1;
+  } else if (a.stride == 1) {
     gdim[0] = cs; gdim[1] = W; gdim[2] = H; gdim[3] = N; gdim[4] = 1;
     gstr[0] = cs * 2; gstr[1] = W * cs * 2; gstr[2] = H * W * cs * 2; gstr[3] = N * H * W * cs * 2;
     box[0] = p.KC; box[1] = p.bw; box[2] = p.bh; box[3] = p.bn; box[4] = 1;
+    if (p.halo == 1) { box[1] = 16; box[2] = 16 + 2 * a.pad; box[3] = 1; }
   } else {
     gdim[0] = 2 * cs; gdim[1] = W / 2; gdim[2] = 2; gdim[3] = H / 2; gdim[4] = N;
     gstr[0] = 2 * cs * 2; gstr[1] = W * cs * 2; gstr[2] = 2 * W * cs * 2; gstr[3] = H * W * cs * 2;
@@ -645,8 +761,8 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: " + std::to_string(int(r)));
 
   plan->grid = std::min(p.total_tiles, num_sms());
-  plan->smem = p.stages * p.stage_bytes + param_bytes + 1024 /*alignment*/ +
-               8 * (2 * kMaxStages + 4) + 16;
+  plan->smem = p.ring_off + p.stages * p.stage_bytes + param_bytes + 1024 /*alignment*/ +
+               8 * (2 * kMaxStages + 10) + 16;
   plan->flops = 2.0 * p.N * p.H_out * p.W_out * double(a.cout_pad) * a.kh * a.kw * a.cin_pad;
   kernel_for(p.KC);
   return plan;
