@@ -412,81 +412,109 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
+    // The tensor pipe queues only one or two tcgen05.mma (measured: the issuing
+    // thread runs in lock-step with it), so every cycle between the last MMA of one
+    // ring iteration and the first MMA of the next is a pipe bubble.  The loop is
+    // therefore software-pipelined: all but the last MMA of an iteration are issued,
+    // then the barrier wait for the NEXT iteration's data runs while the pipe drains,
+    // then the last MMA and the commits go out.
     int stage = 0, pb = 0;
     uint32_t phase = 0, pphase = 0;
     int tile_it = 0;
     const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
-    const uint32_t halo_hi = umma_desc_hi(2048, p.layout_type);   // 16 patch rows per 8-row group step
-    const uint32_t a_lo0 = umma_desc_lo(ring);
+    const uint32_t halo_hi = umma_desc_hi(2048, p.layout_type);   // 16 patch rows per 8-row group
+    const uint32_t ring_lo = umma_desc_lo(ring);
     const uint32_t stage_step = p.stage_bytes >> 4, sub_step = p.sub_bytes >> 4,
-                   b_off = p.a_bytes >> 4;
+                   b_off = p.halo ? 0u : (p.a_bytes >> 4);
+    const int total_iters = p.halo ? p.kchunks * p.iters_kc : p.iters;
+    const bool skip_mma = (p.debug & 2) != 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_it) {
       const int acc = tile_it & 1;
       const uint32_t acc_phase = (tile_it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + acc * p.N_tile;
-      int kb = 0;
-      uint32_t accumulate = 0;
-      if (p.halo) {
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(pfull_bar(pb), pphase, p.err, 6);
-          const uint32_t patch = base + pb * p.patch_bytes;
-          int tap = 0;
-          for (int it = 0; it < p.iters_kc; ++it) {
-            const int nsub = min(p.sub, p.taps - tap);
-            mbar_wait(full_bar(stage), phase, p.err, 3);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-              const uint32_t b_lo0 = a_lo0 + stage * stage_step;
-              for (int j = 0; j < nsub; ++j) {
-                const int t = tap + j, r = t / p.kw, s = t - r * p.kw;
-                const uint32_t rows_off = p.halo == 1 ? r * 16 + s : s * 16 + r;
-                const uint32_t a_start = patch + rows_off * 128u;
-                const uint32_t a_lo = umma_desc_lo(a_start);
-                const uint32_t a_hi = halo_hi | (p.halo_base_mode ? ((a_start >> 7) & 7u) << 17 : 0u);
-                const uint32_t b_lo = b_lo0 + j * (p.b_bytes >> 4);
-#pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) {
-                  umma_f16(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, desc_hi, p.idesc, accumulate);
-                  accumulate = 1;
-                }
-              }
-              umma_commit(empty_bar(stage));
-              if (it == p.iters_kc - 1) {
-                umma_commit(pempty_bar(pb));
-                if (kc == p.kchunks - 1) umma_commit(tfull_bar(acc));
-              }
-            }
-            __syncwarp();
-            tap += nsub;
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-          }
-          if (++pb == 2) { pb = 0; pphase ^= 1u; }
-        }
-        continue;
-      }
-      for (int it = 0; it < p.iters; ++it) {
-        const int nsub = min(p.sub, p.k_blocks - kb);
-        kb += nsub;
-        mbar_wait(full_bar(stage), phase, p.err, 3);
+      int kb = 0;                       // plain mode: k-blocks consumed
+      int it_kc = 0, tap = 0, tr = 0, ts = 0;   // halo mode: position inside the channel chunk
+      if (p.halo) mbar_wait(pfull_bar(pb), pphase, p.err, 6);
+      mbar_wait(full_bar(stage), phase, p.err, 3);
+      for (int it = 0; it < total_iters; ++it) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-          uint32_t a_lo = a_lo0 + stage * stage_step;
-          if (!(p.debug & 2)) {
-            for (int j = 0; j < nsub; ++j, a_lo += sub_step) {
+        const int left = p.halo ? p.taps - tap : p.k_blocks - kb;
+        const int nsub = min(p.sub, left);
+        // descriptors of this iteration's k-blocks (warp-uniform)
+        uint32_t a_lo[kMaxSub], b_lo[kMaxSub];
+        const uint32_t st_lo = ring_lo + stage * stage_step;
+        if (p.halo) {
+          const uint32_t patch = base + pb * p.patch_bytes;
+          int r = tr, c = ts;
+#pragma unroll
+          for (int j = 0; j < kMaxSub; ++j) {
+            const uint32_t rows_off = p.halo == 1 ? r * 16 + c : c * 16 + r;
+            a_lo[j] = umma_desc_lo(patch + rows_off * 128u);
+            b_lo[j] = st_lo + j * sub_step;
+            if (++c == p.kw) { c = 0; ++r; }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kMaxSub; ++j) {
+            a_lo[j] = st_lo + j * sub_step;
+            b_lo[j] = a_lo[j] + b_off;
+          }
+        }
+        const uint32_t a_hi = p.halo ? halo_hi : desc_hi;
+        const uint32_t acc_in = it > 0 ? 1u : 0u;
+        if (elect_one() && !skip_mma) {
+#pragma unroll
+          for (int j = 0; j < kMaxSub; ++j) {
+            if (j < nsub) {
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {      // +32 B (2 x 16 B units) per K step
-                umma_f16(d_tmem, a_lo + 2 * k, desc_hi, a_lo + b_off + 2 * k, desc_hi, p.idesc, accumulate);
-                accumulate = 1;
+                if (j == nsub - 1 && k == KSTEPS - 1) break;      // held back, see below
+                umma_f16(d_tmem, a_lo[j] + 2 * k, a_hi, b_lo[j] + 2 * k, desc_hi, p.idesc,
+                         acc_in | uint32_t(j | k));
               }
             }
           }
-          umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
-          if (it == p.iters - 1) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        // ---- bookkeeping for the next iteration + wait for its data (pipe is busy meanwhile)
+        const bool last = it == total_iters - 1;
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == p.stages) { nstage = 0; nphase ^= 1u; }
+        bool end_kc = false;
+        int npb = pb;
+        uint32_t npphase = pphase;
+        if (p.halo) {
+          tap += nsub;
+          ts += nsub;
+          while (ts >= p.kw) { ts -= p.kw; ++tr; }
+          if (++it_kc == p.iters_kc) {
+            end_kc = true;
+            it_kc = 0; tap = 0; tr = 0; ts = 0;
+            if (++npb == 2) { npb = 0; npphase ^= 1u; }
+          }
+        } else {
+          kb += nsub;
+        }
+        if (!last) {
+          if (end_kc) mbar_wait(pfull_bar(npb), npphase, p.err, 6);
+          mbar_wait(full_bar(nstage), nphase, p.err, 3);
+        }
+        uint32_t a_last = a_lo[0], b_last = b_lo[0];
+#pragma unroll
+        for (int j = 1; j < kMaxSub; ++j)
+          if (j < nsub) { a_last = a_lo[j]; b_last = b_lo[j]; }
+        if (elect_one()) {
+          if (!skip_mma)
+            umma_f16(d_tmem, a_last + 2 * (KSTEPS - 1), a_hi, b_last + 2 * (KSTEPS - 1),
+                     desc_hi, p.idesc, acc_in | uint32_t((nsub - 1) | (KSTEPS - 1)));
+          umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
+          if (end_kc) umma_commit(pempty_bar(pb));
+          if (last) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        stage = nstage; phase = nphase; pb = npb; pphase = npphase;
       }
     }
   } else {
