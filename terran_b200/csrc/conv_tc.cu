@@ -37,8 +37,10 @@ namespace trb {
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kMmaWarps = 2;                 // alternate ring iterations, see the MMA role
+constexpr int kFirstEpiWarp = 1 + kMmaWarps;
 constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
 constexpr int kMaxStages = 8;
 constexpr int kMaxSub = 4;
 constexpr uint32_t kSmemBudget = 196 * 1024;
@@ -68,7 +70,7 @@ struct TcParams {
   const __half* res; int res_cs, res_coff, res_up2, res_H, res_W;
   float* out_f32;
   int* err;   // device flag set on a pipeline timeout
-  int debug;  // timing experiments only: 1 = skip TMA loads, 2 = skip MMAs (results are garbage)
+  int debug;  // timing experiments only: 1 skip TMA loads, 2 skip MMAs, 4 skip epilogue stores, 8 skip epilogue
   // halo mode: the input patch of a tile (+ filter halo) is loaded ONCE per channel chunk and
   // every tap's A operand is a shifted UMMA descriptor into it.  1: tile 8w x 16h, 2: 16w x 8h.
   int halo, halo_base_mode, taps, iters_kc;
@@ -207,7 +209,7 @@ struct EpiCtx {
 // Scale/shift/activation/residual/store of 16 consecutive output channels.
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiCtx& e,
                                                const uint32_t (&v)[16], int cbase) {
-  if (!e.valid || cbase >= p.cout_store) return;
+  if (!e.valid || cbase >= p.cout_store || (p.debug & 8)) return;
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const int c = cbase + g * 8;
@@ -241,6 +243,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiCtx& 
         y[2 * j + 1] += f.y;
       }
     }
+    if (p.debug & 4) continue;
     if (p.out_f32) {
       float4* o = reinterpret_cast<float4*>(p.out_f32 + e.pix * p.out_cs + p.out_coff + c);
       o[0] = make_float4(y[0], y[1], y[2], y[3]);
@@ -312,10 +315,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                  ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= 2 && cpad) {
+  if (warp >= kFirstEpiWarp && cpad) {
     // Stage the per-channel epilogue parameters once per CTA.
     float* sp = reinterpret_cast<float*>(smem_raw + (params_s - smem_u32(smem_raw)));
-    for (int i = threadIdx.x - 64; i < cpad; i += kThreads - 64) {
+    for (int i = threadIdx.x - 32 * kFirstEpiWarp; i < cpad; i += 32 * kEpiWarps) {
       sp[i] = p.scale[i];
       sp[cpad + i] = p.shift[i];
       sp[2 * cpad + i] = p.slope ? p.slope[i] : 0.f;
@@ -410,116 +413,96 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
-    // The tensor pipe queues only one or two tcgen05.mma (measured: the issuing
-    // thread runs in lock-step with it), so every cycle between the last MMA of one
-    // ring iteration and the first MMA of the next is a pipe bubble.  The loop is
-    // therefore software-pipelined: all but the last MMA of an iteration are issued,
-    // then the barrier wait for the NEXT iteration's data runs while the pipe drains,
-    // then the last MMA and the commits go out.
+  } else if (warp <= kMmaWarps) {
+    // ------------------------------------------------------------- MMA issuers
+    // The tensor pipe queues only one or two tcgen05.mma: the issuing thread runs
+    // in lock-step with it, so the ~300 cycles of barrier wait / fence / elect /
+    // commit per ring iteration (a single warp's dependent instruction stream) were
+    // pure pipe bubbles (measured: iteration time = MMA time + skeleton time).  Two
+    // warps therefore alternate ring iterations: while one is blocked behind its
+    // MMAs the other has already waited for the next stage and queues right behind.
+    // A named-barrier token keeps the issue order (the first MMA of a tile
+    // overwrites the accumulator); completion is in order, so the last iteration's
+    // commit covers the tile.
+    const int which = warp - 1;
     int stage = 0, pb = 0;
     uint32_t phase = 0, pphase = 0;
     int tile_it = 0;
+    unsigned g = 0;                                   // global ring-iteration counter
     const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
     const uint32_t halo_hi = umma_desc_hi(2048, p.layout_type);   // 16 patch rows per 8-row group
     const uint32_t ring_lo = umma_desc_lo(ring);
     const uint32_t stage_step = p.stage_bytes >> 4, sub_step = p.sub_bytes >> 4,
                    b_off = p.halo ? 0u : (p.a_bytes >> 4);
     const int total_iters = p.halo ? p.kchunks * p.iters_kc : p.iters;
+    const int my_tiles = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
+    const unsigned g_last = static_cast<unsigned>(my_tiles) * total_iters - 1u;
     const bool skip_mma = (p.debug & 2) != 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_it) {
       const int acc = tile_it & 1;
       const uint32_t acc_phase = (tile_it >> 1) & 1u;
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
       const uint32_t d_tmem = tmem_base + acc * p.N_tile;
-      int kb = 0;                       // plain mode: k-blocks consumed
+      int kb = 0;                               // plain mode: k-blocks consumed
       int it_kc = 0, tap = 0, tr = 0, ts = 0;   // halo mode: position inside the channel chunk
-      if (p.halo) mbar_wait(pfull_bar(pb), pphase, p.err, 6);
-      mbar_wait(full_bar(stage), phase, p.err, 3);
-      for (int it = 0; it < total_iters; ++it) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int left = p.halo ? p.taps - tap : p.k_blocks - kb;
-        const int nsub = min(p.sub, left);
-        // descriptors of this iteration's k-blocks (warp-uniform)
-        uint32_t a_lo[kMaxSub], b_lo[kMaxSub];
-        const uint32_t st_lo = ring_lo + stage * stage_step;
-        if (p.halo) {
+      for (int it = 0; it < total_iters; ++it, ++g) {
+        const int nsub = min(p.sub, p.halo ? p.taps - tap : p.k_blocks - kb);
+        const bool mine = (g & 1u) == static_cast<unsigned>(which);
+        const bool end_kc = p.halo && it_kc == p.iters_kc - 1;
+        if (mine) {
+          if (it == 0) mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
+          if (p.halo && it_kc == 0) mbar_wait(pfull_bar(pb), pphase, p.err, 6);
+          mbar_wait(full_bar(stage), phase, p.err, 3);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st_lo = ring_lo + stage * stage_step;
           const uint32_t patch = base + pb * p.patch_bytes;
-          int r = tr, c = ts;
+          // issue-order token from the other warp (it issued iteration g-1)
+          if (g > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + ((g - 1) & 1u)) : "memory");
+          if (elect_one()) {
+            if (!skip_mma) {
+              int r = tr, c = ts;
+              for (int j = 0; j < nsub; ++j) {
+                uint32_t a_lo, b_lo;
+                if (p.halo) {
+                  const uint32_t rows_off = p.halo == 1 ? r * 16 + c : c * 16 + r;
+                  a_lo = umma_desc_lo(patch + rows_off * 128u);
+                  b_lo = st_lo + j * sub_step;
+                  if (++c == p.kw) { c = 0; ++r; }
+                } else {
+                  a_lo = st_lo + j * sub_step;
+                  b_lo = a_lo + b_off;
+                }
 #pragma unroll
-          for (int j = 0; j < kMaxSub; ++j) {
-            const uint32_t rows_off = p.halo == 1 ? r * 16 + c : c * 16 + r;
-            a_lo[j] = umma_desc_lo(patch + rows_off * 128u);
-            b_lo[j] = st_lo + j * sub_step;
-            if (++c == p.kw) { c = 0; ++r; }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < kMaxSub; ++j) {
-            a_lo[j] = st_lo + j * sub_step;
-            b_lo[j] = a_lo[j] + b_off;
-          }
-        }
-        const uint32_t a_hi = p.halo ? halo_hi : desc_hi;
-        const uint32_t acc_in = it > 0 ? 1u : 0u;
-        if (elect_one() && !skip_mma) {
-#pragma unroll
-          for (int j = 0; j < kMaxSub; ++j) {
-            if (j < nsub) {
-#pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {      // +32 B (2 x 16 B units) per K step
-                if (j == nsub - 1 && k == KSTEPS - 1) break;      // held back, see below
-                umma_f16(d_tmem, a_lo[j] + 2 * k, a_hi, b_lo[j] + 2 * k, desc_hi, p.idesc,
-                         acc_in | uint32_t(j | k));
+                for (int k = 0; k < KSTEPS; ++k)       // +32 B (2 x 16 B units) per K step
+                  umma_f16(d_tmem, a_lo + 2 * k, p.halo ? halo_hi : desc_hi, b_lo + 2 * k, desc_hi,
+                           p.idesc, (it | j | k) != 0 ? 1u : 0u);
               }
             }
+            umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
+            if (end_kc) umma_commit(pempty_bar(pb));
+            if (it == total_iters - 1) umma_commit(tfull_bar(acc));
           }
+          __syncwarp();
+          if (g != g_last) asm volatile("bar.arrive %0, 64;" ::"r"(1 + (g & 1u)) : "memory");
         }
-        __syncwarp();
-        // ---- bookkeeping for the next iteration + wait for its data (pipe is busy meanwhile)
-        const bool last = it == total_iters - 1;
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == p.stages) { nstage = 0; nphase ^= 1u; }
-        bool end_kc = false;
-        int npb = pb;
-        uint32_t npphase = pphase;
+        // bookkeeping (both warps)
         if (p.halo) {
           tap += nsub;
           ts += nsub;
           while (ts >= p.kw) { ts -= p.kw; ++tr; }
           if (++it_kc == p.iters_kc) {
-            end_kc = true;
             it_kc = 0; tap = 0; tr = 0; ts = 0;
-            if (++npb == 2) { npb = 0; npphase ^= 1u; }
+            if (++pb == 2) { pb = 0; pphase ^= 1u; }
           }
         } else {
           kb += nsub;
         }
-        if (!last) {
-          if (end_kc) mbar_wait(pfull_bar(npb), npphase, p.err, 6);
-          mbar_wait(full_bar(nstage), nphase, p.err, 3);
-        }
-        uint32_t a_last = a_lo[0], b_last = b_lo[0];
-#pragma unroll
-        for (int j = 1; j < kMaxSub; ++j)
-          if (j < nsub) { a_last = a_lo[j]; b_last = b_lo[j]; }
-        if (elect_one()) {
-          if (!skip_mma)
-            umma_f16(d_tmem, a_last + 2 * (KSTEPS - 1), a_hi, b_last + 2 * (KSTEPS - 1),
-                     desc_hi, p.idesc, acc_in | uint32_t((nsub - 1) | (KSTEPS - 1)));
-          umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
-          if (end_kc) umma_commit(pempty_bar(pb));
-          if (last) umma_commit(tfull_bar(acc));
-        }
-        __syncwarp();
-        stage = nstage; phase = nphase; pb = npb; pphase = npphase;
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
     // ---------------------------------------------------------------- epilogue
-    const int ew = warp - 2;
+    const int ew = warp - kFirstEpiWarp;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = ew >> 2;               // which 16-column chunks (even / odd) it takes
     const int row = q * 32 + lane;
