@@ -37,10 +37,8 @@ namespace trb {
 
 namespace {
 
-constexpr int kMmaWarps = 2;                 // alternate ring iterations, see the MMA role
-constexpr int kFirstEpiWarp = 1 + kMmaWarps;
+constexpr int kThreads = 320;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
 constexpr int kMaxStages = 8;
 constexpr int kMaxSub = 4;
 constexpr uint32_t kSmemBudget = 196 * 1024;
@@ -73,7 +71,7 @@ struct TcParams {
   int debug;  // timing experiments only: 1 skip TMA loads, 2 skip MMAs, 4 skip epilogue stores, 8 skip epilogue
   // halo mode: the input patch of a tile (+ filter halo) is loaded ONCE per channel chunk and
   // every tap's A operand is a shifted UMMA descriptor into it.  1: tile 8w x 16h, 2: 16w x 8h.
-  int halo, halo_base_mode, taps, iters_kc;
+  int halo, taps, iters_kc;
   uint32_t patch_bytes, patch_tx, ring_off;
 };
 
@@ -315,10 +313,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                  ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= kFirstEpiWarp && cpad) {
+  if (warp >= 2 && cpad) {
     // Stage the per-channel epilogue parameters once per CTA.
     float* sp = reinterpret_cast<float*>(smem_raw + (params_s - smem_u32(smem_raw)));
-    for (int i = threadIdx.x - 32 * kFirstEpiWarp; i < cpad; i += 32 * kEpiWarps) {
+    for (int i = threadIdx.x - 64; i < cpad; i += kThreads - 64) {
       sp[i] = p.scale[i];
       sp[cpad + i] = p.shift[i];
       sp[2 * cpad + i] = p.slope ? p.slope[i] : 0.f;
@@ -413,96 +411,88 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp <= kMmaWarps) {
-    // ------------------------------------------------------------- MMA issuers
-    // The tensor pipe queues only one or two tcgen05.mma: the issuing thread runs
-    // in lock-step with it, so the ~300 cycles of barrier wait / fence / elect /
-    // commit per ring iteration (a single warp's dependent instruction stream) were
-    // pure pipe bubbles (measured: iteration time = MMA time + skeleton time).  Two
-    // warps therefore alternate ring iterations: while one is blocked behind its
-    // MMAs the other has already waited for the next stage and queues right behind.
-    // A named-barrier token keeps the issue order (the first MMA of a tile
-    // overwrites the accumulator); completion is in order, so the last iteration's
-    // commit covers the tile.
-    const int which = warp - 1;
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
     int stage = 0, pb = 0;
     uint32_t phase = 0, pphase = 0;
     int tile_it = 0;
-    unsigned g = 0;                                   // global ring-iteration counter
     const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
-    const uint32_t halo_hi = umma_desc_hi(2048, p.layout_type);   // 16 patch rows per 8-row group
-    const uint32_t ring_lo = umma_desc_lo(ring);
+    const uint32_t halo_hi = umma_desc_hi(2048, p.layout_type);   // 16 patch rows per 8-row group step
+    const uint32_t a_lo0 = umma_desc_lo(ring);
     const uint32_t stage_step = p.stage_bytes >> 4, sub_step = p.sub_bytes >> 4,
-                   b_off = p.halo ? 0u : (p.a_bytes >> 4);
-    const int total_iters = p.halo ? p.kchunks * p.iters_kc : p.iters;
-    const int my_tiles = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                         static_cast<int>(gridDim.x);
-    const unsigned g_last = static_cast<unsigned>(my_tiles) * total_iters - 1u;
-    const bool skip_mma = (p.debug & 2) != 0;
+                   b_off = p.a_bytes >> 4;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_it) {
       const int acc = tile_it & 1;
       const uint32_t acc_phase = (tile_it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + acc * p.N_tile;
-      int kb = 0;                               // plain mode: k-blocks consumed
-      int it_kc = 0, tap = 0, tr = 0, ts = 0;   // halo mode: position inside the channel chunk
-      for (int it = 0; it < total_iters; ++it, ++g) {
-        const int nsub = min(p.sub, p.halo ? p.taps - tap : p.k_blocks - kb);
-        const bool mine = (g & 1u) == static_cast<unsigned>(which);
-        const bool end_kc = p.halo && it_kc == p.iters_kc - 1;
-        if (mine) {
-          if (it == 0) mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
-          if (p.halo && it_kc == 0) mbar_wait(pfull_bar(pb), pphase, p.err, 6);
-          mbar_wait(full_bar(stage), phase, p.err, 3);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t st_lo = ring_lo + stage * stage_step;
+      int kb = 0;
+      uint32_t accumulate = 0;
+      if (p.halo) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(pfull_bar(pb), pphase, p.err, 6);
           const uint32_t patch = base + pb * p.patch_bytes;
-          // issue-order token from the other warp (it issued iteration g-1)
-          if (g > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + ((g - 1) & 1u)) : "memory");
-          if (elect_one()) {
-            if (!skip_mma) {
-              int r = tr, c = ts;
+          int tap = 0;
+          for (int it = 0; it < p.iters_kc; ++it) {
+            const int nsub = min(p.sub, p.taps - tap);
+            mbar_wait(full_bar(stage), phase, p.err, 3);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+              const uint32_t b_lo0 = a_lo0 + stage * stage_step;
               for (int j = 0; j < nsub; ++j) {
-                uint32_t a_lo, b_lo;
-                if (p.halo) {
-                  const uint32_t rows_off = p.halo == 1 ? r * 16 + c : c * 16 + r;
-                  a_lo = umma_desc_lo(patch + rows_off * 128u);
-                  b_lo = st_lo + j * sub_step;
-                  if (++c == p.kw) { c = 0; ++r; }
-                } else {
-                  a_lo = st_lo + j * sub_step;
-                  b_lo = a_lo + b_off;
-                }
+                const int t = tap + j, r = t / p.kw, s = t - r * p.kw;
+                const uint32_t rows_off = p.halo == 1 ? r * 16 + s : s * 16 + r;
+                const uint32_t a_start = patch + rows_off * 128u;
+                const uint32_t a_lo = umma_desc_lo(a_start);
+                const uint32_t a_hi = halo_hi;   // base_offset stays 0: the swizzle XOR uses absolute smem address bits
+                const uint32_t b_lo = b_lo0 + j * (p.b_bytes >> 4);
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k)       // +32 B (2 x 16 B units) per K step
-                  umma_f16(d_tmem, a_lo + 2 * k, p.halo ? halo_hi : desc_hi, b_lo + 2 * k, desc_hi,
-                           p.idesc, (it | j | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < KSTEPS; ++k) {
+                  umma_f16(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, desc_hi, p.idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit(empty_bar(stage));
+              if (it == p.iters_kc - 1) {
+                umma_commit(pempty_bar(pb));
+                if (kc == p.kchunks - 1) umma_commit(tfull_bar(acc));
               }
             }
-            umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
-            if (end_kc) umma_commit(pempty_bar(pb));
-            if (it == total_iters - 1) umma_commit(tfull_bar(acc));
+            __syncwarp();
+            tap += nsub;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-          __syncwarp();
-          if (g != g_last) asm volatile("bar.arrive %0, 64;" ::"r"(1 + (g & 1u)) : "memory");
+          if (++pb == 2) { pb = 0; pphase ^= 1u; }
         }
-        // bookkeeping (both warps)
-        if (p.halo) {
-          tap += nsub;
-          ts += nsub;
-          while (ts >= p.kw) { ts -= p.kw; ++tr; }
-          if (++it_kc == p.iters_kc) {
-            it_kc = 0; tap = 0; tr = 0; ts = 0;
-            if (++pb == 2) { pb = 0; pphase ^= 1u; }
+        continue;
+      }
+      for (int it = 0; it < p.iters; ++it) {
+        const int nsub = min(p.sub, p.k_blocks - kb);
+        kb += nsub;
+        mbar_wait(full_bar(stage), phase, p.err, 3);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          uint32_t a_lo = a_lo0 + stage * stage_step;
+          if (!(p.debug & 2)) {
+            for (int j = 0; j < nsub; ++j, a_lo += sub_step) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {      // +32 B (2 x 16 B units) per K step
+                umma_f16(d_tmem, a_lo + 2 * k, desc_hi, a_lo + b_off + 2 * k, desc_hi, p.idesc, accumulate);
+                accumulate = 1;
+              }
+            }
           }
-        } else {
-          kb += nsub;
+          umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
+          if (it == p.iters - 1) umma_commit(tfull_bar(acc));
         }
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
     // ---------------------------------------------------------------- epilogue
-    const int ew = warp - kFirstEpiWarp;
+    const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = ew >> 2;               // which 16-column chunks (even / odd) it takes
     const int row = q * 32 + lane;
@@ -667,7 +657,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   // straddles a patch row and the group stride (SBO) is a whole swizzle repeat (2048 B).
   p.taps = a.kh * a.kw;
   {
-    int want = 0;                                   // 0 off, 1 / 2 forced orientation, 3 auto
+    int want = 3;                                   // 0 off, 1 / 2 forced orientation, 3 auto
     if (const char* h = getenv("TRB_TC_HALO")) want = atoi(h);
     const bool ok = a.stride == 1 && p.KC == 64 && a.kh == a.kw && a.kh >= 3 && a.pad == a.kh / 2 &&
                     8 + 2 * a.pad <= 16;
@@ -678,14 +668,15 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
       int mode = want == 3 ? (t2 < t1 ? 2 : 1) : want;
       const long th = mode == 1 ? t1 : t2;
       const int sms = num_sms();
-      const bool worth = (a.cin_pad <= 128 || a.kh >= 5) &&
+      // Measured (profiles/r01_conv_microbench_*): the halo patch pays where re-reading
+      // the input once per tap through L2 is the bound — 3x3 layers with K = 9*64/9*128.
+      const bool worth = a.cin_pad <= 128 && a.kh == 3 &&
                          ceil_div(int(th * p.n_tiles), sms) * 100 <= ceil_div(int(t0 * p.n_tiles), sms) * 115;
       if (want != 3 || worth) {
         p.halo = mode;
         p.bw = mode == 1 ? 8 : 16; p.bh = mode == 1 ? 16 : 8; p.bn = 1;
       }
     }
-    if (const char* h = getenv("TRB_TC_HALO_BASE")) p.halo_base_mode = atoi(h);
   }
   p.rows = p.bw * p.bh * p.bn;
   p.tiles_w = ceil_div(p.W_out, p.bw);
