@@ -163,6 +163,41 @@ def run_reference(args):
 
 # ------------------------------------------------------------------- our arm
 
+def per_config_throughput(det_model, pose_model, frames, dev, steps):
+    """Device-resident throughput of the single-GPU BASELINE configs (CUDA events):
+    C2 RetinaFace 32x1080p, C3 ArcFace 256 crops of 112x112, C4 OpenPose 16x720p."""
+    from terran_b200 import synth
+    from terran_b200.face.recognition.arcface import ArcFace
+    from terran_b200.frames import resize_short_side
+
+    def timed(fn, units):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {'value': units / ms * 1e3, 'ms_per_step': ms}
+
+    out = {}
+    out['retinaface_1080p_b32'] = dict(
+        timed(lambda: det_model.detect_device(resize_short_side(frames, 416)[0]), 32), unit='frames/s')
+    f720 = torch.from_numpy(np.random.default_rng(1).integers(
+        0, 256, (16, 720, 1280, 3), dtype=np.uint8)).to(dev)
+    out['openpose_720p_b16'] = dict(timed(lambda: pose_model.estimate_device(f720), 16), unit='frames/s')
+    arc = ArcFace(device=dev, state_dict=synth.arcface_state_dict())
+    crops = torch.from_numpy(np.random.default_rng(2).integers(
+        0, 256, (256, 112, 112, 3), dtype=np.uint8)).to(dev)
+    out['arcface_112_b256'] = dict(timed(lambda: arc.embed_device(crops), 256), unit='crops/s')
+    st = arc.net.stats()
+    out['arcface_112_b256']['tc_tflops'] = st['tc_flops'] / (out['arcface_112_b256']['ms_per_step'] * 1e-3) / 1e12
+    return out
+
+
 def run_ours(args):
     from terran_b200 import parallel, synth
     from terran_b200.face.detection import Detection
@@ -298,6 +333,8 @@ def run_ours(args):
             'algorithmic_gflop_per_step': tc_flops / max(args.steps, 1) / 1e9,
         },
     }
+    if world == 1 and not args.no_per_config:
+        line['per_config'] = per_config_throughput(det_model, pose_model, frames, dev, args.steps)
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         fps, _ = time_cpu_pipeline(4, 1, 1)
@@ -317,6 +354,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-per-config', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -171,6 +171,40 @@ def test_openpose_maps(native, opose, golden, mode):
     assert np.abs(heat.cpu().numpy() - g['heat']).max() <= 4e-3
 
 
+def test_full_size_tensor_core_path_agrees_with_direct_path(native, retina, opose):
+    """BASELINE sizes (no CPU oracle at this size): the tcgen05 implicit-GEMM
+    program and the CUDA-core direct program are two independent implementations
+    of the same fp16 network; their outputs must agree to fp16 round-off, and a
+    run is deterministic (bit-identical when repeated)."""
+    rng = np.random.default_rng(12)
+    det, _ = retina
+    frames = torch.from_numpy(rng.integers(0, 256, (32, 416, 739, 3), dtype=np.uint8)).cuda()
+    tc = [t.clone() for t in det.heads(frames)]
+    again = det.heads(frames)
+    for a, b in zip(tc, again):
+        assert torch.equal(a, b)
+    det.net.set_force_direct(True)
+    try:
+        direct = det.heads(frames)
+    finally:
+        det.net.set_force_direct(False)
+    for i, (a, b) in enumerate(zip(tc, direct)):
+        tol = 2e-2 if i % 3 == 0 else 4e-3
+        assert (a - b).abs().max().item() < tol, (i, (a - b).abs().max().item())
+
+    op, _ = opose
+    frames = torch.from_numpy(rng.integers(0, 256, (16, 184, 327, 3), dtype=np.uint8)).cuda()
+    paf, heat = (t.clone() for t in op.maps(frames))
+    op.net.set_force_direct(True)
+    try:
+        paf_d, heat_d = op.maps(frames)
+    finally:
+        op.net.set_force_direct(False)
+    assert (paf - paf_d).abs().max().item() < 4e-3
+    assert (heat - heat_d).abs().max().item() < 4e-3
+    assert tuple(paf.shape) == (16, 38, 23, 40)
+
+
 def test_streaming_pipeline_matches_sequential_calls(native, retina, opose):
     """FrameFeeder + PerceptionPipeline (prefetched uploads, detect and pose on
     two streams) return exactly what the plain sequential calls return."""

@@ -88,6 +88,31 @@ def test_registry_resolves_classes(tmp_path, monkeypatch):
     assert (tmp_path / 'checkpoints').exists()
 
 
+def test_register_with_reference_registry(monkeypatch):
+    """The plugin hook: entries appended to the reference's CHECKPOINTS list make
+    its own lookup resolve alias 'b200' to these classes (terran/checkpoint.py:
+    190-197, 244-245), without disturbing the defaults."""
+    import types
+    from terran_b200 import checkpoint as ck
+    fake_pkg, fake = types.ModuleType('terran'), types.ModuleType('terran.checkpoint')
+    fake.CHECKPOINTS = [{'id': 'b5d77fff', 'task': 'face-detection', 'alias': 'gpu-realtime',
+                         'default': True, 'class': 'terran.face.detection.retinaface.RetinaFace'}]
+    fake_pkg.checkpoint = fake
+    monkeypatch.setitem(sys.modules, 'terran', fake_pkg)
+    monkeypatch.setitem(sys.modules, 'terran.checkpoint', fake)
+    ck.register_with_reference()
+    ck.register_with_reference()          # idempotent
+    added = [c for c in fake.CHECKPOINTS if c['alias'] == 'b200']
+    assert [c['task'] for c in added] == ['face-detection', 'face-recognition', 'pose-estimation']
+    assert all(not c['default'] for c in added)
+    assert added[0]['id'] == 'b5d77fff' and added[0]['class'].startswith('terran_b200.')
+    # the reference's own selection rule
+    pick = [c for c in fake.CHECKPOINTS if c['task'] == 'face-detection' and c['alias'] == 'b200']
+    assert len(pick) == 1
+    default = [c for c in fake.CHECKPOINTS if c['task'] == 'face-detection' and c['default']]
+    assert default[0]['class'] == 'terran.face.detection.retinaface.RetinaFace'
+
+
 def test_public_surface():
     import terran_b200
     from terran_b200.pose import Keypoint
