@@ -72,6 +72,8 @@ struct TcParams {
   // halo mode: the input patch of a tile (+ filter halo) is loaded ONCE per channel chunk and
   // every tap's A operand is a shifted UMMA descriptor into it.  1: tile 8w x 16h, 2: 16w x 8h.
   int halo, taps, iters_kc;
+  int cta2, pair_units;      // CTA-pair kernel: units = ceil(m_tiles / 2) * n_tiles
+  uint32_t idesc2;
   uint32_t patch_bytes, patch_tx, ring_off;
 };
 
@@ -558,6 +560,284 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2).  Two CTAs of a cluster compute two
+// adjacent pixel tiles against the SAME filter tile: each CTA loads its own A
+// tile and only HALF of the B tile; one tcgen05.mma (M = 256) issued by the
+// leader CTA drives both SMs, reading A and its B half from each CTA's shared
+// memory and writing each CTA's 128 accumulator rows to its own TMEM.  Per SM
+// this halves the filter traffic (L2 -> smem and smem -> tensor core) and the
+// number of MMA instructions per flop.  Barriers: both CTAs' TMA loads signal
+// the leader's `full` barrier; tcgen05.commit multicasts to both CTAs' `empty`
+// and `tmem_full` barriers; both CTAs' epilogue warps arrive on the leader's
+// `tmem_empty` barrier.  Plain (per-tap) A loads only, KC = 64.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                             int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                             int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
+                                          uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b16 m;\n"
+      "mov.b16 m, 3;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+      "}\n"
+      ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t params_s = base + p.stages * p.stage_bytes;
+  const int cpad = p.cout_pad;
+  const uint32_t bars = params_s + 5u * cpad * 4u;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);          // leader's expect_tx arrive (+ tx bytes of both CTAs)
+      mbar_init(empty_bar(s), 1);         // multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);                 // multicast commit
+      mbar_init(tempty_bar(a), 2 * kEpiWarps);    // leader's copy is the one used
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    float* sp = reinterpret_cast<float*>(smem_raw + (params_s - smem_u32(smem_raw)));
+    for (int i = threadIdx.x - 64; i < cpad; i += kThreads - 64) {
+      sp[i] = p.scale[i];
+      sp[cpad + i] = p.shift[i];
+      sp[2 * cpad + i] = p.slope ? p.slope[i] : 0.f;
+      sp[3 * cpad + i] = p.scale2 ? p.scale2[i] : 1.f;
+      sp[4 * cpad + i] = p.shift2 ? p.shift2[i] : 0.f;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                 // peer barriers are initialised before anyone signals them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  const int units = p.pair_units;     // (pixel-tile pairs) x n_tiles
+  const int half_n = p.N_tile >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t cta_tx = p.rows * p.KC * 2 + half_n * p.KC * 2;
+    for (int u = pair; u < units; u += npairs) {
+      const int nt = u % p.n_tiles;
+      int mt = (u / p.n_tiles) * 2 + static_cast<int>(rank);
+      const int wb = mt % p.tiles_w; mt /= p.tiles_w;
+      const int hb = mt % p.tiles_h; mt /= p.tiles_h;
+      const int nb = mt;                  // may be >= tiles_n for the odd tail: loads zero-fill
+      const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = nb * p.bn;
+      int r = 0, s = 0, kc = 0, kb = 0;
+      for (int it = 0; it < p.iters; ++it) {
+        const int nsub = min(p.sub, p.k_blocks - kb);
+        mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
+        const uint32_t sa = base + stage * p.stage_bytes;
+        const uint32_t lead_full = mapa_u32(full_bar(stage), 0);
+        if (rank == 0 && elect_one()) mbar_expect_tx(full_bar(stage), 2u * cta_tx * nsub);
+        __syncwarp();
+        for (int j = 0; j < nsub; ++j, ++kb) {
+          int c0 = p.in_coff + kc * p.KC, c1, c2, c3, c4;
+          if (p.stride == 1) {
+            c1 = w0 + s - p.pad; c2 = h0 + r - p.pad; c3 = n0; c4 = 0;
+          } else {
+            const int oy = r - p.pad, ox = s - p.pad;
+            const int py = oy & 1, px = ox & 1;
+            c0 += px * p.in_cs;
+            c1 = w0 + ((ox - px) >> 1); c2 = py; c3 = h0 + ((oy - py) >> 1); c4 = n0;
+          }
+          const uint32_t dst = sa + j * p.sub_bytes;
+          if (elect_one()) {
+            tma2_load_5d(dst, &tmA, lead_full, c0, c1, c2, c3, c4);
+            tma2_load_2d(dst + p.a_bytes, &tmB, lead_full, (r * p.kw + s) * p.cin_pad + kc * p.KC,
+                         nt * p.N_tile + static_cast<int>(rank) * half_n);
+          }
+          if (++kc == p.kchunks) { kc = 0; if (++s == p.kw) { s = 0; ++r; } }
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------- MMA issuer (leader CTA only)
+    if (rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int tile_it = 0;
+      const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
+      const uint32_t a_lo0 = umma_desc_lo(base);
+      const uint32_t stage_step = p.stage_bytes >> 4, sub_step = p.sub_bytes >> 4,
+                     b_off = p.a_bytes >> 4;
+      for (int u = pair; u < units; u += npairs, ++tile_it) {
+        const int acc = tile_it & 1;
+        const uint32_t acc_phase = (tile_it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + acc * p.N_tile;
+        int kb = 0;
+        uint32_t accumulate = 0;
+        for (int it = 0; it < p.iters; ++it) {
+          const int nsub = min(p.sub, p.k_blocks - kb);
+          kb += nsub;
+          mbar_wait(full_bar(stage), phase, p.err, 3);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            uint32_t a_lo = a_lo0 + stage * stage_step;
+            if (!(p.debug & 2)) {
+              for (int j = 0; j < nsub; ++j, a_lo += sub_step) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma2_f16(d_tmem, a_lo + 2 * k, a_lo + b_off + 2 * k, desc_hi, p.idesc2, accumulate);
+                  accumulate = 1;
+                }
+              }
+            }
+            umma2_commit_both(empty_bar(stage));
+            if (it == p.iters - 1) umma2_commit_both(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int row = q * 32 + lane;
+    const int w_l = row % p.bw;
+    const int h_l = (row / p.bw) % p.bh;
+    const int n_l = row / (p.bw * p.bh);
+    const int nchunks = p.N_tile >> 4;
+    EpiCtx e;
+    e.cpad = cpad;
+    e.sp = reinterpret_cast<const float*>(smem_raw + (params_s - smem_u32(smem_raw)));
+    int tile_it = 0;
+    for (int u = pair; u < units; u += npairs, ++tile_it) {
+      const int acc = tile_it & 1;
+      const uint32_t acc_phase = (tile_it >> 1) & 1u;
+      const int nt = u % p.n_tiles;
+      int mt = (u / p.n_tiles) * 2 + static_cast<int>(rank);
+      const int wb = mt % p.tiles_w; mt /= p.tiles_w;
+      const int hb = mt % p.tiles_h; mt /= p.tiles_h;
+      const int nb = mt;
+      const int ow = wb * p.bw + w_l, oh = hb * p.bh + h_l, on = nb * p.bn + n_l;
+      e.valid = row < p.rows && ow < p.W_out && oh < p.H_out && on < p.N;
+      e.pix = (static_cast<long>(on) * p.H_out + oh) * p.W_out + ow;
+      e.rpix = e.pix;
+      if (p.res && p.res_up2)
+        e.rpix = (static_cast<long>(on) * p.res_H + (oh >> 1)) * p.res_W + (ow >> 1);
+
+      mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.N_tile;
+      const int cn0 = nt * p.N_tile;
+      uint32_t va[16], vb[16];
+      int c = half;
+      __syncwarp();
+      if (c < nchunks) tmem_ld16_async(taddr + c * 16, va);
+      while (c < nchunks) {
+        __syncwarp();
+        tmem_ld_wait();
+        if (c + 2 < nchunks) tmem_ld16_async(taddr + (c + 2) * 16, vb);
+        epilogue_chunk(p, e, va, cn0 + c * 16);
+        c += 2;
+        if (c >= nchunks) break;
+        __syncwarp();
+        tmem_ld_wait();
+        if (c + 2 < nchunks) tmem_ld16_async(taddr + (c + 2) * 16, va);
+        epilogue_chunk(p, e, vb, cn0 + c * 16);
+        c += 2;
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0));
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                 // the peer may still signal our barriers / read our smem
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(p.tmem_cols) : "memory");
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -683,9 +963,26 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   p.tiles_h = ceil_div(p.H_out, p.bh);
   p.tiles_n = ceil_div(p.N, p.bn);
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  {
+    // CTA-pair kernel (cta_group::2): big-K layers with wide filter tiles, when pairing the
+    // pixel tiles does not add a scheduling round.
+    int want = 2;                                   // 0 off, 1 forced, 2 auto
+    if (const char* c = getenv("TRB_TC_CTA2")) want = atoi(c);
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int units = ceil_div(m_tiles, 2) * p.n_tiles;
+    const int sms = num_sms();
+    const bool ok = !p.halo && p.KC == 64 && p.N_tile % 32 == 0 && m_tiles >= 2;
+    const bool worth = p.N_tile >= 128 && p.k_blocks >= 8 &&
+                       ceil_div(units, sms / 2) <= ceil_div(p.total_tiles, sms);
+    if (ok && (want == 1 || (want == 2 && worth))) {
+      p.cta2 = 1;
+      p.pair_units = units;
+      p.idesc2 = (1u << 4) | (uint32_t(p.N_tile >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+    }
+  }
 
   p.a_bytes = round_up(128 * p.KC * 2, 1024);         // MMA always reads 128 rows
-  p.b_bytes = round_up(p.N_tile * p.KC * 2, 1024);
+  p.b_bytes = round_up((p.cta2 ? p.N_tile / 2 : p.N_tile) * p.KC * 2, 1024);
   p.sub_bytes = p.halo ? p.b_bytes : p.a_bytes + p.b_bytes;
   // k-blocks per ring stage: enough tensor work (>= ~512 cycles = 8 MMAs of N=128) to
   // cover the single-warp issue latency, within ~64 KB per stage.
@@ -756,13 +1053,13 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   const cuuint64_t ktot = cuuint64_t(a.kh) * a.kw * a.cin_pad;
   cuuint64_t wdim[2] = {ktot, cuuint64_t(a.cout_pad)};
   cuuint64_t wstr[1] = {ktot * 2};
-  cuuint32_t wbox[2] = {cuuint32_t(p.KC), cuuint32_t(p.N_tile)};
+  cuuint32_t wbox[2] = {cuuint32_t(p.KC), cuuint32_t(p.cta2 ? p.N_tile / 2 : p.N_tile)};
   r = encode(&plan->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(a.w), wdim, wstr,
              wbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: " + std::to_string(int(r)));
 
-  plan->grid = std::min(p.total_tiles, num_sms());
+  plan->grid = p.cta2 ? 2 * std::min(p.pair_units, num_sms() / 2) : std::min(p.total_tiles, num_sms());
   plan->smem = p.ring_off + p.stages * p.stage_bytes + param_bytes + 1024 /*alignment*/ +
                8 * (2 * kMaxStages + 10) + 16;
   plan->flops = 2.0 * p.N * p.H_out * p.W_out * double(a.cout_pad) * a.kh * a.kw * a.cin_pad;
@@ -775,6 +1072,28 @@ void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
 double conv_tc_plan_flops(const ConvTcPlan* p) { return p->flops; }
 
 void conv_tc_launch(const ConvTcPlan* plan, cudaStream_t s) {
+  if (plan->p.cta2) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(plan->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = plan->smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TR_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel, plan->tmA, plan->tmB, plan->p));
+    return;
+  }
   kernel_for(plan->p.KC)<<<plan->grid, kThreads, plan->smem, s>>>(plan->tmA, plan->tmB, plan->p);
   TR_CUDA(cudaGetLastError());
 }
