@@ -966,7 +966,11 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   {
     // CTA-pair kernel (cta_group::2): big-K layers with wide filter tiles, when pairing the
     // pixel tiles does not add a scheduling round.
-    int want = 2;                                   // 0 off, 1 forced, 2 auto
+    // Default off: measured slower than the single-CTA kernel on every BASELINE layer
+    // (profiles/r01_conv_microbench_cta2.txt) — those layers are bound by the tensor pipe and
+    // by tile/wave quantisation, not by filter traffic.  Kept (and covered by the parity
+    // tests under TRB_TC_CTA2=1) as the base for B-multicast / larger-N work.
+    int want = 0;                                   // 0 off, 1 forced, 2 auto
     if (const char* c = getenv("TRB_TC_CTA2")) want = atoi(c);
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     const int units = ceil_div(m_tiles, 2) * p.n_tiles;
