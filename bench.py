@@ -282,15 +282,17 @@ def run_ours(args):
     from terran_b200.pipeline import FrameFeeder, PerceptionPipeline
     feeder = FrameFeeder((host for _ in range(args.steps + 2)), device=dev)
     pipe = PerceptionPipeline(detection, estimation, device=dev)
-    batches = iter(feeder)
+    results = pipe.run(feeder)
     for _ in range(2):
-        faces, poses = pipe(next(batches))          # warm-up; primes the prefetch
+        faces, poses = next(results)                # warm-up; primes prefetch and lookahead
     barrier()
     t0 = time.perf_counter()
-    for d in batches:
-        faces, poses = pipe(d)
+    n_timed = 0
+    for faces, poses in results:
+        n_timed += 1
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    assert n_timed == args.steps
     pipe.close()
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)

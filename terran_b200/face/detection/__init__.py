@@ -47,9 +47,12 @@ class Detection:
             self.model = self.detection_cls(device=self.device)
         return self.model
 
-    def __call__(self, images):
-        """Face detection on one image, an array batch or a list of images.
-        Returns a list of face dicts per image (or one list for one image)."""
+    def submit(self, images):
+        """Start face detection on ``images`` and return a handle whose
+        ``result()`` gives what ``__call__`` returns.  For array / CUDA-tensor
+        batches everything up to the result download is only ENQUEUED on the
+        current CUDA stream (no host synchronisation), so the caller can overlap
+        the next batch or other work; lists of images are processed right away."""
         single = not isinstance(images, (list, tuple)) and len(images.shape) == 3
         if single:
             images = images[None]
@@ -59,6 +62,9 @@ class Detection:
             idx = cuda_index(self.device)
             with torch.cuda.device(idx):
                 frames, scales = resize_short_side(to_device_u8(images, idx), self.short_side)
+                if hasattr(model, 'detect_async'):
+                    pending = model.detect_async(frames)
+                    return _Deferred(lambda: _first(pending.result(scale=scales), single))
             offsets = None
         else:
             if isinstance(images, torch.Tensor):
@@ -67,15 +73,31 @@ class Detection:
             frames, offsets = self.merger.merge(resized)
             model = self._model()
 
-        if offsets is None and not isinstance(scales, list) and hasattr(model, 'call_arrays'):
-            # one scale, no padding: rescale + round the whole batch at once
-            from terran_b200.face.detection.retinaface.wrapper import unpack_detections
-            faces = unpack_detections(*model.call_arrays(frames), scale=scales)
-        else:
-            faces = model.call(frames)
-            faces = self.merger.unpad_faces(faces, offsets)
-            faces = round_faces(faces, scales)
-        return faces[0] if single else faces
+        faces = model.call(frames)
+        faces = self.merger.unpad_faces(faces, offsets)
+        faces = round_faces(faces, scales)
+        return _Deferred(lambda: _first(faces, single))
+
+    def __call__(self, images):
+        """Face detection on one image, an array batch or a list of images.
+        Returns a list of face dicts per image (or one list for one image)."""
+        return self.submit(images).result()
+
+
+def _first(out, single):
+    return out[0] if single else out
+
+
+class _Deferred:
+    """Handle returned by ``submit``: ``result()`` finishes the computation once."""
+
+    def __init__(self, finish):
+        self._finish, self._done, self._value = finish, False, None
+
+    def result(self):
+        if not self._done:
+            self._value, self._done, self._finish = self._finish(), True, None
+        return self._value
 
 
 face_detection = Detection(lazy=True)

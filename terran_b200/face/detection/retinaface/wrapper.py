@@ -38,6 +38,7 @@ class RetinaFace:
         with torch.cuda.device(self.device_index):
             self.net = Net(program, self.device_index)
         self._ws = None
+        self._host = {}
         self.last_candidates = None
 
     # -- stages, exposed for the parity tests --------------------------------
@@ -86,22 +87,77 @@ class RetinaFace:
                 return count, cand, det
             max_det = top            # rare: more survivors than rows; redo the select
 
+    def detect_async(self, frames, threshold=0.5, max_det=512):
+        """Enqueue forward + post-processing + the D2H of the results on the current
+        stream without any host synchronisation; returns a ``PendingDetections``."""
+        N, H, W, _ = frames.shape
+        dev = frames.device
+        self.forward(frames)
+        ws = self._workspace(N, H, W)
+        count = torch.empty(N, dtype=torch.int32, device=dev)
+        cand = torch.empty(N, dtype=torch.int32, device=dev)
+        det = torch.empty((N, max_det, 16), dtype=torch.float32, device=dev)
+        heads = (C.c_int * 3)(*self.roles['heads'])
+        nat.check(nat.lib().tr_retinaface_detect(
+            self.net.handle, heads, float(threshold), float(self.nms_threshold), max_det,
+            C.c_void_p(ws.data_ptr()), C.c_void_p(count.data_ptr()), C.c_void_p(cand.data_ptr()),
+            C.c_void_p(det.data_ptr()), nat.current_stream_ptr()))
+        slot = self._host_slot(N, max_det)
+        slot['count'].copy_(count, non_blocking=True)
+        slot['det'].copy_(det, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        self.last_candidates = cand
+        return PendingDetections(self, frames, threshold, max_det, slot, done)
+
+    def _host_slot(self, N, max_det):
+        """Pinned result buffers, three sets in rotation (a result may still be
+        unread while the next two batches are in flight)."""
+        key = (N, max_det)
+        ring = self._host.setdefault(key, {'i': 0, 'slots': []})
+        if len(ring['slots']) < 3:
+            ring['slots'].append({
+                'count': torch.empty(N, dtype=torch.int32).pin_memory(),
+                'det': torch.empty((N, max_det, 16), dtype=torch.float32).pin_memory()})
+            ring['i'] = len(ring['slots']) - 1
+            return ring['slots'][-1]
+        ring['i'] = (ring['i'] + 1) % 3
+        return ring['slots'][ring['i']]
+
     def call_arrays(self, images, threshold=0.5):
         """``call`` without the per-face dict building: (counts (N,), rows
         (N,R,16) float32 on the host) — see ``unpack_detections``."""
         with torch.cuda.device(self.device_index):
             frames = to_device_u8(images, self.device_index)
-            count, cand, det = self.detect_device(frames, threshold)
-            counts = count.cpu().numpy()
-            self.last_candidates = cand
-            top = int(counts.max()) if len(counts) else 0
-            rows = det[:, :max(top, 1)].cpu().numpy()
-        return counts, rows
+            return self.detect_async(frames, threshold).arrays()
 
     def call(self, images, threshold=0.5):
         """Run the detection.  ``images`` is a (N,H,W,3) uint8 RGB array
         (numpy, or a CUDA tensor to skip the upload)."""
         return unpack_detections(*self.call_arrays(images, threshold))
+
+
+class PendingDetections:
+    """Results of ``RetinaFace.detect_async`` still in flight."""
+
+    def __init__(self, model, frames, threshold, max_det, slot, done):
+        self.model, self.frames, self.threshold = model, frames, threshold
+        self.max_det, self.slot, self.done = max_det, slot, done
+
+    def arrays(self):
+        """(counts (N,), rows (N,R,16)) on the host; blocks until the copy landed."""
+        self.done.synchronize()
+        counts = self.slot['count'].numpy().copy()
+        top = int(counts.max()) if len(counts) else 0
+        if top > self.max_det:
+            # rare: more survivors than rows were copied — redo synchronously with room
+            with torch.cuda.device(self.model.device_index):
+                count, _, det = self.model.detect_device(self.frames, self.threshold, max_det=top)
+                return count.cpu().numpy(), det.cpu().numpy()
+        return counts, self.slot['det'][:, :max(top, 1)].numpy().copy()
+
+    def result(self, scale=None):
+        return unpack_detections(*self.arrays(), scale=scale)
 
 
 def unpack_detections(counts, rows, scale=None):

@@ -5,13 +5,12 @@ Shape of the reference's end-to-end use (``examples/video.py:33-42``,
 the next batch of ``rgb24`` frames through a ``Queue(1)`` while the main thread
 runs the perception callables on the current one.  Here the prefetch also
 covers the host->device copy (pinned staging buffers, a dedicated copy stream,
-double buffering), and face detection and pose estimation of one batch run
-concurrently on two CUDA streams driven by two host threads, so the host-side
-result unpacking of one task overlaps the GPU work of the other.
+double buffering), face detection and pose estimation of one batch run
+concurrently on two CUDA streams, and the host-side result unpacking of batch i
+overlaps the GPU work of batch i+1.
 """
 import queue
 import threading
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -81,31 +80,54 @@ class FrameFeeder:
 
 
 class PerceptionPipeline:
-    """``faces, poses = pipeline(frames)``: the two public callables on the same
-    batch, concurrently (one host thread + one CUDA stream each)."""
+    """Face detection + pose estimation of a stream of frame batches.
+
+    ``submit(frames)`` enqueues both tasks for one batch on two CUDA streams
+    (they are independent: the small post-processing kernels of one overlap the
+    convolutions of the other) without synchronising the host; ``result()`` of
+    the returned handle downloads and unpacks.  ``run(batches)`` keeps one batch
+    of lookahead: the GPU works on batch i+1 while the host unpacks batch i —
+    the synchronous per-batch loop of the reference's ``examples/video.py``,
+    software-pipelined."""
 
     def __init__(self, detection, estimation, device=default_device):
         self.detection, self.estimation = detection, estimation
         self.device_index = cuda_index(device)
-        self.pool = ThreadPoolExecutor(max_workers=2)
         self.streams = [torch.cuda.Stream(device=self.device_index) for _ in range(2)]
 
-    def _call(self, fn, stream, frames, ready):
-        torch.cuda.set_device(self.device_index)
-        with torch.cuda.stream(stream):
-            stream.wait_event(ready)
-            if isinstance(frames, torch.Tensor) and frames.is_cuda:
-                frames.record_stream(stream)    # allocated on the feeder's copy stream
-            out = fn(frames)
-            stream.synchronize()
-        return out
-
-    def __call__(self, frames):
+    def submit(self, frames):
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(self.device_index))
-        a = self.pool.submit(self._call, self.detection, self.streams[0], frames, ready)
-        b = self.pool.submit(self._call, self.estimation, self.streams[1], frames, ready)
-        return a.result(), b.result()
+        handles = []
+        for fn, stream in zip((self.detection.submit, self.estimation.submit), self.streams):
+            with torch.cuda.stream(stream):
+                stream.wait_event(ready)
+                if isinstance(frames, torch.Tensor) and frames.is_cuda:
+                    frames.record_stream(stream)     # allocated on the feeder's copy stream
+                handles.append(fn(frames))
+        return _PendingPair(handles)
+
+    def __call__(self, frames):
+        return self.submit(frames).result()
+
+    def run(self, batches):
+        """Yield (faces, poses) per batch, one batch of lookahead."""
+        previous = None
+        for frames in batches:
+            current = self.submit(frames)
+            if previous is not None:
+                yield previous.result()
+            previous = current
+        if previous is not None:
+            yield previous.result()
 
     def close(self):
-        self.pool.shutdown()
+        pass
+
+
+class _PendingPair:
+    def __init__(self, handles):
+        self.handles = handles
+
+    def result(self):
+        return tuple(h.result() for h in self.handles)

@@ -56,16 +56,27 @@ class Estimation:
     def __repr__(self):
         return f'<Estimation({self.estimation_cls.__name__})>'
 
-    def __call__(self, images):
+    def submit(self, images):
+        """Start pose estimation and return a handle with ``result()`` (see
+        ``Detection.submit``): for array / CUDA batches the work is only enqueued."""
+        from terran_b200.face.detection import _Deferred, _first
         single = not isinstance(images, (list, tuple)) and len(images.shape) == 3
         if single:
             images = images[None] if isinstance(images, torch.Tensor) else np.expand_dims(images, 0)
         batch, offsets = self.merger.merge(images)
         if self.model is None:
             self.model = self.estimation_cls(device=self.device, short_side=self.short_side)
-        poses = self.model.call(batch)
-        poses = self.merger.unpad_poses(poses, offsets)
-        return poses[0] if single else poses
+        model = self.model
+        if offsets is None and hasattr(model, 'estimate_async'):
+            from terran_b200.frames import to_device_u8
+            with torch.cuda.device(model.device_index):
+                pending = model.estimate_async(to_device_u8(batch, model.device_index))
+            return _Deferred(lambda: _first(pending.result(), single))
+        poses = self.merger.unpad_poses(model.call(batch), offsets)
+        return _Deferred(lambda: _first(poses, single))
+
+    def __call__(self, images):
+        return self.submit(images).result()
 
 
 pose_estimation = Estimation(lazy=True)

@@ -44,7 +44,8 @@ def parse_device(paf, heat, scale, workspace=None):
 
 
 def unpack_poses(count, kps, score, status):
-    count, status = count.cpu().numpy(), status.cpu().numpy()
+    """Device or (pinned) host tensors -> the reference's list of lists of dicts."""
+    count, status = count.cpu().numpy().copy(), status.cpu().numpy().copy()
     if status.any():
         bad = int(np.flatnonzero(status)[0])
         raise nat.NativeError(
@@ -52,8 +53,8 @@ def unpack_poses(count, kps, score, status):
             f'1 = more than {nat.TR_PEAK_CAP} peaks of one part, 2 = more than '
             f'{nat.TR_CAND_CAP} limb candidates, 4 = more than {nat.TR_HUMAN_CAP} humans)')
     top = int(count.max()) if len(count) else 0
-    kps = kps[:, :max(top, 1)].cpu().numpy()
-    score = score[:, :max(top, 1)].cpu().numpy()
+    kps = kps[:, :max(top, 1)].cpu().numpy().copy()
+    score = score[:, :max(top, 1)].cpu().numpy().copy()
     return [
         [{'keypoints': kps[n, i].copy(), 'score': score[n, i]} for i in range(k)]
         for n, k in enumerate(count)
@@ -76,6 +77,7 @@ class OpenPose:
         with torch.cuda.device(self.device_index):
             self.net = Net(program, self.device_index)
         self._ws = None
+        self._host = {}
 
     # -- device stages --------------------------------------------------------
     def maps(self, resized):
@@ -93,9 +95,45 @@ class OpenPose:
         count, kps, score, status, self._ws = parse_device(paf, heat, scale, self._ws)
         return count, kps, score, status
 
+    def estimate_async(self, frames):
+        """Enqueue resize + forward + parse + the D2H of the results on the current
+        stream without host synchronisation; returns a ``PendingPoses``."""
+        count, kps, score, status = self.estimate_device(frames)
+        N = frames.shape[0]
+        ring = self._host.setdefault(N, {'i': 0, 'slots': []})
+        if len(ring['slots']) < 3:
+            ring['slots'].append({
+                'count': torch.empty(N, dtype=torch.int32).pin_memory(),
+                'status': torch.empty(N, dtype=torch.int32).pin_memory(),
+                'kps': torch.empty((N, nat.TR_HUMAN_CAP, 18, 3), dtype=torch.int32).pin_memory(),
+                'score': torch.empty((N, nat.TR_HUMAN_CAP), dtype=torch.float64).pin_memory()})
+            ring['i'] = len(ring['slots']) - 1
+            slot = ring['slots'][-1]
+        else:
+            ring['i'] = (ring['i'] + 1) % 3
+            slot = ring['slots'][ring['i']]
+        slot['count'].copy_(count, non_blocking=True)
+        slot['status'].copy_(status, non_blocking=True)
+        slot['kps'].copy_(kps, non_blocking=True)
+        slot['score'].copy_(score, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        return PendingPoses(slot, done)
+
     def call(self, images):
         """Pose estimation on a (N,H,W,3) uint8 RGB batch (numpy or CUDA tensor)."""
         with torch.cuda.device(self.device_index):
             frames = to_device_u8(images, self.device_index)
-            out = self.estimate_device(frames)
-            return unpack_poses(*out)
+            return self.estimate_async(frames).result()
+
+
+class PendingPoses:
+    """Results of ``OpenPose.estimate_async`` still in flight."""
+
+    def __init__(self, slot, done):
+        self.slot, self.done = slot, done
+
+    def result(self):
+        self.done.synchronize()
+        s = self.slot
+        return unpack_poses(s['count'], s['kps'], s['score'], s['status'])

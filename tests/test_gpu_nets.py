@@ -219,9 +219,12 @@ def test_streaming_pipeline_matches_sequential_calls(native, retina, opose):
     batches = [rng.integers(0, 256, (3, 270, 480, 3), dtype=np.uint8) for _ in range(4)]
     want = [(det(b), est(b)) for b in batches]
     pipe = PerceptionPipeline(det, est, device=torch.device('cuda'))
-    got = [pipe(frames) for frames in FrameFeeder(batches, device=torch.device('cuda'))]
-    pipe.close()
+    got = list(pipe.run(FrameFeeder(batches, device=torch.device('cuda'))))     # lookahead path
     assert len(got) == len(want)
+    one = pipe(torch.from_numpy(batches[0]).cuda())                             # single batch
+    assert [len(f) for f in one[0]] == [len(f) for f in want[0][0]]
+    handle = det.submit(batches[1])                                             # deferred handle
+    assert [len(f) for f in handle.result()] == [len(f) for f in want[1][0]]
     for (f_got, p_got), (f_want, p_want) in zip(got, want):
         assert [len(f) for f in f_got] == [len(f) for f in f_want]
         for a, b in zip(sum(f_got, []), sum(f_want, [])):
