@@ -241,11 +241,11 @@ def run_ours(args):
         fork.record(cur)
         with torch.cuda.stream(side[1]):
             side[1].wait_event(fork)
-            out_p = pose_model.estimate_device(frames)        # fully asynchronous
+            out_p = pose_model.estimate_async(frames)         # no host synchronisation
         with torch.cuda.stream(side[0]):
             side[0].wait_event(fork)
             small, _ = resize_short_side(frames, 416)
-            out_d = det_model.detect_device(small)            # one host sync (survivor count)
+            out_d = det_model.detect_async(small)             # no host synchronisation
         cur.wait_stream(side[0])
         cur.wait_stream(side[1])
         return out_d, out_p
