@@ -332,6 +332,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);     // provably warp-uniform
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation,
+  // parameter staging — none of it reads the previous layer's output) may overlap the
+  // tail of the previous kernel; activations are only touched after this wait.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // The producer and MMA loops run with the WHOLE warp converged and every
   // operand warp-uniform; one elected lane issues the TMA / tcgen05 instructions.
@@ -684,6 +689,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int units = p.pair_units;     // (pixel-tile pairs) x n_tiles
   const int half_n = p.N_tile >> 1;
@@ -1088,18 +1095,30 @@ void conv_tc_launch(const ConvTcPlan* plan, cudaStream_t s) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = plan->smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     TR_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel, plan->tmA, plan->tmB, plan->p));
     return;
   }
-  kernel_for(plan->p.KC)<<<plan->grid, kThreads, plan->smem, s>>>(plan->tmA, plan->tmB, plan->p);
-  TR_CUDA(cudaGetLastError());
+  static const bool pdl = [] { const char* e = getenv("TRB_TC_PDL"); return !e || atoi(e) != 0; }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(plan->grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = plan->smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  TR_CUDA(cudaLaunchKernelEx(&cfg, kernel_for(plan->p.KC), plan->tmA, plan->tmB, plan->p));
 }
 
 }  // namespace trb
