@@ -115,6 +115,13 @@ int tr_retinaface_detect(tr_net* net, const int* head_buffers3, float threshold,
  * sklearn.preprocessing.normalize(axis=1) of arcface/wrapper.py:174-176. */
 int tr_l2_normalize(const float* in_dev, float* out_dev, int N, int D, void* stream);
 
+/* Inverse-affine bilinear warp of F faces to (F,3,side,side) uint8 BGR crops, bit-exact
+ * with PIL Image.transform(AFFINE, BILINEAR, fillcolor=0): replaces the per-face host warp of
+ * arcface/wrapper.py:22-72.  frames: (N,H,W,3) uint8 RGB; coef: F x 6 doubles (the PIL AFFINE
+ * data = first two rows of the inverse similarity); image_index: frame of each face. */
+int tr_face_align(const uint8_t* frames_dev, int H, int W, const double* coef_dev,
+                  const int32_t* image_index_dev, int F, uint8_t* out_dev, int side, void* stream);
+
 /* ---- OpenPose parse ---------------------------------------------------------
  * Replaces openpose/wrapper.py:214-483: x8 bicubic up-sampling (fused, never
  * materialised), peak extraction, PAF line integrals, greedy limb matching,

@@ -15,6 +15,10 @@ CASES = [  # N, H, W, cin, cout, k, stride, tag
     (32, 46, 81, 256, 256, 3, 1, 'vgg 3x3 256->256'),
     (32, 184, 327, 64, 64, 3, 1, 'vgg 3x3 64->64 full res'),
     (32, 23, 40, 128, 128, 1, 1, 'openpose 1x1 128->128'),
+    (32, 23, 40, 128, 512, 1, 1, 'openpose 1x1 128->512'),
+    (32, 23, 40, 512, 38, 1, 1, 'openpose 1x1 512->38'),
+    (32, 92, 163, 64, 128, 3, 1, 'vgg 3x3 64->128 @92x163'),
+    (32, 92, 163, 128, 128, 3, 1, 'vgg 3x3 128->128 @92x163'),
     (256, 56, 56, 64, 64, 3, 1, 'arcface 3x3 64 @56'),
     (256, 28, 28, 128, 128, 3, 1, 'arcface 3x3 128 @28'),
     (256, 14, 14, 256, 256, 3, 1, 'arcface 3x3 256 @14'),

@@ -17,7 +17,7 @@ SYMBOLS = (
     'tr_net_profile',
     'tr_conv2d',
     'tr_detect_workspace_bytes', 'tr_retinaface_decode_nms', 'tr_retinaface_detect',
-    'tr_l2_normalize',
+    'tr_l2_normalize', 'tr_face_align',
     'tr_pose_workspace_bytes', 'tr_openpose_parse', 'tr_bicubic_table',
     'tr_resize_bilinear_u8',
 )
@@ -90,6 +90,7 @@ def lib():
                                                vp, vp, vp]
         L.tr_retinaface_detect.argtypes = [vp, C.POINTER(i32), f32, f64, i32, vp, vp, vp, vp, vp]
         L.tr_l2_normalize.argtypes = [vp, vp, i32, i32, vp]
+        L.tr_face_align.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, vp]
         L.tr_pose_workspace_bytes.argtypes = [i32]
         L.tr_pose_workspace_bytes.restype = C.c_size_t
         L.tr_openpose_parse.argtypes = [vp, vp, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp]

@@ -281,3 +281,69 @@ void detect_post_launch(const DetHeads& heads, int N, int H, int W, float thr, d
 }
 
 }  // namespace trb
+
+// ---------------------------------------------------------------------------
+// Face alignment: inverse-affine bilinear warp of a detected face to the 112x112
+// ArcFace crop, bit-exact with PIL's Image.transform(AFFINE, BILINEAR,
+// fillcolor=0) that the reference uses (arcface/wrapper.py:22-72; Pillow
+// Geometry.c affine_transform + bilinear_filter32RGB: sample at pixel centres,
+// neighbours clamped to the image, lerp in double along x then y, truncate).
+// Output is the reference model input layout: (F,3,S,S) uint8, channels BGR.
+// This file is compiled with -fmad=false, so the double arithmetic is not contracted.
+// ---------------------------------------------------------------------------
+namespace trb {
+namespace {
+
+__global__ void __launch_bounds__(128)
+face_align_kernel(const uint8_t* __restrict__ frames, int H, int W, const double* __restrict__ coef,
+                  const int* __restrict__ image_index, uint8_t* __restrict__ out, int S) {
+  const int f = blockIdx.y, y = blockIdx.x, x = threadIdx.x;
+  if (x >= S) return;
+  const double* a = coef + 6 * f;
+  const uint8_t* im = frames + static_cast<long>(image_index[f]) * H * W * 3;
+  const double xc = x + 0.5, yc = y + 0.5;
+  double xin = a[0] * xc + a[1] * yc + a[2];
+  double yin = a[3] * xc + a[4] * yc + a[5];
+  uint8_t px[3] = {0, 0, 0};
+  if (!(xin < 0.0 || xin >= W || yin < 0.0 || yin >= H)) {
+    xin -= 0.5;
+    yin -= 0.5;
+    const int x0 = xin < 0.0 ? static_cast<int>(floor(xin)) : static_cast<int>(xin);
+    const int y0 = yin < 0.0 ? static_cast<int>(floor(yin)) : static_cast<int>(yin);
+    const double dx = xin - x0, dy = yin - y0;
+    const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
+    const int ya = min(max(y0, 0), H - 1);
+    const bool has_next = y0 + 1 >= 0 && y0 + 1 < H;
+    const uint8_t* r0 = im + static_cast<long>(ya) * W * 3;
+    const uint8_t* r1 = im + static_cast<long>(has_next ? y0 + 1 : ya) * W * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double p00 = r0[xa * 3 + c], p01 = r0[xb * 3 + c];
+      double v1 = p00 + (p01 - p00) * dx;
+      double v2 = v1;
+      if (has_next) {
+        const double p10 = r1[xa * 3 + c], p11 = r1[xb * 3 + c];
+        v2 = p10 + (p11 - p10) * dx;
+      }
+      v1 = v1 + (v2 - v1) * dy;
+      px[c] = static_cast<uint8_t>(v1);
+    }
+  }
+  // RGB -> BGR planes
+  uint8_t* o = out + static_cast<long>(f) * 3 * S * S + static_cast<long>(y) * S + x;
+  o[0] = px[2];
+  o[static_cast<long>(S) * S] = px[1];
+  o[2L * S * S] = px[0];
+}
+
+}  // namespace
+
+void face_align_launch(const uint8_t* frames, int H, int W, const double* coef,
+                       const int* image_index, int F, uint8_t* out, int S, cudaStream_t s) {
+  if (F == 0) return;
+  TR_CHECK(S <= 128, "crop side");
+  face_align_kernel<<<dim3(S, F), 128, 0, s>>>(frames, H, W, coef, image_index, out, S);
+  TR_CUDA(cudaGetLastError());
+}
+
+}  // namespace trb

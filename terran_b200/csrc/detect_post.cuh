@@ -40,4 +40,8 @@ void pose_parse_launch(const float* paf, const float* heat, int N, int h, int w,
                        void* workspace, const PoseOut& out, cudaStream_t s);
 void bicubic_table_host(float out[32]);
 
+// ---- face alignment (PIL-exact inverse affine bilinear warp to (F,3,S,S) BGR)
+void face_align_launch(const uint8_t* frames, int H, int W, const double* coef,
+                       const int* image_index, int F, uint8_t* out, int S, cudaStream_t s);
+
 }  // namespace trb

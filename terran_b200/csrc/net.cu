@@ -498,6 +498,14 @@ int tr_l2_normalize(const float* in_dev, float* out_dev, int N, int D, void* str
   return guarded([&] { l2_normalize_launch(in_dev, out_dev, N, D, static_cast<cudaStream_t>(stream)); });
 }
 
+int tr_face_align(const uint8_t* frames_dev, int H, int W, const double* coef_dev,
+                  const int32_t* image_index_dev, int F, uint8_t* out_dev, int side, void* stream) {
+  return guarded([&] {
+    face_align_launch(frames_dev, H, W, coef_dev, image_index_dev, F, out_dev, side,
+                      static_cast<cudaStream_t>(stream));
+  });
+}
+
 size_t tr_pose_workspace_bytes(int N) { return pose_workspace_bytes(N); }
 
 int tr_openpose_parse(const float* paf_dev, const float* heat_dev, int N, int h, int w, double scale,

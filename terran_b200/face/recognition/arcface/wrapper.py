@@ -6,9 +6,11 @@ returning L2-normalised 512-d float32 embeddings, split per image when faces
 are given.  The ResNet forward, the final FC + BatchNorm1d and the L2
 normalisation (done on the host with sklearn upstream) run in the native library.
 
-Face alignment stays on the host in this round (PIL affine warp exactly as
-upstream; the similarity transform is the closed-form Umeyama estimate that
-``skimage.transform.SimilarityTransform.estimate`` implements).
+Face alignment: the 2x3 similarity per face is estimated on the host (closed-form
+Umeyama, what ``skimage.transform.SimilarityTransform.estimate`` implements — 5
+points per face); the affine bilinear warp to the 112x112 crop runs on the GPU
+(``tr_face_align``, bit-exact with the PIL warp upstream uses) when the frames
+come as one batch, and through PIL exactly as upstream otherwise.
 """
 import ctypes as C
 
@@ -64,14 +66,20 @@ def umeyama_similarity(src, dst):
     return T
 
 
-def preprocess_face(image, landmark, image_size=(112, 112)):
-    """Align one face with its 5 landmarks and return the (3,112,112) uint8 BGR
-    crop (reference ``preprocess_face`` :22-72)."""
+def alignment_coefficients(landmark, image_size=(112, 112)):
+    """The 6 PIL ``AFFINE`` coefficients (first two rows of the inverse
+    similarity landmarks -> template) of reference ``preprocess_face`` :39-61."""
     template = LANDMARK_TEMPLATE.copy()
     if image_size[1] == 112:
         template[:, 0] += 8.0
     T = umeyama_similarity(np.asarray(landmark).astype(np.float32), template)
-    coeffs = np.linalg.inv(T)[0:-1, :].flatten()
+    return np.linalg.inv(T)[0:-1, :].flatten()
+
+
+def preprocess_face(image, landmark, image_size=(112, 112)):
+    """Align one face with its 5 landmarks and return the (3,112,112) uint8 BGR
+    crop (reference ``preprocess_face`` :22-72) — host path (PIL)."""
+    coeffs = alignment_coefficients(landmark, image_size)
     warped = Image.fromarray(image).transform(
         size=(image_size[1], image_size[0]), method=Image.AFFINE, data=coeffs,
         resample=Image.BILINEAR, fillcolor=0)
@@ -123,9 +131,47 @@ class ArcFace:
                                             N, 512, nat.current_stream_ptr()))
         return out
 
+    def align_device(self, frames, faces_per_image):
+        """frames: CUDA uint8 (N,H,W,3) RGB; faces: the detection dicts.  Warps every
+        face to the (F,3,112,112) BGR crop on the GPU (``tr_face_align``, bit-exact
+        with the PIL warp of the host path); the 2x3 matrices are estimated on the
+        host (five points per face)."""
+        S = self.image_side
+        coefs, index = [], []
+        for i, faces in enumerate(faces_per_image):
+            for face in faces:
+                coefs.append(alignment_coefficients(face['landmarks'], (S, S)))
+                index.append(i)
+        F = len(index)
+        out = torch.empty((F, 3, S, S), dtype=torch.uint8, device=frames.device)
+        if F:
+            N, H, W, _ = frames.shape
+            coef = torch.from_numpy(np.asarray(coefs, np.float64)).to(frames.device)
+            idx = torch.from_numpy(np.asarray(index, np.int32)).to(frames.device)
+            nat.check(nat.lib().tr_face_align(
+                C.c_void_p(frames.data_ptr()), H, W, C.c_void_p(coef.data_ptr()),
+                C.c_void_p(idx.data_ptr()), F, C.c_void_p(out.data_ptr()), S,
+                nat.current_stream_ptr()))
+        return out
+
     def call(self, images, faces_per_image=None):
         """Feature extraction (reference ``ArcFace.call`` :109-184)."""
         S = self.image_side
+        # Uniform frame batch + faces: align on the GPU, no per-face host warp.
+        batched = isinstance(images, (np.ndarray, torch.Tensor)) and images.ndim == 4
+        if not batched and faces_per_image is not None and len(images) and all(
+                isinstance(im, np.ndarray) and im.shape == images[0].shape for im in images):
+            images, batched = np.stack(images, 0), True
+        if batched and faces_per_image is not None:
+            if not any(len(f) for f in faces_per_image):
+                return [np.empty((0, 512)) for _ in images]
+            from terran_b200.frames import to_device_u8
+            with torch.cuda.device(self.device_index):
+                frames = to_device_u8(images, self.device_index)
+                crops = self.align_device(frames, faces_per_image)
+                features = self.embed_device(crops, 'nchw_bgr').cpu().numpy()
+            splits = np.cumsum(list(map(len, faces_per_image)))[:-1]
+            return np.split(features, splits, axis=0)
         fast = faces_per_image is None and all(
             getattr(im, 'shape', None) == (S, S, 3) for im in images)
         if fast and len(images):

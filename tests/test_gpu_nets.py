@@ -256,3 +256,39 @@ def test_estimation_wrapper(native, opose):
     assert np.abs(heat.cpu().numpy() - heat_ref.numpy()).max() <= 4e-3
     want = pose.parse(paf_ref.numpy(), heat_ref.numpy(), scale)
     assert [len(p) for p in out[:1]] == [len(w) for w in want]
+
+
+def test_gpu_face_alignment_matches_pil(native, arc):
+    """tr_face_align == PIL Image.transform(AFFINE, BILINEAR, fillcolor=0) bit for
+    bit (the reference's preprocess_face), including faces partly outside the frame;
+    Recognition with faces on a frame batch == the host-aligned crops' embeddings."""
+    from terran_b200.face.recognition import Recognition
+    from terran_b200.face.recognition.arcface.wrapper import preprocess_face
+    model, _ = arc
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (2, 240, 320, 3), dtype=np.uint8)
+    template = np.array([[38.3, 51.7], [73.5, 51.5], [56.0, 71.7], [41.5, 92.4], [70.7, 92.2]])
+
+    def face(scale, angle, tx, ty):
+        c, s = np.cos(angle) * scale, np.sin(angle) * scale
+        pts = template @ np.array([[c, s], [-s, c]]) + [tx, ty]
+        return {'landmarks': (pts + rng.normal(0, 1.0, pts.shape)).astype(np.float32)}
+
+    faces = [[face(0.8, 0.2, 60, 40), face(1.6, -0.4, 150, 20), face(0.5, 0.0, -20, 200)],
+             [face(1.0, 0.1, 250, 170)]]
+    crops = model.align_device(torch.from_numpy(frames).cuda(), faces).cpu().numpy()
+    k = 0
+    for i, fs in enumerate(faces):
+        for f in fs:
+            want = preprocess_face(frames[i], f['landmarks'])
+            np.testing.assert_array_equal(crops[k], want)
+            k += 1
+    assert crops.shape == (4, 3, 112, 112) and crops.any()
+    rec = Recognition(device=torch.device('cuda'), lazy=True)
+    rec.model = model
+    out = rec(frames, faces)
+    assert [o.shape for o in out] == [(3, 512), (1, 512)]
+    host = model.embed_device(torch.from_numpy(np.stack(
+        [preprocess_face(frames[0], f['landmarks']) for f in faces[0]])).cuda(), 'nchw_bgr')
+    np.testing.assert_allclose(out[0], host.cpu().numpy(), atol=1e-6)
+    assert [o.shape for o in rec(frames, [[], []])] == [(0, 512), (0, 512)]
