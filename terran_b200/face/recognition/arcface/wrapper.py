@@ -115,6 +115,7 @@ class ArcFace:
     def embed_device(self, crops, layout='nhwc_rgb', normalise=True):
         """crops: CUDA uint8, (N,112,112,3) RGB (``nhwc_rgb``) or the reference
         model input (N,3,112,112) BGR (``nchw_bgr``).  Returns (N,512) fp32 CUDA."""
+        crops = crops.contiguous()          # element strides below assume a dense tensor
         N = crops.shape[0]
         S = self.image_side
         if layout == 'nhwc_rgb':
