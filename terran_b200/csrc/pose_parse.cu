@@ -9,6 +9,9 @@
 // one fixed by oracle/pose.py, which this file reproduces bit for bit.
 #include "detect_post.cuh"
 
+#include <algorithm>
+#include <cmath>
+
 namespace trb {
 
 namespace {
@@ -27,6 +30,7 @@ struct PoseParams {
   const float* heat;   // (N,19,h,w)
   int N, h, w, Hu, Wu;
   double scale;
+  float bicubic_gain;              // (max over phases of sum |w|)^2 * (1 + eps)
   unsigned long long* peak_keys;   // [N][18][kPeakCap]  (pos << 32 | score bits)
   int* peak_cnt;                   // [N][18]
   int* conn_src;                   // [N][19][kPeakCap]
@@ -70,6 +74,17 @@ __global__ void __launch_bounds__(256) pose_peaks_kernel(const PoseParams p) {
   float* rows_h = sm;                 // [5][Wu] horizontally interpolated source rows band-2..band+2
   float* up = sm + 5 * Wu;            // [10][Wu] up-sampled rows 8*band-1 .. 8*band+8
   const float* m = p.heat + (static_cast<long>(n) * 19 + part) * p.h * p.w;
+  // Early out: every up-sampled value of this band is a bicubic combination of the
+  // source rows band-2..band+2, so |value| <= (max sum|w|)^2 * max|source|.  If that bound
+  // is below the 0.1 peak threshold the band cannot contain a peak (exact, not a heuristic).
+  {
+    float mx = 0.f;
+    for (int t = threadIdx.x; t < 5 * p.w; t += 256) {
+      const int k = t / p.w, x = t % p.w;
+      mx = fmaxf(mx, fabsf(m[clampi(band - 2 + k, 0, p.h - 1) * p.w + x]));
+    }
+    if (__syncthreads_count(mx * p.bicubic_gain >= 0.1f) == 0) return;
+  }
   for (int t = threadIdx.x; t < 5 * Wu; t += 256) {
     const int k = t / Wu, x = t % Wu;
     const float* row = m + clampi(band - 2 + k, 0, p.h - 1) * p.w;
@@ -418,13 +433,21 @@ void pose_parse_launch(const float* paf, const float* heat, int N, int h, int w,
                        void* workspace, const PoseOut& out, cudaStream_t s) {
   if (N == 0) return;
   static bool table_set = false;
+  static float gain = 0.f;
   if (!table_set) {
     float tab[32];
     bicubic_table_host(tab);
     TR_CUDA(cudaMemcpyToSymbol(c_bicubic, tab, sizeof(tab)));
+    for (int ph = 0; ph < 8; ++ph) {
+      float a = 0.f;
+      for (int k = 0; k < 4; ++k) a += fabsf(tab[ph * 4 + k]);
+      gain = std::max(gain, a);
+    }
+    gain = gain * gain * 1.001f;
     table_set = true;
   }
   PoseParams p{};
+  p.bicubic_gain = gain;
   p.paf = paf; p.heat = heat; p.N = N; p.h = h; p.w = w; p.Hu = 8 * h; p.Wu = 8 * w;
   p.scale = scale;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
