@@ -49,6 +49,16 @@ def measured_peaks():
             'source': 'fallback'}
 
 
+def conv_tc_traffic():
+    """DRAM bytes per conv_tc_kernel launch (read + write), averaged over the 126
+    launches of one step, from the committed ncu capture (profiles/) — None if absent."""
+    path = os.path.join(ROOT, 'profiles', 'r01_conv_tc_traffic.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)['dram_bytes_per_launch']
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -346,7 +356,7 @@ def run_ours(args):
             'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops_sustained'],
             'unit': 'TFLOP/s', 'frac': achieved / peaks['bf16_tflops_sustained'],
             'peak_source': peaks['source'] + ' (sustained: kernel timed inside a long step)',
-            'traffic': None,
+            'traffic': conv_tc_traffic(),
             'share_of_step': tc_ms / all_ms if all_ms else None,
             'launches_per_step': tc_launch // max(args.steps, 1),
             'algorithmic_gflop_per_step': tc_flops / max(args.steps, 1) / 1e9,
