@@ -331,26 +331,32 @@ def openpose_program(sd):
     for stage in range(1, 7):
         src = cat[0] if stage == 1 else cat[stage % 2]
         dst = cat[0] if stage == 1 else cat[(stage + 1) % 2]
+        specs = {b: openpose_stage_layers(stage, b) for b in (1, 2)}
+        # The first layer of both branches reads the same tensor: one conv with the two
+        # filter banks stacked (N = 256 fills the UMMA tile; one launch instead of two).
+        (n1, cin, c1, k, _), (n2, _, c2, _, _) = specs[1][0], specs[2][0]
+        w = torch.cat([sd[f'model{stage}_1.{n1}.weight'], sd[f'model{stage}_2.{n2}.weight']], 0)
+        b = torch.cat([sd[f'model{stage}_1.{n1}.bias'], sd[f'model{stage}_2.{n2}.bias']], 0)
+        first = P.buffer(c1 + c2)
+        kw = dict(in_coff=64) if stage == 1 else dict(in_map=OPENPOSE_CAT_MAP, cin_pad=192)
+        P.conv(w, one(c1 + c2), b.float().numpy(), src, first, act=relu, **kw)
         for branch in (1, 2):
-            layers = openpose_stage_layers(stage, branch)
-            x = src
+            layers = specs[branch]
+            x, x_coff = first, (branch - 1) * c1
             tmp = [P.buffer(128), P.buffer(128)]
             for li, (name, cin, cout, k, has_relu) in enumerate(layers):
+                if li == 0:
+                    continue
                 pfx = f'model{stage}_{branch}.{name}'
                 w, b = sd[pfx + '.weight'], sd[pfx + '.bias'].float().numpy()
                 act = relu if has_relu else nat.TR_ACT_NONE
-                kw = {}
-                if li == 0:
-                    if stage == 1:
-                        kw = dict(in_coff=64)
-                    else:
-                        kw = dict(in_map=OPENPOSE_CAT_MAP, cin_pad=192)
                 if li == len(layers) - 1:
-                    P.conv(w, one(cout), b, x, dst, out_coff=0 if branch == 1 else 40, act=act, **kw)
+                    P.conv(w, one(cout), b, x, dst, in_coff=x_coff, out_coff=0 if branch == 1 else 40,
+                           act=act)
                 else:
                     y = P.buffer(cout) if cout != 128 else tmp[li & 1]
-                    P.conv(w, one(cout), b, x, y, act=act, **kw)
-                    x = y
+                    P.conv(w, one(cout), b, x, y, in_coff=x_coff, act=act)
+                    x, x_coff = y, 0
     return P, {'maps': cat[(6 + 1) % 2], 'paf_coff': 0, 'heat_coff': 40}
 
 
