@@ -37,6 +37,7 @@ int tr_init(int device);
 enum { TR_OP_STEM = 0, TR_OP_CONV = 1, TR_OP_DWCONV = 2, TR_OP_MAXPOOL = 3, TR_OP_COPY = 4,
        TR_OP_VIEW = 5 };
 enum { TR_ACT_NONE = 0, TR_ACT_RELU = 1, TR_ACT_PRELU = 2 };
+enum { TR_SYNC_FORK = 1, TR_SYNC_JOIN = 2 };
 
 typedef struct tr_buffer_desc {
   int32_t channels;   /* total channels (multiple of 8) */
@@ -53,6 +54,9 @@ typedef struct tr_op_desc {
   int32_t cout_pad;                 /* filter rows in the blob (multiple of 16) */
   int32_t cin_real, cout_real;      /* un-padded channel counts (algorithmic flop accounting) */
   int32_t force_direct;             /* 1: never use the tcgen05 kernel for this op */
+  int32_t lane;                     /* 0: the caller's stream; 1: the net's side stream (independent branch) */
+  int32_t sync;                     /* TR_SYNC_FORK: ops of lane 1 issued later start after this op;
+                                       TR_SYNC_JOIN: this op starts after everything issued on lane 1 */
   int64_t w_off, scale_off, shift_off, slope_off, scale2_off, shift2_off; /* blob byte offsets, -1 = none */
   float in_scale, in_shift;         /* stem only: x' = x*in_scale + in_shift on in-bounds taps */
 } tr_op_desc;

@@ -24,6 +24,7 @@ SYMBOLS = (
 
 TR_OP_STEM, TR_OP_CONV, TR_OP_DWCONV, TR_OP_MAXPOOL, TR_OP_COPY, TR_OP_VIEW = range(6)
 TR_ACT_NONE, TR_ACT_RELU, TR_ACT_PRELU = range(3)
+TR_SYNC_FORK, TR_SYNC_JOIN = 1, 2
 TR_PEAK_CAP, TR_CAND_CAP, TR_HUMAN_CAP = 512, 4096, 128
 
 
@@ -41,7 +42,7 @@ class OpDesc(C.Structure):
         ('k', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32), ('act', C.c_int32),
         ('cout_pad', C.c_int32),
         ('cin_real', C.c_int32), ('cout_real', C.c_int32),
-        ('force_direct', C.c_int32),
+        ('force_direct', C.c_int32), ('lane', C.c_int32), ('sync', C.c_int32),
         ('w_off', C.c_int64), ('scale_off', C.c_int64), ('shift_off', C.c_int64),
         ('slope_off', C.c_int64), ('scale2_off', C.c_int64), ('shift2_off', C.c_int64),
         ('in_scale', C.c_float), ('in_shift', C.c_float),

@@ -68,6 +68,7 @@ struct TcParams {
   const __half* res; int res_cs, res_coff, res_up2, res_H, res_W;
   float* out_f32;
   int* err;   // device flag set on a pipeline timeout
+  int pdl_late;   // 1: let the next kernel start when this CTA begins its last tile, not at once
   int debug;  // timing experiments only: 1 skip TMA loads, 2 skip MMAs, 4 skip epilogue stores, 8 skip epilogue
   // halo mode: the input patch of a tile (+ filter halo) is loaded ONCE per channel chunk and
   // every tap's A operand is a shifted UMMA descriptor into it.  1: tile 8w x 16h, 2: 16w x 8h.
@@ -336,7 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // parameter staging — none of it reads the previous layer's output) may overlap the
   // tail of the previous kernel; activations are only touched after this wait.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (!p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // The producer and MMA loops run with the WHOLE warp converged and every
   // operand warp-uniform; one elected lane issues the TMA / tcgen05 instructions.
@@ -349,6 +350,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0, pphase = 0;
     const uint32_t sub_tx = p.rows * p.KC * 2 + p.N_tile * p.KC * 2;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      // A dependent CTA that is resident early only spins in griddepcontrol.wait while holding
+      // an SM that a kernel of another stream could use: release it late.
+      if (p.pdl_late && tile + int(gridDim.x) >= p.total_tiles)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
       const int wb = mt % p.tiles_w; mt /= p.tiles_w;
@@ -1034,6 +1039,8 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   p.out_f32 = a.out_f32;
   p.err = tc_error_flag();
   if (const char* dbg = getenv("TRB_TC_DEBUG")) p.debug = atoi(dbg);
+  p.pdl_late = 1;
+  if (const char* e = getenv("TRB_TC_PDL_LATE")) p.pdl_late = atoi(e);
   TR_CHECK(a.scale && a.shift, "epilogue scale/shift are required");
   TR_CHECK(a.act != ACT_PRELU || a.slope, "PReLU needs slopes");
   TR_CHECK(!a.out2.ptr || (a.scale2 && a.shift2), "second output needs scale2/shift2");

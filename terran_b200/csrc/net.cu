@@ -68,11 +68,19 @@ struct tr_net {
   size_t weight_bytes = 0;
   int force_direct = 0;
   int profile = 0;
+  int lanes = 1;                // 0: issue every op on the caller's stream
+  // Side stream for ops of lane 1 (independent branches that fill each other's scheduling
+  // tails) and the two events that order it against the caller's stream.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::map<std::tuple<int, int, int, int>, std::unique_ptr<Plan>> plans;
   Plan* last = nullptr;
   ~tr_net() {
     plans.clear();
     if (weights) cudaFree(weights);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
   }
 };
 
@@ -238,9 +246,43 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
   return raw;
 }
 
-void run_plan(Plan* plan, const uint8_t* image, int64_t sn, int64_t sh, int64_t sw, int64_t sc,
-              cudaStream_t s, bool profile) {
+void run_plan(tr_net* net, Plan* plan, const uint8_t* image, int64_t sn, int64_t sh, int64_t sw,
+              int64_t sc, cudaStream_t main_stream, bool profile) {
+  // Lanes: ops of lane 1 go to the net's side stream.  A FORK op marks the point of the main
+  // stream the side stream has to reach first; a JOIN op (and the end of the program) waits
+  // for the side stream.  Per-op profiling keeps everything on one stream.
+  const bool lanes = net->lanes && !profile;
+  bool fork_pending = false, side_dirty = false;
+  auto ensure_side = [&] {
+    if (net->side) return;
+    TR_CUDA(cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking));
+    TR_CUDA(cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming));
+    TR_CUDA(cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming));
+  };
+  auto join = [&] {
+    if (!side_dirty) return;
+    TR_CUDA(cudaEventRecord(net->ev_join, net->side));
+    TR_CUDA(cudaStreamWaitEvent(main_stream, net->ev_join, 0));
+    side_dirty = false;
+  };
   for (auto& po : plan->ops) {
+    cudaStream_t s = main_stream;
+    if (lanes) {
+      if (po.d.sync & TR_SYNC_JOIN) join();
+      if (po.d.lane == 1) {
+        ensure_side();
+        if (!fork_pending && !side_dirty) {      // no explicit fork point: everything issued so far
+          TR_CUDA(cudaEventRecord(net->ev_fork, main_stream));
+          fork_pending = true;
+        }
+        if (fork_pending) {
+          TR_CUDA(cudaStreamWaitEvent(net->side, net->ev_fork, 0));
+          fork_pending = false;
+        }
+        s = net->side;
+        side_dirty = true;
+      }
+    }
     if (profile && po.d.type != TR_OP_VIEW) {
       if (!po.e0) { TR_CUDA(cudaEventCreate(&po.e0)); TR_CUDA(cudaEventCreate(&po.e1)); }
       TR_CUDA(cudaEventRecord(po.e0, s));
@@ -262,7 +304,13 @@ void run_plan(Plan* plan, const uint8_t* image, int64_t sn, int64_t sh, int64_t 
       default: break;
     }
     if (profile && po.d.type != TR_OP_VIEW) TR_CUDA(cudaEventRecord(po.e1, s));
+    if (lanes && (po.d.sync & TR_SYNC_FORK)) {
+      ensure_side();
+      TR_CUDA(cudaEventRecord(net->ev_fork, main_stream));
+      fork_pending = true;
+    }
   }
+  join();
 }
 
 template <class F>
@@ -316,6 +364,7 @@ int tr_net_create(const tr_buffer_desc* buffers, int n_buffers, const tr_op_desc
     net->weight_bytes = weight_bytes;
     TR_CUDA(cudaMalloc(&net->weights, weight_bytes + 256));
     TR_CUDA(cudaMemcpy(net->weights, weights_host, weight_bytes, cudaMemcpyHostToDevice));
+    if (const char* e = getenv("TRB_LANES")) net->lanes = atoi(e) != 0;
     *out = net.release();
   });
 }
@@ -333,7 +382,7 @@ int tr_net_run(tr_net* net, const uint8_t* image_dev, int N, int H, int W, int64
     auto it = net->plans.find(std::make_tuple(N, H, W, net->force_direct));
     Plan* plan = it != net->plans.end() ? it->second.get() : build_plan(net, N, H, W);
     net->last = plan;
-    run_plan(plan, image_dev, stride_n, stride_h, stride_w, stride_c,
+    run_plan(net, plan, image_dev, stride_n, stride_h, stride_w, stride_c,
              static_cast<cudaStream_t>(stream), net->profile != 0);
   });
 }

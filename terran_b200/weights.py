@@ -62,7 +62,7 @@ class Program:
     def _op(self, **kw):
         d = dict(type=0, in_=-1, in_coff=0, in_c=0, out=-1, out_coff=0, out_c=0, out2=-1,
                  out2_coff=0, res=-1, res_coff=0, res_up2=0, k=1, stride=1, pad=0, act=0,
-                 cout_pad=0, cin_real=0, cout_real=0, force_direct=0, w_off=-1, scale_off=-1, shift_off=-1, slope_off=-1,
+                 cout_pad=0, cin_real=0, cout_real=0, force_direct=0, lane=0, sync=0, w_off=-1, scale_off=-1, shift_off=-1, slope_off=-1,
                  scale2_off=-1, shift2_off=-1, in_scale=1.0, in_shift=0.0)
         d.update(kw)
         self.ops.append(nat.OpDesc(**d))
@@ -70,7 +70,7 @@ class Program:
     def conv(self, w, scale, shift, in_, out, *, in_coff=0, in_map=None, cin_pad=None,
              out_coff=0, k=None, stride=1, pad=None, act=nat.TR_ACT_NONE, slope=None,
              res=-1, res_coff=0, res_up2=0, out2=-1, scale2=None, shift2=None,
-             force_direct=0):
+             force_direct=0, lane=0, sync=0):
         """w: (cout, cin, k, k) fp32 tensor.  ``in_map[c]`` is the position of
         reference input channel c inside the (padded) input view."""
         w = w.detach().float().numpy()
@@ -86,7 +86,7 @@ class Program:
         self._op(type=nat.TR_OP_CONV, in_=in_, in_coff=in_coff, in_c=cin_pad, out=out,
                  out_coff=out_coff, out_c=_r(cout, 8), out2=out2, res=res, res_coff=res_coff,
                  res_up2=res_up2, k=k, stride=stride, pad=pad, act=act, cout_pad=cout_pad,
-                 cin_real=cin, cout_real=cout, force_direct=force_direct,
+                 cin_real=cin, cout_real=cout, force_direct=force_direct, lane=lane, sync=sync,
                  w_off=self.add(packed, np.float16),
                  scale_off=self.add_vec(scale, cout_pad), shift_off=self.add_vec(shift, cout_pad),
                  slope_off=self.add_vec(slope, cout_pad),
@@ -339,7 +339,10 @@ def openpose_program(sd):
         b = torch.cat([sd[f'model{stage}_1.{n1}.bias'], sd[f'model{stage}_2.{n2}.bias']], 0)
         first = P.buffer(c1 + c2)
         kw = dict(in_coff=64) if stage == 1 else dict(in_map=OPENPOSE_CAT_MAP, cin_pad=192)
-        P.conv(w, one(c1 + c2), b.float().numpy(), src, first, act=relu, **kw)
+        # The two branches are independent until the next stage: branch 2 runs on the net's
+        # side stream so that each chain's kernels fill the scheduling tail of the other's.
+        P.conv(w, one(c1 + c2), b.float().numpy(), src, first, act=relu,
+               sync=nat.TR_SYNC_FORK | (nat.TR_SYNC_JOIN if stage > 1 else 0), **kw)
         for branch in (1, 2):
             layers = specs[branch]
             x, x_coff = first, (branch - 1) * c1
@@ -352,10 +355,10 @@ def openpose_program(sd):
                 act = relu if has_relu else nat.TR_ACT_NONE
                 if li == len(layers) - 1:
                     P.conv(w, one(cout), b, x, dst, in_coff=x_coff, out_coff=0 if branch == 1 else 40,
-                           act=act)
+                           act=act, lane=branch - 1)
                 else:
                     y = P.buffer(cout) if cout != 128 else tmp[li & 1]
-                    P.conv(w, one(cout), b, x, y, in_coff=x_coff, act=act)
+                    P.conv(w, one(cout), b, x, y, in_coff=x_coff, act=act, lane=branch - 1)
                     x, x_coff = y, 0
     return P, {'maps': cat[(6 + 1) % 2], 'paf_coff': 0, 'heat_coff': 40}
 

@@ -42,7 +42,7 @@ def test_op_desc_layout_matches_header(native):
             for n, t in fields]
     got = [(n.rstrip('_'), t) for n, t in native.OpDesc._fields_]
     assert got == want
-    assert C.sizeof(native.OpDesc) == 20 * 4 + 6 * 8 + 2 * 4
+    assert C.sizeof(native.OpDesc) == 22 * 4 + 6 * 8 + 2 * 4
 
 
 def test_no_gpu_calls_fail_loudly(native):
