@@ -17,7 +17,7 @@ for step in "$@"; do
   case $step in
     post)    run post 900 python -m pytest tests/test_gpu_post.py -q -m gpu --tb=short ;;
     direct)  run ops_direct 900 python -m pytest tests/test_gpu_ops.py -q -m gpu --tb=short -k "not tcgen05" ;;
-    tc)      run ops_tc 900 python -m pytest tests/test_gpu_ops.py -q -m gpu --tb=line -k "tcgen05" ;;
+    tc)      run ops_tc 900 python -m pytest tests/test_gpu_ops.py -q -m gpu --tb=line -k "tcgen05 or stream_k" ;;
     nets_direct) run nets_direct 1500 python -m pytest tests/test_gpu_nets.py -q -m gpu --tb=short -k "direct" ;;
     nets)    run nets 1500 python -m pytest tests/test_gpu_nets.py -q -m gpu --tb=short -k "not direct" ;;
     all)     run all 2400 python -m pytest tests -x -q -m gpu ;;

@@ -43,6 +43,13 @@ def profile(model_name, reps):
     for _ in range(3):
         run()
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    whole = e0.elapsed_time(e1) / 10
     net.set_profile(True)
     acc = None
     for _ in range(reps):
@@ -54,22 +61,38 @@ def profile(model_name, reps):
     acc /= reps
     ops = [op for op in net.program.ops if op.type != nat.TR_OP_VIEW]
     total = acc.sum()
-    print(f'== {model_name}: {len(ops)} launches, {total:.3f} ms per batch of {x.shape[0]} '
-          f'({x.shape[0] / total * 1e3:.0f} units/s)')
+    print(f'== {model_name}: {len(ops)} launches, {total:.3f} ms per batch of {x.shape[0]} summed over '
+          f'per-op events ({x.shape[0] / total * 1e3:.0f} units/s); {whole:.3f} ms back to back '
+          f'({x.shape[0] / whole * 1e3:.0f} units/s)')
     tc_ms = tc_fl = 0.0
+    groups = {}
     for i, (op, (_, is_tc, flops)) in enumerate(zip(ops, prof)):
         _, n, h, w, c = net.buffer_info(op.out)
         tf = flops / (acc[i] * 1e-3) / 1e12 if acc[i] > 0 else 0
         if is_tc:
             tc_ms += acc[i]
             tc_fl += flops
+        key = (NAMES[op.type], bool(is_tc), op.k, op.stride, op.cin_real or op.in_c,
+               op.cout_real or op.out_c, h, w, op.res >= 0, op.out2 >= 0)
+        g = groups.setdefault(key, [0, 0.0, 0.0])
+        g[0] += 1; g[1] += acc[i]; g[2] += flops
+        if BRIEF:
+            continue
         print(f'{i:3d} {NAMES[op.type]:5s}{"*" if is_tc else " "} k{op.k} s{op.stride} '
               f'{op.cin_real or op.in_c:4d}->{op.cout_real or op.out_c:4d} out {h:3d}x{w:3d} '
               f'{acc[i] * 1e3:8.1f} us {100 * acc[i] / total:5.1f}% {tf:7.1f} TFLOP/s')
+    if BRIEF:
+        for key, (cnt, ms, fl) in groups.items():
+            name, is_tc, k, st, ci, co, h, w, has_res, has_out2 = key
+            print(f'{cnt:3d}x {name:5s}{"*" if is_tc else " "} k{k} s{st} {ci:4d}->{co:4d} out {h:3d}x{w:3d}'
+                  f'{" +res" if has_res else ""}{" +out2" if has_out2 else ""}: {ms / cnt * 1e3:8.1f} us each, '
+                  f'{100 * ms / total:5.1f}%, {fl / (ms * 1e-3) / 1e12 if ms else 0:7.1f} TFLOP/s')
     if tc_ms:
         print(f'   tcgen05 total: {tc_ms:.3f} ms, {tc_fl / 1e9:.1f} GFLOP, '
               f'{tc_fl / (tc_ms * 1e-3) / 1e12:.1f} TFLOP/s')
 
+
+BRIEF = '--brief' in sys.argv
 
 if __name__ == '__main__':
     names = [a for a in sys.argv[1:] if not a.startswith('--')] or ['retinaface', 'openpose']

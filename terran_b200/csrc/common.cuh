@@ -66,9 +66,13 @@ struct ConvArgs {
   int kh = 1, kw = 1, stride = 1, pad = 0;
   int act = ACT_NONE;
   int H_out = 0, W_out = 0;
+  // Stream-K scratch shared by the plans of one stream (conv_tc_sk_scratch_bytes() bytes,
+  // zero-initialised); null: the plan allocates its own.
+  void* sk_scratch = nullptr;
 };
 
 // conv_tc.cu
+size_t conv_tc_sk_scratch_bytes();
 bool conv_tc_eligible(const ConvArgs& a);
 struct ConvTcPlan;   // opaque: tensor maps + launch geometry
 ConvTcPlan* conv_tc_plan_create(const ConvArgs& a);

@@ -68,6 +68,14 @@ struct TcParams {
   const __half* res; int res_cs, res_coff, res_up2, res_H, res_W;
   float* out_f32;
   int* err;   // device flag set on a pipeline timeout
+  // Stream-K: the CTAs split the launch's (tile, stage-iteration) sequence into equal
+  // contiguous ranges instead of whole tiles, so no SM idles in the last scheduling round.
+  // A range may start inside a tile (its TAIL: the raw fp32 accumulators go to sk_ws[cta] and
+  // sk_flags[cta] is raised) and end inside one (its HEAD: the CTA adds the tail partial of
+  // CTA + 1 — computed first thing by that CTA — and runs the normal epilogue).
+  int sk;
+  float* sk_ws;
+  int* sk_flags;
   int pdl_late;   // 1: let the next kernel start when this CTA begins its last tile, not at once
   int debug;  // timing experiments only: 1 skip TMA loads, 2 skip MMAs, 4 skip epilogue stores, 8 skip epilogue
   // halo mode: the input patch of a tile (+ filter halo) is loaded ONCE per channel chunk and
@@ -198,6 +206,38 @@ __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&v)[16
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Walks the tile segments of one CTA: whole tiles with the static stride, or the CTA's
+// contiguous share of all stage iterations under stream-K.
+struct TileWalk {
+  long long pos, end;
+  int tile;
+};
+__device__ __forceinline__ TileWalk walk_begin(const TcParams& p) {
+  TileWalk w;
+  const long long total = static_cast<long long>(p.total_tiles) * p.iters;
+  w.pos = p.sk ? total * blockIdx.x / gridDim.x : 0;
+  w.end = p.sk ? total * (blockIdx.x + 1) / gridDim.x : 0;
+  w.tile = blockIdx.x;
+  return w;
+}
+__device__ __forceinline__ bool walk_next(const TcParams& p, TileWalk& w, int& tile, int& it0, int& it1) {
+  if (p.sk) {
+    if (w.pos >= w.end) return false;
+    tile = static_cast<int>(w.pos / p.iters);
+    it0 = static_cast<int>(w.pos - static_cast<long long>(tile) * p.iters);
+    it1 = static_cast<int>(min(static_cast<long long>(p.iters), it0 + (w.end - w.pos)));
+    w.pos += it1 - it0;
+    return true;
+  }
+  if (w.tile >= p.total_tiles) return false;
+  tile = w.tile; it0 = 0; it1 = p.iters;
+  w.tile += gridDim.x;
+  return true;
+}
+__device__ __forceinline__ bool walk_done(const TcParams& p, const TileWalk& w) {
+  return p.sk ? w.pos >= w.end : w.tile >= p.total_tiles;
 }
 
 struct EpiCtx {
@@ -349,10 +389,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0, pb = 0;
     uint32_t phase = 0, pphase = 0;
     const uint32_t sub_tx = p.rows * p.KC * 2 + p.N_tile * p.KC * 2;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    TileWalk walk = walk_begin(p);
+    int tile, it0, it1;
+    while (walk_next(p, walk, tile, it0, it1)) {
       // A dependent CTA that is resident early only spins in griddepcontrol.wait while holding
       // an SM that a kernel of another stream could use: release it late.
-      if (p.pdl_late && tile + int(gridDim.x) >= p.total_tiles)
+      if (p.pdl_late && walk_done(p, walk))
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
@@ -389,8 +431,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         continue;
       }
-      int r = 0, s = 0, kc = 0, kb = 0;           // running (tap row, tap col, channel chunk)
-      for (int it = 0; it < p.iters; ++it) {
+      int kb = it0 * p.sub;                       // running (tap row, tap col, channel chunk)
+      int kc = kb % p.kchunks, s = (kb / p.kchunks) % p.kw, r = kb / (p.kchunks * p.kw);
+      for (int it = it0; it < it1; ++it) {
         const int nsub = min(p.sub, p.k_blocks - kb);
         mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
         const uint32_t sa = ring + stage * p.stage_bytes;
@@ -433,13 +476,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t a_lo0 = umma_desc_lo(ring);
     const uint32_t stage_step = p.stage_bytes >> 4, sub_step = p.sub_bytes >> 4,
                    b_off = p.a_bytes >> 4;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_it) {
+    TileWalk walk = walk_begin(p);
+    int tile, it0, it1;
+    for (; walk_next(p, walk, tile, it0, it1); ++tile_it) {
       const int acc = tile_it & 1;
       const uint32_t acc_phase = (tile_it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + acc * p.N_tile;
-      int kb = 0;
+      int kb = it0 * p.sub;
       uint32_t accumulate = 0;
       if (p.halo) {
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -479,7 +524,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         continue;
       }
-      for (int it = 0; it < p.iters; ++it) {
+      for (int it = it0; it < it1; ++it) {
         const int nsub = min(p.sub, p.k_blocks - kb);
         kb += nsub;
         mbar_wait(full_bar(stage), phase, p.err, 3);
@@ -496,7 +541,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
-          if (it == p.iters - 1) umma_commit(tfull_bar(acc));
+          if (it == it1 - 1) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -517,7 +562,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     e.cpad = cpad;
     e.sp = reinterpret_cast<const float*>(smem_raw + (params_s - smem_u32(smem_raw)));
     int tile_it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_it) {
+    TileWalk walk = walk_begin(p);
+    int tile, it0, it1;
+    for (; walk_next(p, walk, tile, it0, it1); ++tile_it) {
       const int acc = tile_it & 1;
       const uint32_t acc_phase = (tile_it >> 1) & 1u;
       const int nt = tile % p.n_tiles;
@@ -536,28 +583,91 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.N_tile;
       const int cn0 = nt * p.N_tile;
-      // software-pipelined TMEM reads: chunk i+2 is in flight while chunk i is stored
       uint32_t va[16], vb[16];
       int c = half;
+      if (it0 > 0) {
+        // TAIL of a tile whose first iterations belong to the previous CTA: park the raw
+        // accumulators, laid out [chunk][row][16] so that a warp writes 2 KB runs.
+        float4* ws = reinterpret_cast<float4*>(p.sk_ws + static_cast<size_t>(blockIdx.x) * 128 * p.N_tile);
+        for (; c < nchunks; c += 2) {
+          __syncwarp();
+          tmem_ld16_async(taddr + c * 16, va);
+          tmem_ld_wait();
+          float4* dst = ws + (c * 128 + row) * 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            __stcg(dst + j, make_float4(__uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]),
+                                        __uint_as_float(va[4 * j + 2]), __uint_as_float(va[4 * j + 3])));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(tempty_bar(acc));
+          atomicAdd(p.sk_flags + blockIdx.x, 1);
+        }
+        continue;
+      }
+      const float4* partial = nullptr;
+      if (it1 < p.iters) {
+        // HEAD: the rest of this tile is the tail partial of the next CTA (the first thing
+        // that CTA computes).  All kEpiWarps warps of both CTAs take part; the last reader
+        // re-arms the flag for the next launch.
+        int* flag = p.sk_flags + blockIdx.x + 1;
+        if (lane == 0) {
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile int*>(flag) < kEpiWarps) {
+            if (clock64() - t0 > 4000000000LL) {
+              if (p.err) atomicExch(p.err, 9);
+              __threadfence_system();
+              __trap();
+            }
+          }
+          __threadfence();
+        }
+        __syncwarp();
+        partial = reinterpret_cast<const float4*>(p.sk_ws + static_cast<size_t>(blockIdx.x + 1) * 128 * p.N_tile);
+      }
+      auto add_partial = [&](uint32_t (&v)[16], int chunk) {
+        if (!partial) return;
+        const float4* src = partial + (chunk * 128 + row) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 f = __ldcg(src + j);
+          v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + f.x);
+          v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + f.y);
+          v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + f.z);
+          v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + f.w);
+        }
+      };
+      // software-pipelined TMEM reads: chunk i+2 is in flight while chunk i is stored
       __syncwarp();
       if (c < nchunks) tmem_ld16_async(taddr + c * 16, va);
       while (c < nchunks) {
         __syncwarp();                       // tcgen05.ld / wait::ld are warp-collective
         tmem_ld_wait();
         if (c + 2 < nchunks) tmem_ld16_async(taddr + (c + 2) * 16, vb);
+        add_partial(va, c);
         epilogue_chunk(p, e, va, cn0 + c * 16);
         c += 2;
         if (c >= nchunks) break;
         __syncwarp();
         tmem_ld_wait();
         if (c + 2 < nchunks) tmem_ld16_async(taddr + (c + 2) * 16, va);
+        add_partial(vb, c);
         epilogue_chunk(p, e, vb, cn0 + c * 16);
         c += 2;
       }
       // Release the accumulator back to the MMA warp.
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        mbar_arrive(tempty_bar(acc));
+        if (partial) {
+          int* flag = p.sk_flags + blockIdx.x + 1;
+          if (atomicAdd(flag, 1) == 2 * kEpiWarps - 1) atomicExch(flag, 0);
+        }
+      }
     }
   }
 
@@ -896,9 +1006,14 @@ KernelFn kernel_for(int kc) {
 
 }  // namespace
 
+// Stream-K scratch: one flag per CTA (+1), then per CTA a 128 x 256 fp32 accumulator tile.
+constexpr size_t kSkFlagBytes = 1024;
+size_t conv_tc_sk_scratch_bytes() { return kSkFlagBytes + size_t(num_sms()) * 128 * 256 * 4; }
+
 struct ConvTcPlan {
   CUtensorMap tmA, tmB;
   TcParams p;
+  void* sk_own = nullptr;
   int grid;
   uint32_t smem;
   double flops;
@@ -1040,6 +1155,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   p.err = tc_error_flag();
   if (const char* dbg = getenv("TRB_TC_DEBUG")) p.debug = atoi(dbg);
   p.pdl_late = 1;
+  p.pdl_late = 1;
   if (const char* e = getenv("TRB_TC_PDL_LATE")) p.pdl_late = atoi(e);
   TR_CHECK(a.scale && a.shift, "epilogue scale/shift are required");
   TR_CHECK(a.act != ACT_PRELU || a.slope, "PReLU needs slopes");
@@ -1080,12 +1196,39 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   plan->grid = p.cta2 ? 2 * std::min(p.pair_units, num_sms() / 2) : std::min(p.total_tiles, num_sms());
   plan->smem = p.ring_off + p.stages * p.stage_bytes + param_bytes + 1024 /*alignment*/ +
                8 * (2 * kMaxStages + 10) + 16;
+  {
+    // Stream-K where whole-tile scheduling leaves SMs idle in the last round.  Measured
+    // (profiles/r01_stream_k.txt): the partial-tile hand-over costs ~8 us per launch with
+    // N = 128 tiles and ~18 us with N = 256, so it pays only where the idle tail is longer.
+    int want = 1;                                     // 0 off, 1 auto, 2 whenever possible
+    if (const char* e = getenv("TRB_TC_SK")) want = atoi(e);
+    const int rounds = ceil_div(p.total_tiles, plan->grid);
+    const double tile_us = 2.0 * 128 * p.N_tile * p.k_blocks * p.KC / 7.5e6;   // ~7.5 TFLOP/s per SM
+    const double saved_us = (rounds - double(p.total_tiles) / plan->grid) * tile_us;
+    const bool ok = !p.halo && !p.cta2 && p.total_tiles > plan->grid && p.iters >= 2 &&
+                    plan->grid < int(kSkFlagBytes / 4);
+    const bool worth = p.iters >= 4 && saved_us >= 14.0;
+    if (ok && (want == 2 || (want == 1 && worth))) {
+      void* scratch = a.sk_scratch;
+      if (!scratch) {
+        TR_CUDA(cudaMalloc(&plan->sk_own, conv_tc_sk_scratch_bytes()));
+        TR_CUDA(cudaMemset(plan->sk_own, 0, kSkFlagBytes));
+        scratch = plan->sk_own;
+      }
+      p.sk = 1;
+      p.sk_flags = static_cast<int*>(scratch);
+      p.sk_ws = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + kSkFlagBytes);
+    }
+  }
   plan->flops = 2.0 * p.N * p.H_out * p.W_out * double(a.cout_pad) * a.kh * a.kw * a.cin_pad;
   kernel_for(p.KC);
   return plan;
 }
 
-void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
+void conv_tc_plan_destroy(ConvTcPlan* p) {
+  if (p->sk_own) cudaFree(p->sk_own);
+  delete p;
+}
 
 double conv_tc_plan_flops(const ConvTcPlan* p) { return p->flops; }
 

@@ -71,6 +71,7 @@ struct tr_net {
   int lanes = 1;                // 0: issue every op on the caller's stream
   // Side stream for ops of lane 1 (independent branches that fill each other's scheduling
   // tails) and the two events that order it against the caller's stream.
+  void* sk_scratch[2] = {nullptr, nullptr};   // stream-K scratch, one per lane
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::map<std::tuple<int, int, int, int>, std::unique_ptr<Plan>> plans;
@@ -78,6 +79,8 @@ struct tr_net {
   ~tr_net() {
     plans.clear();
     if (weights) cudaFree(weights);
+    for (void* s : sk_scratch)
+      if (s) cudaFree(s);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (side) cudaStreamDestroy(side);
@@ -213,6 +216,12 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
         po.flops = 2.0 * B[d.out].N * a.H_out * a.W_out * double(d.cout_real) * d.k * d.k * d.cin_real;
         const bool use_tc = !net->force_direct && !d.force_direct && conv_tc_eligible(a);
         if (use_tc) {
+          void*& scratch = net->sk_scratch[d.lane == 1];
+          if (!scratch) {
+            TR_CUDA(cudaMalloc(&scratch, conv_tc_sk_scratch_bytes()));
+            TR_CUDA(cudaMemset(scratch, 0, conv_tc_sk_scratch_bytes()));
+          }
+          a.sk_scratch = scratch;
           po.tc = conv_tc_plan_create(a);
           plan->tc_flops += po.flops;
           plan->tc_launches++;

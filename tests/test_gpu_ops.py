@@ -68,6 +68,38 @@ def test_conv_matches_reference(native, case, use_tc):
     assert torch.isfinite(out.float()).all() and err <= tol, describe_mismatch(out, ref, tol)
 
 
+# Stream-K (the CTAs split the k-iterations of all tiles evenly; split tiles are completed
+# through an fp32 partial in global memory): shapes with more tiles than SMs.
+STREAMK_CASES = [
+    (24, 23, 40, 64, 64, 3, 1, 1, None, 'sk-conv3'),
+    (24, 23, 40, 512, 256, 1, 1, 2, 'same', 'sk-gemm-res'),
+    (24, 46, 80, 128, 128, 3, 2, 0, None, 'sk-stride2'),
+    (12, 23, 40, 128, 512, 3, 1, 1, None, 'sk-2ntiles'),
+    (20, 23, 40, 128, 128, 7, 1, 1, None, 'sk-conv7'),
+]
+
+
+@pytest.mark.parametrize('case', STREAMK_CASES, ids=[c[-1] for c in STREAMK_CASES])
+def test_conv_stream_k(native, case, monkeypatch):
+    N, H, W, cin, cout, k, stride, act, res_kind, tag = case
+    x, w, scale, shift, slope, res, up2 = make_case(case)
+    kw = dict(stride=stride, act=act, slope=slope, res=res, res_up2=up2)
+    monkeypatch.setenv('TRB_TC_HALO', '0')
+    monkeypatch.setenv('TRB_TC_SK', '0')
+    whole, _ = conv2d_native(native, x, w, scale, shift, use_tc=True, out_f32=True, **kw)
+    monkeypatch.setenv('TRB_TC_SK', '2')
+    split, _ = conv2d_native(native, x, w, scale, shift, use_tc=True, out_f32=True, **kw)
+    again, _ = conv2d_native(native, x, w, scale, shift, use_tc=True, out_f32=True, **kw)
+    ref = conv2d_reference(x, w, scale, shift, **kw)
+    tol = 1e-4 * max(1.0, float(ref.abs().max()))
+    assert (split.cpu().double() - ref).abs().max() <= tol, describe_mismatch(split, ref, tol)
+    assert (whole.cpu().double() - ref).abs().max() <= tol
+    # the split really happened (a different fp32 summation order shows in the last bit of
+    # some outputs) and is deterministic
+    assert not torch.equal(split, whole)
+    assert torch.equal(split, again)
+
+
 def test_conv_tc_fp32_output(native):
     case = (2, 13, 24, 64, 32, 1, 1, 0, None, 'head')
     x, w, scale, shift, slope, res, up2 = make_case(case, seed=3)
