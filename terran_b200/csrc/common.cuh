@@ -93,6 +93,7 @@ struct StemArgs {
   const float* scale; const float* shift; const float* slope;
   const float* scale2; const float* shift2;
   int cout, stride, act;
+  int use_mma;            // 1: tensor-core kernel (fp16 operands), 0: fp32 CUDA-core kernel
 };
 void stem_launch(const StemArgs& a, cudaStream_t s);
 

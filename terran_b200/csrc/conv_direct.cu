@@ -218,6 +218,184 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemArgs a, int H_out, 
   }
 }
 
+// Tensor-core stem: the same 3x3 / 3-channel conv as an implicit GEMM on the warp-level
+// MMA (mma.sync m16n8k16, fp16 x fp16 -> fp32): M = 16 consecutive output pixels of a row,
+// N = COUT, K = 27 taps padded to 32.  The CUDA-core kernel above needs 27*COUT FMAs per
+// pixel and is FMA-issue bound ~6x above the HBM time of the layer; here the MACs are 2*NT
+// MMAs per 16 pixels and the kernel is bound by writing the activations.
+//   A[m][k]  = x(pixel m, tap k) + in_shift/in_scale   (exact in fp16: u8 plus a half-integer)
+//   B[k][n]  = w[n][k] * scale[n] * in_scale           (rounded to fp16 once)
+//   acc init = shift[n]
+// so the epilogue is activation + fp16 pack.  Zero padding: out-of-bounds taps are staged as
+// 0, like the reference which pads after the input affine.  The block stages the u8 input
+// window of an 8 x 64 pixel tile in smem as fp16; with k = r*9 + s*3 + c the 9 values of a
+// filter row are contiguous there.
+__device__ __forceinline__ void mma_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int COUT, int STRIDE, int ACT>
+__global__ void __launch_bounds__(256, 2) stem_mma_kernel(const StemArgs a, int H_out, int W_out, float in_off,
+                                                          int tiles_w, int tiles_h, int total_tiles) {
+  constexpr int NT = COUT / 8, TH = 8, TW = 64, SEGS = TW / 16;
+  constexpr int IN_H = (TH - 1) * STRIDE + 3, IN_W = (TW - 1) * STRIDE + 3;
+  constexpr int ROWB = IN_W * 3;                     // window row: ROWB contiguous (col, channel) values
+  constexpr int PASSES = (ROWB + 255) / 256;
+  constexpr int ZERO = IN_H * ROWB;                  // a slot that always holds 0 (padded K taps)
+  constexpr int PITCH = COUT + 8;                    // halfs; conflict-free fragment stores
+  __shared__ __half s_in[IN_H * ROWB + 2];
+  __shared__ __align__(16) __half s_out[8][16 * PITCH];
+  __shared__ float sp[5 * COUT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+    sp[i] = a.scale[i];
+    sp[COUT + i] = a.shift[i];
+    sp[2 * COUT + i] = a.slope ? a.slope[i] : 0.f;
+    sp[3 * COUT + i] = a.scale2 ? a.scale2[i] : 1.f;
+    sp[4 * COUT + i] = a.shift2 ? a.shift2[i] : 0.f;
+  }
+  if (threadIdx.x < 2) s_in[ZERO + threadIdx.x] = __float2half(0.f);
+  // B fragments (whole filter bank) stay in registers: b[nt][kstep][half] = w'[n = nt*8+g][k, k+1]
+  uint32_t bfrag[NT][2][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int o = nt * 8 + g;
+    const float fold = a.scale[o] * a.in_scale;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = ks * 16 + h * 8 + 2 * t;
+        const float w0 = k < 27 ? a.w[o * 27 + k] * fold : 0.f;
+        const float w1 = k + 1 < 27 ? a.w[o * 27 + k + 1] * fold : 0.f;
+        const __half2 hw = __floats2half2_rn(w0, w1);
+        bfrag[nt][ks][h] = *reinterpret_cast<const uint32_t*>(&hw);
+      }
+  }
+  // smem offsets of this thread's 8 taps relative to the window origin of a pixel
+  // (k = r*9 + s*3 + c; -1: a padded tap, read from the ZERO slot)
+  int koff[2][2][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = ks * 16 + h * 8 + 2 * t + e;
+        koff[ks][h][e] = k < 27 ? (k / 9) * ROWB + k % 9 : -1;
+      }
+  // Staging map: thread x of pass p owns value x + 256 p of every window row.
+  long goff[PASSES];
+  int gcol[PASSES];
+#pragma unroll
+  for (int p = 0; p < PASSES; ++p) {
+    const int x = threadIdx.x + p * 256;
+    gcol[p] = x < ROWB ? x / 3 : -(1 << 20);
+    goff[p] = (x / 3) * a.sw + (x % 3) * a.sc;
+  }
+  // The u8 window of the NEXT tile is fetched into registers (all loads in flight at once)
+  // while the current tile is computed; 0xffff marks an out-of-bounds (zero) tap.
+  uint16_t raw[IN_H][PASSES];
+  auto fetch = [&](int tile) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int ih0 = th * TH * STRIDE - 1, iw0 = tw * TW * STRIDE - 1;
+    const uint8_t* img = a.in + n * a.sn + ih0 * a.sh + iw0 * a.sw;
+    bool cok[PASSES];
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) cok[p] = iw0 + gcol[p] >= 0 && iw0 + gcol[p] < a.W;
+#pragma unroll
+    for (int r = 0; r < IN_H; ++r) {
+      const bool rok = ih0 + r >= 0 && ih0 + r < a.H;
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p)
+        raw[r][p] = rok && cok[p] ? static_cast<uint16_t>(img[r * a.sh + goff[p]]) : uint16_t(0xffff);
+    }
+  };
+  if (blockIdx.x < total_tiles) fetch(blockIdx.x);
+  // flush map: lane -> (row, 16-byte vector) of the 16 x COUT staging tile
+  const int frow = lane / NT, fvec = lane % NT;
+  constexpr int FROWS = 32 / NT > 16 ? 16 : 32 / NT;  // rows covered per flush instruction
+
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int oh0 = th * TH, ow0 = tw * TW;
+    __syncthreads();                                 // the previous tile's window is consumed
+#pragma unroll
+    for (int r = 0; r < IN_H; ++r)
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+        const int x = threadIdx.x + p * 256;
+        if (x < ROWB)
+          s_in[r * ROWB + x] = __float2half_rn(raw[r][p] == 0xffff ? 0.f : static_cast<float>(raw[r][p]) + in_off);
+      }
+    __syncthreads();
+    if (tile + gridDim.x < total_tiles) fetch(tile + gridDim.x);
+
+    for (int seg = warp; seg < TH * SEGS; seg += 8) {
+      const int r_l = seg / SEGS, c_l = (seg % SEGS) * 16;
+      const int oh = oh0 + r_l, owb = ow0 + c_l;
+      if (oh >= H_out || owb >= W_out) continue;     // warp-uniform
+      const int base0 = r_l * STRIDE * ROWB + (c_l + g) * STRIDE * 3;
+      const int base1 = base0 + 8 * STRIDE * 3;
+      uint32_t afrag[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k0 = koff[ks][h][0], k1 = koff[ks][h][1];
+          const __half2 lo = __halves2half2(s_in[k0 >= 0 ? base0 + k0 : ZERO], s_in[k1 >= 0 ? base0 + k1 : ZERO]);
+          const __half2 hi = __halves2half2(s_in[k0 >= 0 ? base1 + k0 : ZERO], s_in[k1 >= 0 ? base1 + k1 : ZERO]);
+          afrag[ks][2 * h] = *reinterpret_cast<const uint32_t*>(&lo);        // rows g     (a0 / a2)
+          afrag[ks][2 * h + 1] = *reinterpret_cast<const uint32_t*>(&hi);    // rows g + 8 (a1 / a3)
+        }
+      float acc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float2 sh = *reinterpret_cast<const float2*>(sp + COUT + nt * 8 + 2 * t);
+        acc[nt][0] = acc[nt][2] = sh.x;
+        acc[nt][1] = acc[nt][3] = sh.y;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) mma_m16n8k16(acc[nt], afrag[ks], bfrag[nt][ks][0], bfrag[nt][ks][1]);
+      }
+      __half* so = s_out[warp];
+      const long pix0 = (static_cast<long>(n) * H_out + oh) * W_out + owb;
+#pragma unroll 1
+      for (int pass = 0; pass < (a.out2.ptr ? 2 : 1); ++pass) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int c = nt * 8 + 2 * t;
+          float y[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            y[j] = acc[nt][j];
+            if (ACT == ACT_RELU) y[j] = fmaxf(y[j], 0.f);
+            if (ACT == ACT_PRELU) y[j] = y[j] >= 0.f ? y[j] : y[j] * sp[2 * COUT + c + (j & 1)];
+            if (pass) y[j] = fmaf(y[j], sp[3 * COUT + c + (j & 1)], sp[4 * COUT + c + (j & 1)]);
+          }
+          *reinterpret_cast<__half2*>(so + g * PITCH + c) = __floats2half2_rn(y[0], y[1]);
+          *reinterpret_cast<__half2*>(so + (g + 8) * PITCH + c) = __floats2half2_rn(y[2], y[3]);
+        }
+        __syncwarp();
+        const View& ov = pass ? a.out2 : a.out;
+        __half* gp = ov.ptr + (pix0 + frow) * ov.cs + ov.coff + fvec * 8;
+        const __half* sp_row = so + frow * PITCH + fvec * 8;
+#pragma unroll
+        for (int i = 0; i < 16 / FROWS; ++i) {
+          const int row = frow + i * FROWS;
+          if (row < 16 && owb + row < W_out)
+            *reinterpret_cast<uint4*>(gp + static_cast<long>(i) * FROWS * ov.cs) =
+                *reinterpret_cast<const uint4*>(sp_row + i * FROWS * PITCH);
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------- depthwise 3x3
 __global__ void __launch_bounds__(256) dwconv_kernel(const DwArgs a, int H_out, int W_out) {
   const int groups = a.in.C / 8;
@@ -414,11 +592,40 @@ void conv_direct_launch(const ConvArgs& a, cudaStream_t s) {
 
 void stem_launch(const StemArgs& a, cudaStream_t s) {
   const int H_out = (a.H + 2 - 3) / a.stride + 1, W_out = (a.W + 2 - 3) / a.stride + 1;
+  TR_CHECK((a.cout == 8 && a.stride == 2) || (a.cout == 64 && a.stride == 1),
+           "stem conv supports (8 channels, stride 2) or (64 channels, stride 1)");
+  // Tensor-core variant when the input affine folds exactly: x*s + b = s*(x + b/s) with
+  // x + b/s representable in fp16 (an integer or half-integer below 2048).
+  float in_off = a.in_shift / a.in_scale;
+  if (fabsf(in_off * 2.f - rintf(in_off * 2.f)) < 1e-3f) in_off = rintf(in_off * 2.f) * 0.5f;   // 1/255 is inexact
+  static const bool mma_ok = [] { const char* e = getenv("TRB_STEM_MMA"); return !e || atoi(e) != 0; }();
+  if (mma_ok && a.use_mma && in_off * 2.f == rintf(in_off * 2.f) && fabsf(in_off) <= 1024.f) {
+    const int tiles_w = (W_out + 63) / 64, tiles_h = (H_out + 7) / 8;
+    const long total = static_cast<long>(a.N) * tiles_w * tiles_h;
+    TR_CHECK(total < (1L << 31), "stem: too many tiles");
+    int sms = 148;
+    int dev = 0;
+    TR_CUDA(cudaGetDevice(&dev));
+    TR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const unsigned grid = static_cast<unsigned>(std::min<long>(total, 4L * sms));
+    bool done = true;
+    if (a.cout == 8 && a.act == ACT_RELU)
+      stem_mma_kernel<8, 2, ACT_RELU><<<grid, 256, 0, s>>>(a, H_out, W_out, in_off, tiles_w, tiles_h, int(total));
+    else if (a.cout == 64 && a.act == ACT_RELU)
+      stem_mma_kernel<64, 1, ACT_RELU><<<grid, 256, 0, s>>>(a, H_out, W_out, in_off, tiles_w, tiles_h, int(total));
+    else if (a.cout == 64 && a.act == ACT_PRELU)
+      stem_mma_kernel<64, 1, ACT_PRELU><<<grid, 256, 0, s>>>(a, H_out, W_out, in_off, tiles_w, tiles_h, int(total));
+    else
+      done = false;
+    if (done) {
+      TR_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   const long nthreads = static_cast<long>(a.N) * H_out * ((W_out + 3) / 4);
   const unsigned grid = static_cast<unsigned>((nthreads + 127) / 128);
   if (a.cout == 8 && a.stride == 2) stem_kernel<8, 2><<<grid, 128, 0, s>>>(a, H_out, W_out);
-  else if (a.cout == 64 && a.stride == 1) stem_kernel<64, 1><<<grid, 128, 0, s>>>(a, H_out, W_out);
-  else fail("stem conv supports (8 channels, stride 2) or (64 channels, stride 1)");
+  else stem_kernel<64, 1><<<grid, 128, 0, s>>>(a, H_out, W_out);
   TR_CUDA(cudaGetLastError());
 }
 

@@ -184,6 +184,7 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
         a.slope = blob_ptr<float>(net, d.slope_off);
         a.scale2 = blob_ptr<float>(net, d.scale2_off); a.shift2 = blob_ptr<float>(net, d.shift2_off);
         a.cout = d.out_c; a.stride = d.stride; a.act = d.act;
+        a.use_mma = !net->force_direct && !d.force_direct;
         TR_CHECK(d.k == 3 && d.pad == 1, "stem is 3x3 pad 1");
         TR_CHECK(!B[d.out].f32, "stem output is fp16");
         break;
