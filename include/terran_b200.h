@@ -35,7 +35,14 @@ int tr_init(int device);
  * Replaces nn.Module construction + load_state_dict
  * (retinaface/wrapper.py:16-22, arcface/wrapper.py:13-19, openpose/wrapper.py:26-34). */
 enum { TR_OP_STEM = 0, TR_OP_CONV = 1, TR_OP_DWCONV = 2, TR_OP_MAXPOOL = 3, TR_OP_COPY = 4,
-       TR_OP_VIEW = 5 };
+       TR_OP_VIEW = 5,
+       /* depthwise 3x3 (+BN+ReLU) fused with the 1x1 conv (+BN+ReLU) that follows it: the
+        * sep_block of one ConvSepBlock and the conv_block of the next (retinaface/model.py:6-50).
+        * k/stride/pad describe the depthwise stage, w/scale/shift the 1x1, dw_* the depthwise. */
+       TR_OP_SEPCONV = 6 };
+/* tr_op_desc.engine */
+enum { TR_ENGINE_AUTO = 0,   /* tcgen05 implicit GEMM where eligible, else the direct kernel */
+       TR_ENGINE_MMA = 1 };  /* warp-level mma.sync kernel for small-channel layers where eligible */
 enum { TR_ACT_NONE = 0, TR_ACT_RELU = 1, TR_ACT_PRELU = 2 };
 enum { TR_SYNC_FORK = 1, TR_SYNC_JOIN = 2 };
 
@@ -59,6 +66,10 @@ typedef struct tr_op_desc {
                                        TR_SYNC_JOIN: this op starts after everything issued on lane 1 */
   int64_t w_off, scale_off, shift_off, slope_off, scale2_off, shift2_off; /* blob byte offsets, -1 = none */
   float in_scale, in_shift;         /* stem only: x' = x*in_scale + in_shift on in-bounds taps */
+  int64_t dw_w_off, dw_scale_off, dw_shift_off;   /* TR_OP_SEPCONV: depthwise filter [3][3][C] fp32 + BN */
+  int64_t dw_w16_off;               /* the same filter rounded to fp16 (fused kernel operand) */
+  int32_t engine;                   /* TR_OP_CONV: TR_ENGINE_* */
+  int32_t reserved;
 } tr_op_desc;
 
 int tr_net_create(const tr_buffer_desc* buffers, int n_buffers, const tr_op_desc* ops, int n_ops,
@@ -90,12 +101,22 @@ int tr_net_profile(tr_net* net, float* ms, int32_t* is_tc, double* flops, int ca
 
 /* ---- single ops (parity tests, roofline micro-benchmarks) ---------------- */
 /* NHWC fp16 convolution with fused scale/shift/activation/residual epilogue.
- * use_tc: 1 = tcgen05 implicit GEMM, 0 = CUDA-core direct kernel. */
+ * use_tc: 1 = tcgen05 implicit GEMM, 0 = CUDA-core direct kernel, 2 = warp-level mma.sync
+ * kernel (small-channel 1x1 / 3x3 stride-1 layers only). */
 int tr_conv2d(const void* in_dev, int N, int H, int W, int in_cs, int in_coff, int cin_pad,
               const void* w_dev, const float* scale_dev, const float* shift_dev,
               const float* slope_dev, int cout_pad, int cout_store, int k, int stride, int pad,
               int act, const void* res_dev, int res_cs, int res_up2, void* out_dev, int out_cs,
               int out_coff, int out_is_f32, int use_tc, int repeat, float* ms, void* stream);
+
+/* Fused depthwise 3x3 + BN + ReLU -> 1x1 conv + scale/shift (+act): the single-op entry of
+ * TR_OP_SEPCONV.  fused = 1: one mma.sync kernel; fused = 0: the depthwise kernel into
+ * tmp_dev ((N,Ho,Wo,cin_pad) fp16) followed by the direct 1x1 kernel (cross-check). */
+int tr_sepconv2d(const void* in_dev, int N, int H, int W, int in_cs, int in_coff, int cin_pad,
+                 const float* dw_w_dev, const void* dw_w16_dev, const float* dw_scale_dev,
+                 const float* dw_shift_dev, int stride, const void* w_dev, const float* scale_dev, const float* shift_dev,
+                 int cout_pad, int cout_store, int act, void* out_dev, int out_cs, int out_coff,
+                 void* tmp_dev, int fused, int repeat, float* ms, void* stream);
 
 /* ---- RetinaFace post-processing ------------------------------------------
  * Replaces anchors_plane / decode_bboxes / decode_landmarks / threshold /

@@ -15,7 +15,7 @@ import torch  # noqa: E402
 
 from terran_b200 import _native as nat, synth  # noqa: E402
 
-NAMES = {0: 'stem', 1: 'conv', 2: 'dw', 3: 'pool', 4: 'copy', 5: 'view'}
+NAMES = {0: 'stem', 1: 'conv', 2: 'dw', 3: 'pool', 4: 'copy', 5: 'view', 6: 'sep'}
 
 
 def profile(model_name, reps):

@@ -15,14 +15,15 @@ SYMBOLS = (
     'tr_net_create', 'tr_net_destroy', 'tr_net_set_mode', 'tr_net_run', 'tr_net_buffer',
     'tr_net_export_nchw', 'tr_net_export_nchw_f32', 'tr_net_stats', 'tr_net_set_profile',
     'tr_net_profile',
-    'tr_conv2d',
+    'tr_conv2d', 'tr_sepconv2d',
     'tr_detect_workspace_bytes', 'tr_retinaface_decode_nms', 'tr_retinaface_detect',
     'tr_l2_normalize', 'tr_face_align',
     'tr_pose_workspace_bytes', 'tr_openpose_parse', 'tr_bicubic_table',
     'tr_resize_bilinear_u8',
 )
 
-TR_OP_STEM, TR_OP_CONV, TR_OP_DWCONV, TR_OP_MAXPOOL, TR_OP_COPY, TR_OP_VIEW = range(6)
+TR_OP_STEM, TR_OP_CONV, TR_OP_DWCONV, TR_OP_MAXPOOL, TR_OP_COPY, TR_OP_VIEW, TR_OP_SEPCONV = range(7)
+TR_ENGINE_AUTO, TR_ENGINE_MMA = 0, 1
 TR_ACT_NONE, TR_ACT_RELU, TR_ACT_PRELU = range(3)
 TR_SYNC_FORK, TR_SYNC_JOIN = 1, 2
 TR_PEAK_CAP, TR_CAND_CAP, TR_HUMAN_CAP = 512, 4096, 128
@@ -46,6 +47,9 @@ class OpDesc(C.Structure):
         ('w_off', C.c_int64), ('scale_off', C.c_int64), ('shift_off', C.c_int64),
         ('slope_off', C.c_int64), ('scale2_off', C.c_int64), ('shift2_off', C.c_int64),
         ('in_scale', C.c_float), ('in_shift', C.c_float),
+        ('dw_w_off', C.c_int64), ('dw_scale_off', C.c_int64), ('dw_shift_off', C.c_int64),
+        ('dw_w16_off', C.c_int64),
+        ('engine', C.c_int32), ('reserved', C.c_int32),
     ]
 
 
@@ -85,6 +89,8 @@ def lib():
         L.tr_conv2d.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32,
                                 i32, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32,
                                 C.POINTER(f32), vp]
+        L.tr_sepconv2d.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32,
+                                   i32, i32, vp, i32, i32, vp, i32, i32, C.POINTER(f32), vp]
         L.tr_detect_workspace_bytes.argtypes = [i32, i32, i32]
         L.tr_detect_workspace_bytes.restype = C.c_size_t
         L.tr_retinaface_decode_nms.argtypes = [C.POINTER(vp), i32, i32, i32, f32, f64, i32, vp, vp,

@@ -23,6 +23,7 @@ COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC']
 SOURCES = {
     'conv_tc.cu': [],
     'conv_direct.cu': [],
+    'conv_mma.cu': [],
     'detect_post.cu': ['-fmad=false'],
     'pose_parse.cu': ['-fmad=false'],
     'net.cu': [],

@@ -83,6 +83,23 @@ double conv_tc_plan_flops(const ConvTcPlan* p);
 // conv_direct.cu
 void conv_direct_launch(const ConvArgs& a, cudaStream_t s);
 
+// conv_mma.cu — warp-level mma.sync kernels for small-channel layers (RetinaFace)
+bool conv_mma_eligible(const ConvArgs& a);
+void conv_mma_launch(const ConvArgs& a, cudaStream_t s);
+// Fused depthwise 3x3 (pad 1, stride 1|2) + BN + ReLU -> 1x1 conv + scale/shift (+ReLU).
+struct SepArgs {
+  View in, out;
+  const float* dw_w;      // fp32 [3][3][cin_pad] (unfused cross-check path)
+  const __half* dw_w16;   // the same filter in fp16 (fused kernel)
+  const float* dw_scale; const float* dw_shift;
+  int stride;             // of the depthwise stage
+  const __half* w;        // fp16 [cout_pad][cin_pad]
+  const float* scale; const float* shift;
+  int cin_pad, cout_pad, cout_store, act;
+};
+bool sep_mma_eligible(const SepArgs& a);
+void sep_mma_launch(const SepArgs& a, cudaStream_t s);
+
 struct StemArgs {
   const uint8_t* in;      // u8 image, arbitrary element strides
   long sn, sh, sw, sc;    // element strides of (n, h, w, c)

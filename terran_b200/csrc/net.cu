@@ -35,6 +35,9 @@ struct PreparedOp {
   ConvTcPlan* tc = nullptr;
   StemArgs stem;
   DwArgs dw;
+  SepArgs sep;
+  bool mma = false;          // TR_OP_CONV on the warp-level mma.sync kernel
+  void* sep_tmp = nullptr;   // force_direct: depthwise output between the two unfused kernels
   View vin, vout;
 };
 
@@ -47,6 +50,7 @@ struct Plan {
   ~Plan() {
     for (auto& o : ops) {
       if (o.tc) conv_tc_plan_destroy(o.tc);
+      if (o.sep_tmp) cudaFree(o.sep_tmp);
       if (o.e0) cudaEventDestroy(o.e0);
       if (o.e1) cudaEventDestroy(o.e1);
     }
@@ -97,6 +101,12 @@ const T* blob_ptr(const tr_net* net, int64_t off) {
   return reinterpret_cast<const T*>(net->weights + off);
 }
 
+// TRB_MMA=0 keeps TR_ENGINE_MMA / TR_OP_SEPCONV ops off the mma.sync kernels (A/B measurements).
+bool mma_enabled() {
+  static const bool on = [] { const char* e = getenv("TRB_MMA"); return !e || atoi(e) != 0; }();
+  return on;
+}
+
 View make_view(const Buf& b, int coff, int C) {
   View v;
   v.ptr = static_cast<__half*>(b.ptr);
@@ -134,6 +144,7 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
     switch (d.type) {
       case TR_OP_STEM:
       case TR_OP_CONV:
+      case TR_OP_SEPCONV:
       case TR_OP_DWCONV: {
         const int oH = (iH + 2 * d.pad - d.k) / d.stride + 1, oW = (iW + 2 * d.pad - d.k) / d.stride + 1;
         TR_CHECK(oH > 0 && oW > 0, "image too small for the network");
@@ -215,7 +226,9 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
         TR_CHECK(d.in_coff + d.in_c <= B[d.in].C && d.out_coff + d.out_c <= B[d.out].C,
                  "channel slice out of range");
         po.flops = 2.0 * B[d.out].N * a.H_out * a.W_out * double(d.cout_real) * d.k * d.k * d.cin_real;
-        const bool use_tc = !net->force_direct && !d.force_direct && conv_tc_eligible(a);
+        po.mma = !net->force_direct && !d.force_direct && d.engine == TR_ENGINE_MMA && mma_enabled() &&
+                 conv_mma_eligible(a);
+        const bool use_tc = !po.mma && !net->force_direct && !d.force_direct && conv_tc_eligible(a);
         if (use_tc) {
           void*& scratch = net->sk_scratch[d.lane == 1];
           if (!scratch) {
@@ -226,6 +239,42 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
           po.tc = conv_tc_plan_create(a);
           plan->tc_flops += po.flops;
           plan->tc_launches++;
+        }
+        break;
+      }
+      case TR_OP_SEPCONV: {
+        SepArgs& a = po.sep;
+        a = SepArgs{};
+        a.in = make_view(B[d.in], d.in_coff, d.in_c);
+        a.out = make_view(B[d.out], d.out_coff, d.out_c);
+        a.dw_w = blob_ptr<float>(net, d.dw_w_off);
+        a.dw_w16 = blob_ptr<__half>(net, d.dw_w16_off);
+        a.dw_scale = blob_ptr<float>(net, d.dw_scale_off); a.dw_shift = blob_ptr<float>(net, d.dw_shift_off);
+        a.stride = d.stride;
+        a.w = blob_ptr<__half>(net, d.w_off);
+        a.scale = blob_ptr<float>(net, d.scale_off); a.shift = blob_ptr<float>(net, d.shift_off);
+        a.cin_pad = d.in_c; a.cout_pad = d.cout_pad; a.cout_store = d.out_c; a.act = d.act;
+        TR_CHECK(d.k == 3 && d.pad == 1, "fused depthwise stage is 3x3 pad 1");
+        TR_CHECK(!B[d.out].f32, "sepconv output is fp16");
+        TR_CHECK(d.in_coff + d.in_c <= B[d.in].C && d.out_coff + d.out_c <= B[d.out].C,
+                 "channel slice out of range");
+        po.flops = 2.0 * B[d.out].N * B[d.out].H * B[d.out].W * (double(d.cout_real) * d.cin_real + 9.0 * d.cin_real);
+        po.mma = !net->force_direct && !d.force_direct && mma_enabled();
+        if (po.mma) TR_CHECK(sep_mma_eligible(a), "sepconv: unsupported (channels, stride) combination");
+        if (!po.mma) {
+          // Cross-check path: the depthwise kernel into a scratch tensor, then the direct 1x1.
+          const size_t bytes = size_t(B[d.out].N) * B[d.out].H * B[d.out].W * d.in_c * 2;
+          TR_CUDA(cudaMalloc(&po.sep_tmp, bytes + 256));
+          DwArgs& w = po.dw;
+          w.in = a.in;
+          w.out = View{static_cast<__half*>(po.sep_tmp), B[d.out].N, B[d.out].H, B[d.out].W, d.in_c, 0, d.in_c};
+          w.w = a.dw_w; w.scale = a.dw_scale; w.shift = a.dw_shift; w.stride = d.stride;
+          ConvArgs& c = po.conv;
+          c = ConvArgs{};
+          c.in = w.out; c.out = a.out;
+          c.w = a.w; c.scale = a.scale; c.shift = a.shift;
+          c.cout_pad = d.cout_pad; c.cout_store = d.out_c; c.cin_pad = d.in_c;
+          c.act = d.act; c.H_out = B[d.out].H; c.W_out = B[d.out].W;
         }
         break;
       }
@@ -247,7 +296,7 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
       case TR_OP_VIEW:
         break;
     }
-    if (d.type != TR_OP_VIEW) plan->launches++;
+    if (d.type != TR_OP_VIEW) plan->launches += (d.type == TR_OP_SEPCONV && !po.mma) ? 2 : 1;
     plan->ops.push_back(po);
   }
   Plan* raw = plan.get();
@@ -306,7 +355,12 @@ void run_plan(tr_net* net, Plan* plan, const uint8_t* image, int64_t sn, int64_t
       }
       case TR_OP_CONV:
         if (po.tc) conv_tc_launch(po.tc, s);
+        else if (po.mma) conv_mma_launch(po.conv, s);
         else conv_direct_launch(po.conv, s);
+        break;
+      case TR_OP_SEPCONV:
+        if (po.mma) sep_mma_launch(po.sep, s);
+        else { dwconv_launch(po.dw, s); conv_direct_launch(po.conv, s); }
         break;
       case TR_OP_DWCONV: dwconv_launch(po.dw, s); break;
       case TR_OP_MAXPOOL: maxpool2_launch(po.vin, po.vout, s); break;
@@ -487,11 +541,16 @@ int tr_conv2d(const void* in_dev, int N, int H, int W, int in_cs, int in_coff, i
     a.kh = a.kw = k; a.stride = stride; a.pad = pad; a.act = act;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     ConvTcPlan* plan = nullptr;
-    if (use_tc) plan = conv_tc_plan_create(a);
+    if (use_tc == 1) plan = conv_tc_plan_create(a);
+    if (use_tc == 2) TR_CHECK(conv_mma_eligible(a), "layer not supported by the mma.sync kernel");
     cudaEvent_t e0, e1;
     TR_CUDA(cudaEventCreate(&e0));
     TR_CUDA(cudaEventCreate(&e1));
-    auto once = [&] { if (plan) conv_tc_launch(plan, s); else conv_direct_launch(a, s); };
+    auto once = [&] {
+      if (plan) conv_tc_launch(plan, s);
+      else if (use_tc == 2) conv_mma_launch(a, s);
+      else conv_direct_launch(a, s);
+    };
     once();
     TR_CUDA(cudaEventRecord(e0, s));
     for (int i = 0; i < repeat; ++i) once();
@@ -499,6 +558,52 @@ int tr_conv2d(const void* in_dev, int N, int H, int W, int in_cs, int in_coff, i
     cudaError_t err = cudaStreamSynchronize(s);
     if (plan) conv_tc_plan_destroy(plan);
     TR_CUDA(err);
+    float t = 0.f;
+    TR_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = repeat > 0 ? t / repeat : 0.f;
+  });
+}
+
+int tr_sepconv2d(const void* in_dev, int N, int H, int W, int in_cs, int in_coff, int cin_pad,
+                 const float* dw_w_dev, const void* dw_w16_dev, const float* dw_scale_dev,
+                 const float* dw_shift_dev, int stride, const void* w_dev, const float* scale_dev, const float* shift_dev,
+                 int cout_pad, int cout_store, int act, void* out_dev, int out_cs, int out_coff,
+                 void* tmp_dev, int fused, int repeat, float* ms, void* stream) {
+  return guarded([&] {
+    TR_CHECK(stride == 1 || stride == 2, "depthwise stride");
+    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    SepArgs a{};
+    a.in = View{static_cast<__half*>(const_cast<void*>(in_dev)), N, H, W, in_cs, in_coff, cin_pad};
+    a.out = View{static_cast<__half*>(out_dev), N, Ho, Wo, out_cs, out_coff, cout_store};
+    a.dw_w = dw_w_dev; a.dw_w16 = static_cast<const __half*>(dw_w16_dev); a.dw_scale = dw_scale_dev; a.dw_shift = dw_shift_dev; a.stride = stride;
+    a.w = static_cast<const __half*>(w_dev); a.scale = scale_dev; a.shift = shift_dev;
+    a.cin_pad = cin_pad; a.cout_pad = cout_pad; a.cout_store = cout_store; a.act = act;
+    DwArgs d{};
+    ConvArgs c{};
+    if (!fused) {
+      TR_CHECK(tmp_dev, "unfused sepconv needs the scratch tensor");
+      d.in = a.in;
+      d.out = View{static_cast<__half*>(tmp_dev), N, Ho, Wo, cin_pad, 0, cin_pad};
+      d.w = dw_w_dev; d.scale = dw_scale_dev; d.shift = dw_shift_dev; d.stride = stride;
+      c.in = d.out; c.out = a.out; c.w = a.w; c.scale = scale_dev; c.shift = shift_dev;
+      c.cout_pad = cout_pad; c.cout_store = cout_store; c.cin_pad = cin_pad; c.act = act;
+      c.H_out = Ho; c.W_out = Wo;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    auto once = [&] {
+      if (fused) sep_mma_launch(a, s);
+      else { dwconv_launch(d, s); conv_direct_launch(c, s); }
+    };
+    cudaEvent_t e0, e1;
+    TR_CUDA(cudaEventCreate(&e0));
+    TR_CUDA(cudaEventCreate(&e1));
+    once();
+    TR_CUDA(cudaEventRecord(e0, s));
+    for (int i = 0; i < repeat; ++i) once();
+    TR_CUDA(cudaEventRecord(e1, s));
+    TR_CUDA(cudaStreamSynchronize(s));
     float t = 0.f;
     TR_CUDA(cudaEventElapsedTime(&t, e0, e1));
     cudaEventDestroy(e0);

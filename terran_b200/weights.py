@@ -63,14 +63,15 @@ class Program:
         d = dict(type=0, in_=-1, in_coff=0, in_c=0, out=-1, out_coff=0, out_c=0, out2=-1,
                  out2_coff=0, res=-1, res_coff=0, res_up2=0, k=1, stride=1, pad=0, act=0,
                  cout_pad=0, cin_real=0, cout_real=0, force_direct=0, lane=0, sync=0, w_off=-1, scale_off=-1, shift_off=-1, slope_off=-1,
-                 scale2_off=-1, shift2_off=-1, in_scale=1.0, in_shift=0.0)
+                 scale2_off=-1, shift2_off=-1, in_scale=1.0, in_shift=0.0,
+                 dw_w_off=-1, dw_scale_off=-1, dw_shift_off=-1, dw_w16_off=-1, engine=0, reserved=0)
         d.update(kw)
         self.ops.append(nat.OpDesc(**d))
 
     def conv(self, w, scale, shift, in_, out, *, in_coff=0, in_map=None, cin_pad=None,
              out_coff=0, k=None, stride=1, pad=None, act=nat.TR_ACT_NONE, slope=None,
              res=-1, res_coff=0, res_up2=0, out2=-1, scale2=None, shift2=None,
-             force_direct=0, lane=0, sync=0):
+             force_direct=0, lane=0, sync=0, engine=nat.TR_ENGINE_AUTO):
         """w: (cout, cin, k, k) fp32 tensor.  ``in_map[c]`` is the position of
         reference input channel c inside the (padded) input view."""
         w = w.detach().float().numpy()
@@ -87,7 +88,7 @@ class Program:
                  out_coff=out_coff, out_c=_r(cout, 8), out2=out2, res=res, res_coff=res_coff,
                  res_up2=res_up2, k=k, stride=stride, pad=pad, act=act, cout_pad=cout_pad,
                  cin_real=cin, cout_real=cout, force_direct=force_direct, lane=lane, sync=sync,
-                 w_off=self.add(packed, np.float16),
+                 engine=engine, w_off=self.add(packed, np.float16),
                  scale_off=self.add_vec(scale, cout_pad), shift_off=self.add_vec(shift, cout_pad),
                  slope_off=self.add_vec(slope, cout_pad),
                  scale2_off=self.add_vec(scale2, cout_pad), shift2_off=self.add_vec(shift2, cout_pad))
@@ -110,6 +111,26 @@ class Program:
                  pad=1, act=nat.TR_ACT_RELU, cout_pad=c,
                  w_off=self.add(w[:, 0].transpose(1, 2, 0), np.float32),
                  scale_off=self.add_vec(scale, c), shift_off=self.add_vec(shift, c))
+
+    def sepconv(self, dw_w, dw_scale, dw_shift, w, scale, shift, in_, out, *, stride,
+                act=nat.TR_ACT_RELU):
+        """Depthwise 3x3 (pad 1, ``stride``) + BN + ReLU fused with the 1x1 conv + BN (+act)
+        that consumes it.  dw_w: (C, 1, 3, 3); w: (cout, C, 1, 1)."""
+        dw_w = dw_w.detach().float().numpy()
+        w = w.detach().float().numpy()
+        cout, cin = w.shape[:2]
+        cin_pad = _r(cin, 8) if cin <= 8 else _r(cin, 16)
+        cout_pad = _r(cout, 16)
+        packed = np.zeros((cout_pad, cin_pad), np.float16)
+        packed[:cout, :cin] = w[:, :, 0, 0].astype(np.float16)
+        dwp = np.zeros((3, 3, cin_pad), np.float32)
+        dwp[:, :, :cin] = dw_w[:, 0].transpose(1, 2, 0)
+        self._op(type=nat.TR_OP_SEPCONV, in_=in_, in_c=cin_pad, out=out, out_c=_r(cout, 8), k=3,
+                 stride=stride, pad=1, act=act, cout_pad=cout_pad, cin_real=cin, cout_real=cout,
+                 w_off=self.add(packed, np.float16),
+                 scale_off=self.add_vec(scale, cout_pad), shift_off=self.add_vec(shift, cout_pad),
+                 dw_w_off=self.add(dwp, np.float32), dw_w16_off=self.add(dwp, np.float16),
+                 dw_scale_off=self.add_vec(dw_scale, cin_pad), dw_shift_off=self.add_vec(dw_shift, cin_pad))
 
     def maxpool(self, in_, out, channels):
         self._op(type=nat.TR_OP_MAXPOOL, in_=in_, in_c=channels, out=out, out_c=channels, k=2,
@@ -135,40 +156,61 @@ def bn_fold(sd, prefix, eps, conv_bias=None):
 
 # ------------------------------------------------------------------ RetinaFace
 
-def retinaface_program(sd):
+def retinaface_program(sd, fused=None):
     """Program + roles for reference ``RetinaFace`` (retinaface/model.py:319-341).
     The stem reads the frame in MODEL channel order (BGR); callers with RGB
-    memory pass a pointer to channel 2 and a channel stride of -1."""
+    memory pass a pointer to channel 2 and a channel stride of -1.
+
+    ``fused`` (default: env ``TRB_RETINA_FUSED`` != 0): every depthwise 3x3 of the backbone
+    runs inside the 1x1 conv that consumes it (one ``TR_OP_SEPCONV`` per pair) and the
+    refiner / context / head convs go to the warp-level mma.sync kernel; otherwise one op
+    per reference layer on the tcgen05 / direct kernels."""
+    import os
+    if fused is None:
+        fused = os.environ.get('TRB_RETINA_FUSED', '1') != '0'
     P = Program()
     relu = nat.TR_ACT_RELU
+    engine = nat.TR_ENGINE_MMA if fused else nat.TR_ENGINE_AUTO
 
     def cbr(pc, pb, in_, out, eps, **kw):
         s, t = bn_fold(sd, pb, eps, sd.get(pc + '.bias'))
-        P.conv(sd[pc + '.weight'], s, t, in_, out, act=relu, **kw)
+        w = sd[pc + '.weight']
+        # measured (profiles/r01_retinaface_mma.txt): the warp-level kernel wins where either
+        # channel count is <= 16; the 64-channel 3x3 / lateral 1x1 layers stay on tcgen05
+        eng = engine if min(w.shape[0], w.shape[1]) <= 16 else nat.TR_ENGINE_AUTO
+        P.conv(w, s, t, in_, out, act=relu, engine=eng, **kw)
 
     b = P.buffer(8)
     s, t = bn_fold(sd, 'base.first_conv_block.1', 1e-5)
     P.stem(sd['base.first_conv_block.0.weight'], s, t, b, stride=2, act=relu)
-    x = P.buffer(8)
-    s, t = bn_fold(sd, 'base.first_conv_block.4', 1e-5)
-    P.dwconv(sd['base.first_conv_block.3.weight'], s, t, b, x, stride=1)
 
-    def sep_block(prefix, x, cout, stride):
-        conv = P.buffer(cout)
-        cbr(prefix + '.conv_block.0', prefix + '.conv_block.1', x, conv, 1e-5)
-        sep = P.buffer(cout)
-        s, t = bn_fold(sd, prefix + '.sep_block.1', 1e-5)
-        P.dwconv(sd[prefix + '.sep_block.0.weight'], s, t, conv, sep, stride=stride)
-        return conv, sep
-
+    # The backbone is stem -> dw -> [1x1 -> dw]* -> 1x1 (ConvSepBlock = 1x1 conv_block then
+    # depthwise sep_block, model.py:6-50).  Pair every depthwise with the 1x1 that FOLLOWS it.
+    blocks = [(f'base.scales.{si}.{bi}', cout, stride)
+              for si, bl in enumerate(RETINAFACE_SCALES) for bi, (_cin, cout, stride) in enumerate(bl)]
+    blocks.append(('base.final_conv.0', 256, 1))
+    tap_after = {len(RETINAFACE_SCALES[0]) - 1, len(RETINAFACE_SCALES[0]) + len(RETINAFACE_SCALES[1]) - 1}
+    pending = ('base.first_conv_block.3', 'base.first_conv_block.4', 1)   # (dw conv, dw bn, stride)
+    x, ch = b, 8
     taps = []
-    for si, blocks in enumerate(RETINAFACE_SCALES):
-        for bi, (_cin, cout, stride) in enumerate(blocks):
-            conv, x = sep_block(f'base.scales.{si}.{bi}', x, cout, stride)
-        taps.append(conv)
-    _, x = sep_block('base.final_conv.0', x, 256, 1)
-    c32 = P.buffer(256)
-    cbr('base.final_conv.1', 'base.final_conv.2', x, c32, 1e-5)
+    pointwise = [(p + '.conv_block.0', p + '.conv_block.1', c) for p, c, _ in blocks]
+    pointwise.append(('base.final_conv.1', 'base.final_conv.2', 256))
+    next_dw = [(p + '.sep_block.0', p + '.sep_block.1', st) for p, _, st in blocks] + [None]
+    for i, ((pc, pb, cout), nxt) in enumerate(zip(pointwise, next_dw)):
+        dwc, dwb, stride = pending
+        ds, dt = bn_fold(sd, dwb, 1e-5)
+        s, t = bn_fold(sd, pb, 1e-5)
+        y = P.buffer(cout)
+        if fused:
+            P.sepconv(sd[dwc + '.weight'], ds, dt, sd[pc + '.weight'], s, t, x, y, stride=stride)
+        else:
+            d = P.buffer(ch)
+            P.dwconv(sd[dwc + '.weight'], ds, dt, x, d, stride=stride)
+            P.conv(sd[pc + '.weight'], s, t, d, y, act=relu)
+        if i in tap_after:
+            taps.append(y)
+        x, ch, pending = y, cout, nxt
+    c32 = x
     c8, c16 = taps
 
     e = 2e-5
@@ -202,7 +244,7 @@ def retinaface_program(sd):
                           sd[f'outputs.bbox_stride{stride}.bias'],
                           sd[f'outputs.landmark_stride{stride}.bias']], 0)
         head = P.buffer(32, f32=True)
-        P.conv(w, np.ones(32, np.float32), bias.float().numpy(), ctx, head)
+        P.conv(w, np.ones(32, np.float32), bias.float().numpy(), ctx, head, engine=engine)
         heads[stride] = head
         ctxs[stride] = ctx
     roles = {'heads': [heads[32], heads[16], heads[8]], 'context': ctxs}

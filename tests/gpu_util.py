@@ -44,6 +44,55 @@ def conv2d_native(nat, x, w, scale, shift, *, stride=1, pad=None, act=0, slope=N
     return out[..., :cout], ms.value
 
 
+def sepconv2d_native(nat, x, dw_w, dw_scale, dw_shift, w, scale, shift, *, stride=1, act=1,
+                     fused=True, repeat=0):
+    """Depthwise 3x3 + BN + ReLU -> 1x1 + scale/shift (+act) through ``tr_sepconv2d``.
+    x: (N,H,W,C) fp16 CUDA NHWC; dw_w: (C,1,3,3); w: (Cout,C,1,1)."""
+    nat.init(0)
+    N, H, W, cin = x.shape
+    cout = w.shape[0]
+    cout_pad = (cout + 15) // 16 * 16
+    cout_store = (cout + 7) // 8 * 8
+    wp = torch.zeros((cout_pad, cin), dtype=torch.float16)
+    wp[:cout] = w[:, :, 0, 0].half()
+    wp = wp.cuda()
+    dwp = dw_w[:, 0].permute(1, 2, 0).contiguous().float().cuda()
+    dwp16 = dwp.half()
+
+    def vec(v, n):
+        t = torch.zeros(n, dtype=torch.float32)
+        t[:len(v)] = torch.as_tensor(v, dtype=torch.float32)
+        return t.cuda()
+
+    ds, dt = vec(dw_scale, cin), vec(dw_shift, cin)
+    sc, sh = vec(scale, cout_pad), vec(shift, cout_pad)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.full((N, Ho, Wo, cout_store), float('nan'), dtype=torch.float16, device='cuda')
+    tmp = torch.empty((N, Ho, Wo, cin), dtype=torch.float16, device='cuda')
+    ms = C.c_float(0)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    nat.check(nat.lib().tr_sepconv2d(
+        ptr(x), N, H, W, cin, 0, cin, ptr(dwp), ptr(dwp16), ptr(ds), ptr(dt), stride, ptr(wp), ptr(sc), ptr(sh),
+        cout_pad, cout_store, act, ptr(out), cout_store, 0, ptr(tmp), int(fused), repeat,
+        C.byref(ms), nat.current_stream_ptr()))
+    torch.cuda.synchronize()
+    return out[..., :cout], ms.value
+
+
+def sepconv2d_reference(x, dw_w, dw_scale, dw_shift, w, scale, shift, *, stride=1, act=1):
+    """fp64 CPU reference; the depthwise result is rounded to fp16 like the kernels do."""
+    xin = x.detach().cpu().double().permute(0, 3, 1, 2)
+    C_ = xin.shape[1]
+    y = torch.nn.functional.conv2d(xin, dw_w.half().double(), stride=stride, padding=1, groups=C_)
+    y = y * torch.as_tensor(dw_scale).double().view(1, -1, 1, 1) + torch.as_tensor(dw_shift).double().view(1, -1, 1, 1)
+    y = y.clamp_min(0).half().double()
+    z = torch.nn.functional.conv2d(y, w.half().double())
+    z = z * torch.as_tensor(scale).double().view(1, -1, 1, 1) + torch.as_tensor(shift).double().view(1, -1, 1, 1)
+    if act == 1:
+        z = z.clamp_min(0)
+    return z.permute(0, 2, 3, 1).contiguous()
+
+
 def conv2d_reference(x, w, scale, shift, *, stride=1, pad=None, act=0, slope=None, res=None,
                      res_up2=False):
     """fp64 CPU reference on the SAME fp16-rounded operands."""

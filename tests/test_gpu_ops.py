@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.gpu_util import conv2d_native, conv2d_reference, describe_mismatch
+from tests.gpu_util import conv2d_native, conv2d_reference, describe_mismatch, \
+    sepconv2d_native, sepconv2d_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -98,6 +99,78 @@ def test_conv_stream_k(native, case, monkeypatch):
     # some outputs) and is deterministic
     assert not torch.equal(split, whole)
     assert torch.equal(split, again)
+
+
+# Warp-level mma.sync kernel (conv_mma.cu): RetinaFace's refiner / context / head layers.
+# (N, H, W, cin, cout, k, stride, act, residual, tag) — odd sizes exercise the strip masks.
+MMA_CASES = [
+    (2, 13, 24, 256, 64, 1, 1, 1, None, 'lateral-s32'),
+    (2, 26, 47, 128, 64, 1, 1, 1, 'up2', 'lateral-s16-up2'),
+    (1, 52, 93, 64, 64, 1, 1, 1, 'up2', 'lateral-s8-up2'),
+    (2, 26, 47, 64, 64, 3, 1, 1, None, 'aggr'),
+    (3, 13, 24, 64, 32, 3, 1, 1, None, 'ctx-3x3'),
+    (1, 27, 45, 64, 16, 3, 1, 1, None, 'ctx-reducer'),
+    (2, 13, 24, 16, 16, 3, 1, 1, None, 'ctx-16'),
+    (5, 7, 9, 64, 64, 3, 1, 0, 'same', 'res-same'),
+    (1, 1, 1, 64, 32, 1, 1, 0, None, 'one-pixel'),
+]
+
+
+@pytest.mark.parametrize('case', MMA_CASES, ids=[c[-1] for c in MMA_CASES])
+def test_conv_mma_matches_reference(native, case):
+    N, H, W, cin, cout, k, stride, act, res_kind, tag = case
+    x, w, scale, shift, slope, res, up2 = make_case(case)
+    out, _ = conv2d_native(native, x, w, scale, shift, stride=stride, act=act, res=res,
+                           res_up2=up2, use_tc=2)
+    ref = conv2d_reference(x, w, scale, shift, stride=stride, act=act, res=res, res_up2=up2)
+    tol = 2e-3 * max(1.0, float(ref.abs().max()))
+    err = (out.cpu().double() - ref).abs().max()
+    assert torch.isfinite(out.float()).all() and err <= tol, describe_mismatch(out, ref, tol)
+
+
+def test_conv_mma_fp32_head_into_channel_slice(native):
+    """Fused head conv: fp32 output, no activation (retinaface/model.py:248-316)."""
+    case = (2, 13, 24, 64, 32, 1, 1, 0, None, 'head')
+    x, w, scale, shift, slope, res, up2 = make_case(case, seed=3)
+    out, _ = conv2d_native(native, x, w, scale, shift, use_tc=2, out_f32=True)
+    ref = conv2d_reference(x, w, scale, shift)
+    assert out.dtype == torch.float32
+    assert (out.cpu().double() - ref).abs().max() < 1e-4, describe_mismatch(out, ref, 1e-4)
+
+
+# Fused depthwise 3x3 + BN + ReLU -> 1x1 + BN + ReLU: every (channels, stride) pair of the
+# mobilenet-0.25 backbone (retinaface/model.py:53-112), ragged map sizes.
+SEP_CASES = [
+    (2, 21, 70, 8, 16, 1), (1, 20, 67, 16, 32, 2), (2, 11, 19, 32, 32, 1), (2, 21, 35, 32, 64, 2),
+    (1, 13, 24, 64, 64, 1), (3, 13, 23, 64, 128, 2), (2, 9, 17, 128, 128, 1), (2, 13, 24, 128, 256, 2),
+    (2, 7, 12, 256, 256, 1), (1, 1, 1, 8, 16, 1), (33, 2, 3, 128, 128, 1),
+]
+
+
+def make_sep_case(case, seed=0):
+    N, H, W, cin, cout, stride = case
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn((N, H, W, cin), generator=g) * 0.5).abs().half().cuda()
+    dw_w = torch.randn((cin, 1, 3, 3), generator=g) / 3.0
+    dw_scale = torch.empty(cin).uniform_(0.5, 1.5, generator=g)
+    dw_shift = torch.randn(cin, generator=g) * 0.1
+    w = torch.randn((cout, cin, 1, 1), generator=g) / cin ** 0.5
+    scale = torch.empty(cout).uniform_(0.5, 1.5, generator=g)
+    shift = torch.randn(cout, generator=g) * 0.1
+    return x, dw_w, dw_scale, dw_shift, w, scale, shift
+
+
+@pytest.mark.parametrize('case', SEP_CASES, ids=['x'.join(map(str, c)) for c in SEP_CASES])
+@pytest.mark.parametrize('fused', [True, False], ids=['fused', 'unfused'])
+def test_sepconv_matches_reference(native, case, fused):
+    args = make_sep_case(case)
+    out, _ = sepconv2d_native(native, *args, stride=case[5], fused=fused)
+    ref = sepconv2d_reference(*args, stride=case[5])
+    # the depthwise result is rounded to fp16 before the 1x1: one half-ulp flip of an
+    # operand moves the output by ~1e-3 of its scale
+    tol = 4e-3 * max(1.0, float(ref.abs().max()))
+    err = (out.cpu().double() - ref).abs().max()
+    assert torch.isfinite(out.float()).all() and err <= tol, describe_mismatch(out, ref, tol)
 
 
 def test_conv_tc_fp32_output(native):

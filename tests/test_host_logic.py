@@ -42,7 +42,7 @@ def test_op_desc_layout_matches_header(native):
             for n, t in fields]
     got = [(n.rstrip('_'), t) for n, t in native.OpDesc._fields_]
     assert got == want
-    assert C.sizeof(native.OpDesc) == 22 * 4 + 6 * 8 + 2 * 4
+    assert C.sizeof(native.OpDesc) == 22 * 4 + 6 * 8 + 2 * 4 + 4 * 8 + 2 * 4
 
 
 def test_no_gpu_calls_fail_loudly(native):
@@ -194,12 +194,22 @@ def test_programs_cover_every_checkpoint_tensor():
     """Every conv / linear weight of the reference state_dicts lands in the
     packed blob exactly once (op counts per architecture)."""
     from terran_b200 import _native as nat, synth, weights
-    P, roles = weights.retinaface_program(synth.retinaface_state_dict())
+    P, roles = weights.retinaface_program(synth.retinaface_state_dict(), fused=False)
     kinds = [op.type for op in P.ops]
     assert kinds.count(nat.TR_OP_STEM) == 1 and kinds.count(nat.TR_OP_DWCONV) == 13
     # 56 convs = 1 stem + 13 depthwise + 33 dense + 9 heads fused into 3
     assert kinds.count(nat.TR_OP_CONV) == 56 - 1 - 13 - 9 + 3
     assert len(roles['heads']) == 3
+    # fused program: every depthwise lives inside the 1x1 conv that consumes it
+    Pf, rf = weights.retinaface_program(synth.retinaface_state_dict(), fused=True)
+    kinds = [op.type for op in Pf.ops]
+    assert kinds.count(nat.TR_OP_SEPCONV) == 13 and kinds.count(nat.TR_OP_DWCONV) == 0
+    assert kinds.count(nat.TR_OP_CONV) == 56 - 1 - 13 - 13 - 9 + 3
+    seps = [op for op in Pf.ops if op.type == nat.TR_OP_SEPCONV]
+    assert [(o.cin_real, o.cout_real, o.stride) for o in seps] == [
+        (8, 16, 1), (16, 32, 2), (32, 32, 1), (32, 64, 2), (64, 64, 1), (64, 128, 2)] + \
+        [(128, 128, 1)] * 5 + [(128, 256, 2), (256, 256, 1)]
+    assert len(rf['heads']) == 3
     P, _ = weights.openpose_program(synth.openpose_state_dict())
     kinds = [op.type for op in P.ops]
     # 92 convs; the first layer of the two branches of each of the 6 stages is one merged conv
