@@ -81,6 +81,13 @@ struct TcParams {
   // halo mode: the input patch of a tile (+ filter halo) is loaded ONCE per channel chunk and
   // every tap's A operand is a shifted UMMA descriptor into it.  1: tile 8w x 16h, 2: 16w x 8h.
   int halo, taps, iters_kc;
+  // swap mode (128 output channels): the FILTER tile is the UMMA A operand (M = 128 couts) and
+  // the pixel tile the B operand (N = rows <= 256 pixels, a band of full-width rows), so one
+  // instruction does N = 240 instead of 128 columns of work per 128 x 64 filter block read from
+  // shared memory.  TMEM holds D^T: lane = cout, column = pixel.
+  int swap;
+  int rotate;                // per-tile rotation of the tap / k-block order (L2 hot-spot avoidance)
+  int acc_cols;              // TMEM column stride between the two accumulators
   int cta2, pair_units;      // CTA-pair kernel: units = ceil(m_tiles / 2) * n_tiles
   uint32_t idesc2;
   uint32_t patch_bytes, patch_tx, ring_off;
@@ -313,6 +320,40 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiCtx& 
   }
 }
 
+// Swap mode: this thread owns ONE output channel (TMEM lane) and v holds 16 consecutive
+// accumulator columns = pixels of it.  A warp's 32 lanes write 32 consecutive channels of a
+// pixel (64 B runs).  Column n of the tile is pixel pix0 + n of a band of full-width rows, or,
+// with the halo patch (columns of 8 rows), pixel (h0 + (n & 7), w0 + (n >> 3)).
+struct SwapTile {
+  long pix0;          // first pixel of the band / of image `on`
+  int valid;          // band: pixels inside the map
+  int h0, w0;         // halo patch tile origin
+};
+__device__ __forceinline__ void epilogue_chunk_swap(const TcParams& p, const float* sp, int cpad,
+                                                    const uint32_t (&v)[16], int cout,
+                                                    const SwapTile& t, int n0) {
+  if (cout >= p.cout_store || (p.debug & 8)) return;
+  const float sc = sp[cout], sh = sp[cpad + cout], sl = sp[2 * cpad + cout];
+  __half* o = p.out + p.out_coff + cout;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float y = fmaf(__uint_as_float(v[j]), sc, sh);
+    if (p.act == ACT_RELU) y = fmaxf(y, 0.f);
+    else if (p.act == ACT_PRELU) y = y >= 0.f ? y : y * sl;
+    long pix;
+    bool ok;
+    if (p.halo) {
+      const int h = t.h0 + (j & 7), w = t.w0 + ((n0 + j) >> 3);     // n0 is a multiple of 16
+      ok = h < p.H_out && w < p.W_out;
+      pix = t.pix0 + static_cast<long>(h) * p.W_out + w;
+    } else {
+      ok = n0 + j < t.valid;
+      pix = t.pix0 + n0 + j;
+    }
+    if (ok && !(p.debug & 4)) o[pix * p.out_cs] = __float2half_rn(y);
+  }
+}
+
 template <int KSTEPS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -323,7 +364,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t ring = base + p.ring_off;              // halo mode: two patch buffers come first
   const uint32_t params_s = ring + p.stages * p.stage_bytes;
   const int cpad = p.cout_pad <= kMaxParamChannels ? p.cout_pad : 0;
-  const uint32_t bars = params_s + 5u * cpad * 4u;
+  const uint32_t tab_s = params_s + 5u * cpad * 4u;   // halo: per-tap descriptor offset of the shifted patch window
+  const uint32_t bars = tab_s + 256u;
   // barrier layout: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
@@ -355,6 +397,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 0 && p.halo) {
+    // rows_off * 128 B >> 4: what tap (r, s) adds to the patch's descriptor start address
+    for (int t = lane; t < p.taps && t < 64; t += 32) {
+      const int r = t / p.kw, sx = t - r * p.kw;
+      const uint32_t v = (p.halo == 1 ? r * 16 + sx : sx * 16 + r) * 8u;
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_s + 4u * t), "r"(v) : "memory");
+    }
   }
   if (warp >= 2 && cpad) {
     // Stage the per-channel epilogue parameters once per CTA.
@@ -388,9 +438,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------ TMA producer
     int stage = 0, pb = 0;
     uint32_t phase = 0, pphase = 0;
-    const uint32_t sub_tx = p.rows * p.KC * 2 + p.N_tile * p.KC * 2;
+    const int w_rows = p.swap ? 128 : p.N_tile;             // filter rows per k-block
+    const uint32_t sub_tx = p.rows * p.KC * 2 + w_rows * p.KC * 2;
     TileWalk walk = walk_begin(p);
     int tile, it0, it1;
+    long long dbg_wait = 0, dbg_pwait = 0, dbg_t0 = clock64();
+    int dbg_iters = 0;
+    int pq = 0, pq_issued = 0;                   // halo: chunk-steps produced / patches requested
     while (walk_next(p, walk, tile, it0, it1)) {
       // A dependent CTA that is resident early only spins in griddepcontrol.wait while holding
       // an SM that a kernel of another stream could use: release it late.
@@ -402,37 +456,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int hb = mt % p.tiles_h; mt /= p.tiles_h;
       const int nb = mt;
       const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = nb * p.bn;
+      // Every CTA streams the SAME filter blocks; started in lockstep they would all hit the
+      // same L2 lines at the same time.  Each tile walks the taps / k-blocks from its own
+      // starting point (a sum, so the order is free; both CTAs of a stream-K split tile agree).
+      const int rot = p.rotate ? (tile * 13) % (p.halo ? p.taps : p.k_blocks) : 0;
       if (p.halo) {
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(pempty_bar(pb), pphase ^ 1u, p.err, 5);
+        // Patches are requested ONE chunk-step ahead (the next channel chunk of this tile, or
+        // the first chunk of the CTA's next tile): a patch is tens of KB gathered from 16 x
+        // (bw + 2 pad) pixel rows and takes several microseconds to land, far longer than the
+        // few ring stages the filter stream runs ahead of the MMAs.
+        auto issue_patch = [&](int ptile, int pkc) {
+          const int buf = pq_issued & 1;
+          const uint32_t ph = (pq_issued >> 1) & 1u;
+          const long long tp0 = (p.debug & 32) ? clock64() : 0;
+          mbar_wait(pempty_bar(buf), ph ^ 1u, p.err, 5);
+          if (p.debug & 32) dbg_pwait += clock64() - tp0;
           if (elect_one()) {
-            mbar_expect_tx(pfull_bar(pb), p.patch_tx);
-            const int cw = w0 - p.pad, ch = h0 - p.pad;
-            tma_load_5d(base + pb * p.patch_bytes, &tmA, pfull_bar(pb), p.in_coff + kc * p.KC,
-                        p.halo == 1 ? cw : ch, p.halo == 1 ? ch : cw, n0, 0);
+            int pm = ptile / p.n_tiles;
+            const int pwb = pm % p.tiles_w; pm /= p.tiles_w;
+            const int phb = pm % p.tiles_h; pm /= p.tiles_h;
+            const int cw = pwb * p.bw - p.pad, ch = phb * p.bh - p.pad;
+            mbar_expect_tx(pfull_bar(buf), p.patch_tx);
+            tma_load_5d(base + buf * p.patch_bytes, &tmA, pfull_bar(buf), p.in_coff + pkc * p.KC,
+                        p.halo == 1 ? cw : ch, p.halo == 1 ? ch : cw, pm * p.bn, 0);
           }
           __syncwarp();
+          ++pq_issued;
+        };
+        const int pf_it = min(p.stages, p.iters_kc - 1);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          if (pq_issued == pq) issue_patch(tile, kc);       // first step of this CTA
           int tap = 0;
           for (int it = 0; it < p.iters_kc; ++it) {
+            if (it == pf_it && pq_issued == pq + 1 && !(p.debug & 64)) {
+              if (kc + 1 < p.kchunks) issue_patch(tile, kc + 1);
+              else if (!walk_done(p, walk)) issue_patch(walk.tile, 0);   // no stream-K in halo mode
+            }
             const int nsub = min(p.sub, p.taps - tap);
+            const long long tq0 = (p.debug & 32) ? clock64() : 0;
             mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
+            if (p.debug & 32) { dbg_wait += clock64() - tq0; ++dbg_iters; }
             const uint32_t sb = ring + stage * p.stage_bytes;
-            if (elect_one()) {
-              mbar_expect_tx(full_bar(stage), nsub * p.N_tile * p.KC * 2);
-              for (int j = 0; j < nsub; ++j)
-                tma_load_2d(sb + j * p.b_bytes, &tmB, full_bar(stage),
-                            (tap + j) * p.cin_pad + kc * p.KC, nt * p.N_tile);
+            if (p.debug & 1) {                       // timing only: no filter loads
+              if (elect_one()) mbar_arrive(full_bar(stage));
+            } else if (elect_one()) {
+              mbar_expect_tx(full_bar(stage), nsub * w_rows * p.KC * 2);
+              for (int j = 0; j < nsub; ++j) {
+                int t = tap + j + rot;
+                if (t >= p.taps) t -= p.taps;
+                tma_load_2d(sb + j * p.b_bytes, &tmB, full_bar(stage), t * p.cin_pad + kc * p.KC, nt * w_rows);
+              }
             }
             __syncwarp();
             tap += nsub;
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-          if (++pb == 2) { pb = 0; pphase ^= 1u; }
+          ++pq;
         }
         continue;
       }
       int kb = it0 * p.sub;                       // running (tap row, tap col, channel chunk)
-      int kc = kb % p.kchunks, s = (kb / p.kchunks) % p.kw, r = kb / (p.kchunks * p.kw);
+      const int kb0 = (kb + rot) % p.k_blocks;
+      int kc = kb0 % p.kchunks, s = (kb0 / p.kchunks) % p.kw, r = kb0 / (p.kchunks * p.kw);
       for (int it = it0; it < it1; ++it) {
         const int nsub = min(p.sub, p.k_blocks - kb);
         mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
@@ -457,15 +542,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (elect_one()) {
               tma_load_5d(dst, &tmA, full_bar(stage), c0, c1, c2, c3, c4);
               tma_load_2d(dst + p.a_bytes, &tmB, full_bar(stage),
-                          (r * p.kw + s) * p.cin_pad + kc * p.KC, nt * p.N_tile);
+                          (r * p.kw + s) * p.cin_pad + kc * p.KC, nt * w_rows);
             }
-            if (++kc == p.kchunks) { kc = 0; if (++s == p.kw) { s = 0; ++r; } }
+            if (++kc == p.kchunks) { kc = 0; if (++s == p.kw) { s = 0; if (++r == p.kh) r = 0; } }
           }
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
+    if ((p.debug & 32) && blockIdx.x == 0 && lane == 0)
+      printf("producer: total %lld clk, %d iters, wait(empty) %lld, wait(patch empty) %lld\n",
+             clock64() - dbg_t0, dbg_iters, dbg_wait, dbg_pwait);
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     int stage = 0, pb = 0;
@@ -478,43 +566,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                    b_off = p.a_bytes >> 4;
     TileWalk walk = walk_begin(p);
     int tile, it0, it1;
+    long long dbg_wf = 0, dbg_te = 0, dbg_pw = 0, dbg_last = 0, dbg_t0 = clock64(), dbg_issue = 0, dbg_commit = 0;
+    int dbg_n = 0;
     for (; walk_next(p, walk, tile, it0, it1); ++tile_it) {
       const int acc = tile_it & 1;
       const uint32_t acc_phase = (tile_it >> 1) & 1u;
+      if (p.debug & 32) dbg_last = clock64();
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d_tmem = tmem_base + acc * p.N_tile;
+      if (p.debug & 32) dbg_te += clock64() - dbg_last, dbg_last = clock64();
+      const uint32_t d_tmem = tmem_base + acc * p.acc_cols;
       int kb = it0 * p.sub;
       uint32_t accumulate = 0;
+      const int rot = p.rotate && p.halo ? (tile * 13) % p.taps : 0;
       if (p.halo) {
         for (int kc = 0; kc < p.kchunks; ++kc) {
+          if (p.debug & 32) dbg_last = clock64();
           mbar_wait(pfull_bar(pb), pphase, p.err, 6);
-          const uint32_t patch = base + pb * p.patch_bytes;
+          if (p.debug & 32) dbg_pw += clock64() - dbg_last;
+          const uint32_t patch_lo = umma_desc_lo(base + pb * p.patch_bytes);
           int tap = 0;
           for (int it = 0; it < p.iters_kc; ++it) {
             const int nsub = min(p.sub, p.taps - tap);
+            const long long tq0 = (p.debug & 32) ? clock64() : 0;
             mbar_wait(full_bar(stage), phase, p.err, 3);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (p.debug & 32) { dbg_wf += clock64() - tq0; ++dbg_n; }
+            if (!(p.debug & 16)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
+              const long long ti0 = (p.debug & 32) ? clock64() : 0;
               const uint32_t b_lo0 = a_lo0 + stage * stage_step;
               for (int j = 0; j < nsub; ++j) {
-                const int t = tap + j, r = t / p.kw, s = t - r * p.kw;
-                const uint32_t rows_off = p.halo == 1 ? r * 16 + s : s * 16 + r;
-                const uint32_t a_start = patch + rows_off * 128u;
-                const uint32_t a_lo = umma_desc_lo(a_start);
+                int t = tap + j + rot;
+                if (t >= p.taps) t -= p.taps;
+                uint32_t tap_off;                // no divisions on the issuing thread's critical path
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tap_off) : "r"(tab_s + 4u * t));
+                const uint32_t a_lo = patch_lo + tap_off;
                 const uint32_t a_hi = halo_hi;   // base_offset stays 0: the swizzle XOR uses absolute smem address bits
                 const uint32_t b_lo = b_lo0 + j * (p.b_bytes >> 4);
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
-                  umma_f16(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, desc_hi, p.idesc, accumulate);
+                  if (p.debug & 2) break;
+                  if (p.swap)   // filters on M; the shifted patch window (bw columns of 8 rows) on N
+                    umma_f16(d_tmem, b_lo + 2 * k, desc_hi, a_lo + 2 * k, a_hi, p.idesc, accumulate);
+                  else
+                    umma_f16(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, desc_hi, p.idesc, accumulate);
                   accumulate = 1;
                 }
               }
+              const long long ti1 = (p.debug & 32) ? clock64() : 0;
               umma_commit(empty_bar(stage));
               if (it == p.iters_kc - 1) {
                 umma_commit(pempty_bar(pb));
                 if (kc == p.kchunks - 1) umma_commit(tfull_bar(acc));
               }
+              if (p.debug & 32) { dbg_issue += ti1 - ti0; dbg_commit += clock64() - ti1; }
             }
             __syncwarp();
             tap += nsub;
@@ -527,25 +632,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int it = it0; it < it1; ++it) {
         const int nsub = min(p.sub, p.k_blocks - kb);
         kb += nsub;
+        const long long tq0 = (p.debug & 32) ? clock64() : 0;
         mbar_wait(full_bar(stage), phase, p.err, 3);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (p.debug & 32) { dbg_wf += clock64() - tq0; ++dbg_n; }
+        if (!(p.debug & 16)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
+          const long long ti0 = (p.debug & 32) ? clock64() : 0;
           uint32_t a_lo = a_lo0 + stage * stage_step;
           if (!(p.debug & 2)) {
             for (int j = 0; j < nsub; ++j, a_lo += sub_step) {
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {      // +32 B (2 x 16 B units) per K step
-                umma_f16(d_tmem, a_lo + 2 * k, desc_hi, a_lo + b_off + 2 * k, desc_hi, p.idesc, accumulate);
+                if (p.swap)
+                  umma_f16(d_tmem, a_lo + b_off + 2 * k, desc_hi, a_lo + 2 * k, desc_hi, p.idesc, accumulate);
+                else
+                  umma_f16(d_tmem, a_lo + 2 * k, desc_hi, a_lo + b_off + 2 * k, desc_hi, p.idesc, accumulate);
                 accumulate = 1;
               }
             }
           }
+          const long long ti1 = (p.debug & 32) ? clock64() : 0;
           umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
           if (it == it1 - 1) umma_commit(tfull_bar(acc));
+          if (p.debug & 32) { dbg_issue += ti1 - ti0; dbg_commit += clock64() - ti1; }
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+    }
+    if (p.debug & 32) {
+      for (int o = 16; o; o >>= 1) {
+        dbg_issue += __shfl_xor_sync(0xffffffffu, dbg_issue, o);
+        dbg_commit += __shfl_xor_sync(0xffffffffu, dbg_commit, o);
+      }
+      if (blockIdx.x == 0 && lane == 0)
+        printf("mma: total %lld clk, %d iters, wait(full) %lld, wait(tmem empty) %lld, wait(patch) %lld, "
+               "mma issue %lld, commit %lld\n",
+               clock64() - dbg_t0, dbg_n, dbg_wf, dbg_te, dbg_pw, dbg_issue, dbg_commit);
     }
   } else {
     // ---------------------------------------------------------------- epilogue
@@ -575,13 +698,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ow = wb * p.bw + w_l, oh = hb * p.bh + h_l, on = nb * p.bn + n_l;
       e.valid = row < p.rows && ow < p.W_out && oh < p.H_out && on < p.N;
       e.pix = (static_cast<long>(on) * p.H_out + oh) * p.W_out + ow;
+      // swap mode: the tile is a band of full-width rows of image nb (consecutive pixels), or
+      // bw columns x 8 rows of the halo patch
+      SwapTile st;
+      st.pix0 = p.halo ? static_cast<long>(nb) * p.H_out * p.W_out
+                       : (static_cast<long>(nb) * p.H_out + hb * p.bh) * p.W_out;
+      st.valid = min(p.rows, (p.H_out - hb * p.bh) * p.W_out);
+      st.h0 = hb * p.bh; st.w0 = wb * p.bw;
+      const int sw_cout = nt * 128 + row;
       e.rpix = e.pix;
       if (p.res && p.res_up2)
         e.rpix = (static_cast<long>(on) * p.res_H + (oh >> 1)) * p.res_W + (ow >> 1);
 
       mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.N_tile;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.acc_cols;
       const int cn0 = nt * p.N_tile;
       uint32_t va[16], vb[16];
       int c = half;
@@ -648,14 +779,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
         if (c + 2 < nchunks) tmem_ld16_async(taddr + (c + 2) * 16, vb);
         add_partial(va, c);
-        epilogue_chunk(p, e, va, cn0 + c * 16);
+        if (p.swap) epilogue_chunk_swap(p, e.sp, cpad, va, sw_cout, st, c * 16);
+        else epilogue_chunk(p, e, va, cn0 + c * 16);
         c += 2;
         if (c >= nchunks) break;
         __syncwarp();
         tmem_ld_wait();
         if (c + 2 < nchunks) tmem_ld16_async(taddr + (c + 2) * 16, va);
         add_partial(vb, c);
-        epilogue_chunk(p, e, vb, cn0 + c * 16);
+        if (p.swap) epilogue_chunk_swap(p, e.sp, cpad, vb, sw_cout, st, c * 16);
+        else epilogue_chunk(p, e, vb, cn0 + c * 16);
         c += 2;
       }
       // Release the accumulator back to the MMA warp.
@@ -919,6 +1052,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int ow = wb * p.bw + w_l, oh = hb * p.bh + h_l, on = nb * p.bn + n_l;
       e.valid = row < p.rows && ow < p.W_out && oh < p.H_out && on < p.N;
       e.pix = (static_cast<long>(on) * p.H_out + oh) * p.W_out + ow;
+      // swap mode: the tile is a band of full-width rows of image nb (consecutive pixels), or
+      // bw columns x 8 rows of the halo patch
+      SwapTile st;
+      st.pix0 = p.halo ? static_cast<long>(nb) * p.H_out * p.W_out
+                       : (static_cast<long>(nb) * p.H_out + hb * p.bh) * p.W_out;
+      st.valid = min(p.rows, (p.H_out - hb * p.bh) * p.W_out);
+      st.h0 = hb * p.bh; st.w0 = wb * p.bw;
+      const int sw_cout = nt * 128 + row;
       e.rpix = e.pix;
       if (p.res && p.res_up2)
         e.rpix = (static_cast<long>(on) * p.res_H + (oh >> 1)) * p.res_W + (ow >> 1);
@@ -1085,6 +1226,51 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
       }
     }
   }
+  {
+    // Swap mode: 128-cout layers whose K is long enough for the main loop to dominate and whose
+    // epilogue is the plain one (per-channel affine + activation, fp16 store).
+    //   band variant:  N = bh full-width rows (<= 256 pixels), one TMA box per tap (like the
+    //                  plain mode, 46 KB of operands per 128x240x64 block);
+    //   patch variant: N = bw columns x 8 rows read through shifted descriptors from the
+    //                  resident halo patch (orientation 2), so only the 16 KB filter block
+    //                  streams per k-block — the one that pays for 5x5 / 7x7 filters.
+    // Default off.  Measured on the 7x7 128->128 layers (profiles/r01_swap_modes.txt): the band
+    // variant is 3-6 % faster alone and no faster with both OpenPose branches in flight; the patch
+    // variant is bound by the ISSUING thread (~66 cycles per tcgen05.mma against 80 cycles of
+    // tensor work at N = 160, plus the per-stage handshake), not by operand traffic.  Both are
+    // parity-tested (tests/test_gpu_ops.py::test_conv_swap_mode) and kept for the next round.
+    int want = 0;                                   // 0 off, 1 auto, 2 whenever possible, 3 band variant only
+    if (const char* e = getenv("TRB_TC_SWAP")) want = atoi(e);
+    const bool plain_epi = !a.res.ptr && !a.out2.ptr && !a.out_f32;
+    const bool base_ok = a.stride == 1 && p.KC == 64 && a.cout_pad % 128 == 0 && plain_epi;
+    const bool patch_ok = base_ok && a.kh == a.kw && a.kh >= 3 && a.pad == a.kh / 2 && 8 + 2 * a.pad <= 16;
+    const bool patch_worth = a.cout_pad == 128 && p.taps >= 25;
+    if (want && want != 3 && patch_ok && (want == 2 || patch_worth)) {
+      const int tw = ceil_div(p.W_out, 32);
+      int bw = ceil_div(p.W_out, tw);
+      bw += bw & 1;                                 // N = 8 * bw must be a multiple of 16
+      p.swap = 1; p.halo = 2;
+      p.bw = bw; p.bh = 8; p.bn = 1;
+      p.N_tile = 8 * bw;
+      p.n_tiles = a.cout_pad / 128;
+    } else if (want && !p.halo && base_ok && p.W_out <= 256) {
+      // band of bh full-width rows: N = W_out * bh pixels, a multiple of 16, at most 256
+      int best_bh = 0;
+      double best_eff = 0;
+      for (int bh = 1; bh <= p.H_out && bh * p.W_out <= 256; ++bh) {
+        if ((bh * p.W_out) % 16) continue;
+        const double eff = double(p.H_out) / (ceil_div(p.H_out, bh) * bh) * (bh * p.W_out >= 128 ? 1.0 : 0.5);
+        if (eff >= best_eff) { best_eff = eff; best_bh = bh; }
+      }
+      const bool worth = a.cout_pad == 128 && p.k_blocks >= 8 && best_bh * p.W_out >= 192 && best_eff >= 0.9;
+      if (best_bh && (want >= 2 || worth)) {
+        p.swap = 1;
+        p.bw = p.W_out; p.bh = best_bh; p.bn = 1;
+        p.N_tile = p.bw * p.bh;                      // UMMA N = pixels of the band
+        p.n_tiles = a.cout_pad / 128;                // filter (M) tiles
+      }
+    }
+  }
   p.rows = p.bw * p.bh * p.bn;
   p.tiles_w = ceil_div(p.W_out, p.bw);
   p.tiles_h = ceil_div(p.H_out, p.bh);
@@ -1102,7 +1288,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     const int units = ceil_div(m_tiles, 2) * p.n_tiles;
     const int sms = num_sms();
-    const bool ok = !p.halo && p.KC == 64 && p.N_tile % 32 == 0 && m_tiles >= 2;
+    const bool ok = !p.halo && !p.swap && p.KC == 64 && p.N_tile % 32 == 0 && m_tiles >= 2;
     const bool worth = p.N_tile >= 128 && p.k_blocks >= 8 &&
                        ceil_div(units, sms / 2) <= ceil_div(p.total_tiles, sms);
     if (ok && (want == 1 || (want == 2 && worth))) {
@@ -1112,8 +1298,8 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     }
   }
 
-  p.a_bytes = round_up(128 * p.KC * 2, 1024);         // MMA always reads 128 rows
-  p.b_bytes = round_up((p.cta2 ? p.N_tile / 2 : p.N_tile) * p.KC * 2, 1024);
+  p.a_bytes = round_up((p.swap ? p.rows : 128) * p.KC * 2, 1024);   // pixel tile (the MMA reads 128 rows as A)
+  p.b_bytes = round_up((p.swap ? 128 : p.cta2 ? p.N_tile / 2 : p.N_tile) * p.KC * 2, 1024);   // filter tile
   p.sub_bytes = p.halo ? p.b_bytes : p.a_bytes + p.b_bytes;
   // k-blocks per ring stage: enough tensor work (>= ~512 cycles = 8 MMAs of N=128) to
   // cover the single-warp issue latency, within ~64 KB per stage.
@@ -1127,11 +1313,13 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   p.stage_bytes = p.sub * p.sub_bytes;
   const uint32_t param_bytes = 5u * p.cout_pad * 4u;
   if (p.halo) {
-    p.patch_tx = (16 + 2 * a.pad) * 16 * 128;
+    p.patch_tx = ((p.swap ? p.bw : 16) + 2 * a.pad) * 16 * 128;
     p.patch_bytes = round_up(p.patch_tx, 1024);
     p.ring_off = 2 * p.patch_bytes;
   }
-  p.stages = std::min(kMaxStages, int((kSmemBudget - param_bytes - p.ring_off) / p.stage_bytes));
+  // the patch variant of swap mode keeps two (bw + 2 pad) x 16 pixel patches resident: use all 227 KB
+  const uint32_t budget = p.swap && p.halo ? 224u * 1024 : kSmemBudget;
+  p.stages = std::min(kMaxStages, int((budget - param_bytes - p.ring_off) / p.stage_bytes));
   p.stages = std::max(2, std::min(p.stages, (p.halo ? p.iters_kc * p.kchunks : p.iters) + 1));
   p.sbo_bytes = 8u * p.KC * 2u;
   CUtensorMapSwizzle swz;
@@ -1140,8 +1328,9 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   else { p.layout_type = 6; swz = CU_TENSOR_MAP_SWIZZLE_32B; }
   // kind::f16 instruction descriptor: D=f32, A=B=f16, K-major, N>>3, M>>4.
   p.idesc = (1u << 4) | (uint32_t(p.N_tile >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+  p.acc_cols = p.swap ? 256 : p.N_tile;
   uint32_t cols = 32;
-  while (cols < uint32_t(2 * p.N_tile)) cols <<= 1;
+  while (cols < uint32_t(2 * p.acc_cols)) cols <<= 1;
   p.tmem_cols = cols;
 
   p.scale = a.scale; p.shift = a.shift; p.slope = a.slope;
@@ -1155,7 +1344,8 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   p.err = tc_error_flag();
   if (const char* dbg = getenv("TRB_TC_DEBUG")) p.debug = atoi(dbg);
   p.pdl_late = 1;
-  p.pdl_late = 1;
+  p.rotate = 0;   // measured: no effect (profiles/r01_swap_modes.txt) — the filter stream is not L2 hot-spot bound
+  if (const char* e = getenv("TRB_TC_ROTATE")) p.rotate = atoi(e);
   if (const char* e = getenv("TRB_TC_PDL_LATE")) p.pdl_late = atoi(e);
   TR_CHECK(a.scale && a.shift, "epilogue scale/shift are required");
   TR_CHECK(a.act != ACT_PRELU || a.slope, "PReLU needs slopes");
@@ -1169,7 +1359,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   if (p.halo == 2) {        // dims (C, H, W, N): patch rows run along H
     gdim[0] = cs; gdim[1] = H; gdim[2] = W; gdim[3] = N; gdim[4] = 1;
     gstr[0] = W * cs * 2; gstr[1] = cs * 2; gstr[2] = H * W * cs * 2; gstr[3] = N * H * W * cs * 2;
-    box[0] = p.KC; box[1] = 16; box[2] = 16 + 2 * a.pad; box[3] = 1; box[4] = 1;
+    box[0] = p.KC; box[1] = 16; box[2] = (p.swap ? p.bw : 16) + 2 * a.pad; box[3] = 1; box[4] = 1;
   } else if (a.stride == 1) {
     gdim[0] = cs; gdim[1] = W; gdim[2] = H; gdim[3] = N; gdim[4] = 1;
     gstr[0] = cs * 2; gstr[1] = W * cs * 2; gstr[2] = H * W * cs * 2; gstr[3] = N * H * W * cs * 2;
@@ -1187,7 +1377,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   const cuuint64_t ktot = cuuint64_t(a.kh) * a.kw * a.cin_pad;
   cuuint64_t wdim[2] = {ktot, cuuint64_t(a.cout_pad)};
   cuuint64_t wstr[1] = {ktot * 2};
-  cuuint32_t wbox[2] = {cuuint32_t(p.KC), cuuint32_t(p.cta2 ? p.N_tile / 2 : p.N_tile)};
+  cuuint32_t wbox[2] = {cuuint32_t(p.KC), cuuint32_t(p.swap ? 128 : p.cta2 ? p.N_tile / 2 : p.N_tile)};
   r = encode(&plan->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(a.w), wdim, wstr,
              wbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1195,7 +1385,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
 
   plan->grid = p.cta2 ? 2 * std::min(p.pair_units, num_sms() / 2) : std::min(p.total_tiles, num_sms());
   plan->smem = p.ring_off + p.stages * p.stage_bytes + param_bytes + 1024 /*alignment*/ +
-               8 * (2 * kMaxStages + 10) + 16;
+               256 /*tap table*/ + 8 * (2 * kMaxStages + 10) + 16;
   {
     // Stream-K where whole-tile scheduling leaves SMs idle in the last round.  Measured
     // (profiles/r01_stream_k.txt): the partial-tile hand-over costs ~8 us per launch with

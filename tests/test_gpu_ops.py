@@ -86,6 +86,7 @@ def test_conv_stream_k(native, case, monkeypatch):
     x, w, scale, shift, slope, res, up2 = make_case(case)
     kw = dict(stride=stride, act=act, slope=slope, res=res, res_up2=up2)
     monkeypatch.setenv('TRB_TC_HALO', '0')
+    monkeypatch.setenv('TRB_TC_SWAP', '0')
     monkeypatch.setenv('TRB_TC_SK', '0')
     whole, _ = conv2d_native(native, x, w, scale, shift, use_tc=True, out_f32=True, **kw)
     monkeypatch.setenv('TRB_TC_SK', '2')
@@ -171,6 +172,56 @@ def test_sepconv_matches_reference(native, case, fused):
     tol = 4e-3 * max(1.0, float(ref.abs().max()))
     err = (out.cpu().double() - ref).abs().max()
     assert torch.isfinite(out.float()).all() and err <= tol, describe_mismatch(out, ref, tol)
+
+
+# Swap mode (filters on the UMMA M axis, a band of full-width pixel rows on N <= 256; TMEM holds
+# the transposed tile): forced wherever the layer allows it, ragged last bands, two filter
+# tiles, PReLU, and combined with stream-K.
+SWAP_CASES = [
+    (1, 23, 40, 128, 128, 7, 1, 1, None, 'swap-conv7-openpose'),
+    (2, 23, 40, 192, 128, 7, 1, 1, None, 'swap-conv7-cat192'),
+    (3, 13, 24, 64, 128, 3, 1, 2, None, 'swap-ragged-band-prelu'),
+    (1, 23, 40, 64, 256, 3, 1, 0, None, 'swap-two-filter-tiles'),
+    (2, 9, 16, 128, 120, 1, 1, 1, None, 'swap-cout120'),
+    (2, 46, 81, 64, 128, 5, 1, 1, None, 'swap-5x5-wide-map'),
+]
+
+
+@pytest.mark.parametrize('variant', ['2', '3'], ids=['patch', 'band'])
+@pytest.mark.parametrize('case', SWAP_CASES, ids=[c[-1] for c in SWAP_CASES])
+def test_conv_swap_mode(native, case, variant, monkeypatch):
+    N, H, W, cin, cout, k, stride, act, res_kind, tag = case
+    x, w, scale, shift, slope, res, up2 = make_case(case)
+    kw = dict(stride=stride, act=act, slope=slope)
+    monkeypatch.setenv('TRB_TC_HALO', '0')
+    monkeypatch.setenv('TRB_TC_SWAP', '0')
+    plain, _ = conv2d_native(native, x, w, scale, shift, use_tc=True, **kw)
+    # 2: filters x columns of the resident halo patch where the filter allows (k >= 3), else
+    # 3: filters x a band of full-width rows
+    monkeypatch.setenv('TRB_TC_SWAP', variant)
+    out, _ = conv2d_native(native, x, w, scale, shift, use_tc=True, **kw)
+    ref = conv2d_reference(x, w, scale, shift, **kw)
+    tol = 2e-3 * max(1.0, float(ref.abs().max()))
+    err = (out.cpu().double() - ref).abs().max()
+    assert torch.isfinite(out.float()).all() and err <= tol, describe_mismatch(out, ref, tol)
+    # same fp16 operands and fp32 accumulation over the same k order: the two tilings agree
+    # to fp16 output rounding
+    assert (out.float() - plain.float()).abs().max() <= tol
+
+
+def test_conv_swap_mode_stream_k(native, monkeypatch):
+    case = (40, 23, 40, 128, 128, 3, 1, 1, None, 'swap-sk')
+    x, w, scale, shift, slope, res, up2 = make_case(case)
+    monkeypatch.setenv('TRB_TC_HALO', '0')
+    monkeypatch.setenv('TRB_TC_SWAP', '3')
+    monkeypatch.setenv('TRB_TC_SK', '0')
+    whole, _ = conv2d_native(native, x, w, scale, shift, use_tc=True, act=1)
+    monkeypatch.setenv('TRB_TC_SK', '2')
+    split, _ = conv2d_native(native, x, w, scale, shift, use_tc=True, act=1)
+    ref = conv2d_reference(x, w, scale, shift, act=1)
+    tol = 2e-3 * max(1.0, float(ref.abs().max()))
+    assert (split.cpu().double() - ref).abs().max() <= tol, describe_mismatch(split, ref, tol)
+    assert (whole.cpu().double() - ref).abs().max() <= tol, describe_mismatch(whole, ref, tol)
 
 
 def test_conv_tc_fp32_output(native):
