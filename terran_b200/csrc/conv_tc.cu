@@ -354,8 +354,13 @@ __device__ __forceinline__ void epilogue_chunk_swap(const TcParams& p, const flo
   }
 }
 
-template <int KSTEPS>
-__global__ void __launch_bounds__(kThreads, 1)
+// MINB = 2: two CTAs co-resident per SM (<= 96 registers, <= ~110 KB smem, <= 256 TMEM
+// columns each).  tcgen05.mma issue costs the single issuing thread ~50-66 cycles per
+// instruction plus ~500 cycles of barrier/commit latency per ring stage (measured with the
+// clock64 instrumentation, profiles/r01_swap_modes.txt), which is MORE than the tensor time of
+// an N <= 128 instruction (64 cycles): two CTAs give the SM's tensor pipe two issuing threads.
+template <int KSTEPS, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1134,10 +1139,12 @@ int num_sms() {
 
 using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const TcParams);
 
-KernelFn kernel_for(int kc) {
-  KernelFn fn = kc == 64 ? conv_tc_kernel<4> : (kc == 32 ? conv_tc_kernel<2> : conv_tc_kernel<1>);
-  static bool attr_set[3] = {false, false, false};
-  const int slot = kc == 64 ? 0 : (kc == 32 ? 1 : 2);
+KernelFn kernel_for(int kc, int ctas_per_sm) {
+  KernelFn fn = ctas_per_sm == 2
+                    ? (kc == 64 ? conv_tc_kernel<4, 2> : (kc == 32 ? conv_tc_kernel<2, 2> : conv_tc_kernel<1, 2>))
+                    : (kc == 64 ? conv_tc_kernel<4, 1> : (kc == 32 ? conv_tc_kernel<2, 1> : conv_tc_kernel<1, 1>));
+  static bool attr_set[6] = {false, false, false, false, false, false};
+  const int slot = (kc == 64 ? 0 : (kc == 32 ? 1 : 2)) + (ctas_per_sm == 2 ? 3 : 0);
   if (!attr_set[slot]) {
     TR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[slot] = true;
@@ -1148,7 +1155,7 @@ KernelFn kernel_for(int kc) {
 }  // namespace
 
 // Stream-K scratch: one flag per CTA (+1), then per CTA a 128 x 256 fp32 accumulator tile.
-constexpr size_t kSkFlagBytes = 1024;
+constexpr size_t kSkFlagBytes = 2048;
 size_t conv_tc_sk_scratch_bytes() { return kSkFlagBytes + size_t(num_sms()) * 128 * 256 * 4; }
 
 struct ConvTcPlan {
@@ -1156,6 +1163,7 @@ struct ConvTcPlan {
   TcParams p;
   void* sk_own = nullptr;
   int grid;
+  int ctas_per_sm = 1;
   uint32_t smem;
   double flops;
 };
@@ -1307,6 +1315,18 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   const int k_per_group = p.halo ? p.taps : p.k_blocks;
   auto clamp_sub = [&](int v) { return std::max(1, std::min(std::min(kMaxSub, v), k_per_group)); };
   p.sub = clamp_sub(std::min(ceil_div(512, mma_cycles), int(65536 / p.sub_bytes)));
+  {
+    // Two CTAs per SM for narrow filter tiles (see conv_tc_kernel): one k-block per stage so
+    // that three stages fit in half of the SM's shared memory.
+    int want = 1;                                   // 0 off, 1 auto, 2 whenever possible
+    if (const char* e = getenv("TRB_TC_CTAS")) want = atoi(e);
+    const bool ok = !p.halo && !p.cta2 && !p.swap && p.N_tile <= 128 && 3 * p.sub_bytes <= 100 * 1024;
+    const bool worth = p.k_blocks >= 8 && p.total_tiles >= num_sms() + num_sms() / 2;
+    if (ok && (want == 2 || (want == 1 && worth))) {
+      plan->ctas_per_sm = 2;
+      p.sub = 1;
+    }
+  }
   if (const char* s = getenv("TRB_TC_SUB")) p.sub = clamp_sub(atoi(s));
   p.iters = ceil_div(p.k_blocks, p.sub);
   p.iters_kc = ceil_div(p.taps, p.sub);
@@ -1318,7 +1338,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     p.ring_off = 2 * p.patch_bytes;
   }
   // the patch variant of swap mode keeps two (bw + 2 pad) x 16 pixel patches resident: use all 227 KB
-  const uint32_t budget = p.swap && p.halo ? 224u * 1024 : kSmemBudget;
+  const uint32_t budget = p.swap && p.halo ? 224u * 1024 : plan->ctas_per_sm == 2 ? 108u * 1024 : kSmemBudget;
   p.stages = std::min(kMaxStages, int((budget - param_bytes - p.ring_off) / p.stage_bytes));
   p.stages = std::max(2, std::min(p.stages, (p.halo ? p.iters_kc * p.kchunks : p.iters) + 1));
   p.sbo_bytes = 8u * p.KC * 2u;
@@ -1383,7 +1403,8 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: " + std::to_string(int(r)));
 
-  plan->grid = p.cta2 ? 2 * std::min(p.pair_units, num_sms() / 2) : std::min(p.total_tiles, num_sms());
+  plan->grid = p.cta2 ? 2 * std::min(p.pair_units, num_sms() / 2)
+                      : std::min(p.total_tiles, plan->ctas_per_sm * num_sms());
   plan->smem = p.ring_off + p.stages * p.stage_bytes + param_bytes + 1024 /*alignment*/ +
                256 /*tap table*/ + 8 * (2 * kMaxStages + 10) + 16;
   {
@@ -1411,7 +1432,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     }
   }
   plan->flops = 2.0 * p.N * p.H_out * p.W_out * double(a.cout_pad) * a.kh * a.kw * a.cin_pad;
-  kernel_for(p.KC);
+  kernel_for(p.KC, plan->ctas_per_sm);
   return plan;
 }
 
@@ -1458,7 +1479,7 @@ void conv_tc_launch(const ConvTcPlan* plan, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  TR_CUDA(cudaLaunchKernelEx(&cfg, kernel_for(plan->p.KC), plan->tmA, plan->tmB, plan->p));
+  TR_CUDA(cudaLaunchKernelEx(&cfg, kernel_for(plan->p.KC, plan->ctas_per_sm), plan->tmA, plan->tmB, plan->p));
 }
 
 }  // namespace trb
