@@ -29,7 +29,7 @@ for step in "$@"; do
     ncu_full) run ncu_full 1500 ncu --set full --clock-control none --import-source on -k regex:conv_tc \
                 -s 100 -c 3 -f -o gpurun_out/prof_conv_tc python bench.py --steps 1 --warmup 1 --no-cpu-baseline ;;
     ncu_traffic) run ncu_traffic 1500 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
-                --clock-control none -k regex:conv_tc -s 378 -c 126 --csv --log-file gpurun_out/traffic.csv \
+                --clock-control none -k regex:conv_tc -s 279 -c 93 --csv --log-file gpurun_out/traffic.csv \
                 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-per-config ;;
     *)       run custom 1200 bash -c "$step" ;;
   esac

@@ -1,1 +1,2 @@
-for sub in 2 3; do echo "== TRB_TC_CTAS=0 TRB_TC_SUB=$sub"; TRB_TC_CTAS=0 TRB_TC_SUB=$sub python scripts/bench_conv.py "7x7" "arcface 3x3 256" "vgg 3x3 256" "vgg 3x3 512"; done
+for i in 1 0; do echo "== arcface layers TRB_TC_ISSUERS=$i"; TRB_TC_ISSUERS=$i python scripts/arcface_layers.py; done
+for i in 1 0 1 0; do echo "== net TRB_TC_ISSUERS=$i"; TRB_TC_ISSUERS=$i python scripts/profile_ops.py openpose arcface retinaface --brief | grep -E "^==|k7|tcgen05"; done

@@ -38,6 +38,7 @@ namespace trb {
 namespace {
 
 constexpr int kThreads = 320;
+constexpr int kThreads1 = 352;              // single-CTA kernel: + a second MMA-issuing warp (warp 10)
 constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 8;
 constexpr int kMaxSub = 4;
@@ -85,6 +86,11 @@ struct TcParams {
   // the pixel tile the B operand (N = rows <= 256 pixels, a band of full-width rows), so one
   // instruction does N = 240 instead of 128 columns of work per 128 x 64 filter block read from
   // shared memory.  TMEM holds D^T: lane = cout, column = pixel.
+  // 2: warps 1 and 10 issue alternate ring stages into two accumulators the epilogue adds
+  // (non-halo path, N_tile <= 128).  The tensor pipe queues only ~3 instructions, so while ONE
+  // issuer does its per-stage barrier/commit work (~600 cycles) the pipe runs dry; a second
+  // issuer's MMAs fill that time.
+  int issuers;
   int swap;
   int rotate;                // per-tile rotation of the tap / k-block order (L2 hot-spot avoidance)
   int acc_cols;              // TMEM column stride between the two accumulators
@@ -354,13 +360,80 @@ __device__ __forceinline__ void epilogue_chunk_swap(const TcParams& p, const flo
   }
 }
 
+// One of TWO MMA-issuing warps (non-halo path): issuer `w` owns the ring stages of every
+// other GLOBAL iteration (g = w, w + 2, ...), waits for their full barriers, issues their MMAs
+// and commits their empty barriers itself (tcgen05.commit tracks the issuing thread's own
+// instructions only).  Each issuer accumulates into ITS OWN TMEM tile (columns w * N_tile of
+// the accumulator buffer) and the epilogue adds the two: no instruction of one thread ever
+// depends on one of the other, and the result does not depend on how the two streams
+// interleave in the tensor pipe (bit-reproducible).  tmem_full is initialised with count 2;
+// an issuer without work in a (one-iteration) segment arrives plainly.
+template <int KSTEPS>
+__device__ __forceinline__ void mma_issuer_alternate(const TcParams& p, int w, uint32_t ring,
+                                                     uint32_t tmem_base, uint32_t bars) {
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + 2 + a); };
+  const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
+  const uint32_t a_lo0 = umma_desc_lo(ring);
+  const uint32_t stage_step = p.stage_bytes >> 4, sub_step = p.sub_bytes >> 4, b_off = p.a_bytes >> 4;
+  // my stage / phase follow the global iteration counter in steps of two
+  int stage = w % p.stages;
+  uint32_t phase = (w / p.stages) & 1u;
+  int g = 0, tile_it = 0;                       // global iteration index of the segment start
+  TileWalk walk = walk_begin(p);
+  int tile, it0, it1;
+  for (; walk_next(p, walk, tile, it0, it1); ++tile_it) {
+    const int acc = tile_it & 1;
+    const uint32_t acc_phase = (tile_it >> 1) & 1u;
+    const int n_it = it1 - it0;
+    const int first = ((g & 1) == w) ? 0 : 1;   // my first iteration within the segment
+    g += n_it;
+    mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);   // (also: never lap the previous use)
+    if (first >= n_it) {                         // a one-iteration segment owned by the other issuer
+      if (elect_one()) mbar_arrive(tfull_bar(acc));
+      __syncwarp();
+      continue;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t d_tmem = tmem_base + acc * p.acc_cols + w * p.N_tile;
+    for (int i = first; i < n_it; i += 2) {
+      const int nsub = min(p.sub, p.k_blocks - (it0 + i) * p.sub);
+      mbar_wait(full_bar(stage), phase, p.err, 3);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        uint32_t a_lo = a_lo0 + stage * stage_step;
+        uint32_t accumulate = i == first ? 0u : 1u;
+        if (!(p.debug & 2)) {
+          for (int j = 0; j < nsub; ++j, a_lo += sub_step) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+              if (p.swap)
+                umma_f16(d_tmem, a_lo + b_off + 2 * k, desc_hi, a_lo + 2 * k, desc_hi, p.idesc, accumulate);
+              else
+                umma_f16(d_tmem, a_lo + 2 * k, desc_hi, a_lo + b_off + 2 * k, desc_hi, p.idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+        }
+        umma_commit(empty_bar(stage));
+        if (i + 2 >= n_it) umma_commit(tfull_bar(acc));     // my last iteration of this segment
+      }
+      __syncwarp();
+      stage += 2;
+      if (stage >= p.stages) { stage -= p.stages; phase ^= 1u; }
+    }
+  }
+}
+
 // MINB = 2: two CTAs co-resident per SM (<= 96 registers, <= ~110 KB smem, <= 256 TMEM
 // columns each).  tcgen05.mma issue costs the single issuing thread ~50-66 cycles per
 // instruction plus ~500 cycles of barrier/commit latency per ring stage (measured with the
 // clock64 instrumentation, profiles/r01_swap_modes.txt), which is MORE than the tensor time of
 // an N <= 128 instruction (64 cycles): two CTAs give the SM's tensor pipe two issuing threads.
 template <int KSTEPS, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
+__global__ void __launch_bounds__(kThreads1, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -391,7 +464,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
+      mbar_init(tfull_bar(a), p.issuers);
       mbar_init(tempty_bar(a), kEpiWarps);
       mbar_init(pfull_bar(a), 1);
       mbar_init(pempty_bar(a), 1);
@@ -414,7 +487,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp >= 2 && cpad) {
     // Stage the per-channel epilogue parameters once per CTA.
     float* sp = reinterpret_cast<float*>(smem_raw + (params_s - smem_u32(smem_raw)));
-    for (int i = threadIdx.x - 64; i < cpad; i += kThreads - 64) {
+    for (int i = threadIdx.x - 64; i < cpad; i += kThreads1 - 64) {
       sp[i] = p.scale[i];
       sp[cpad + i] = p.shift[i];
       sp[2 * cpad + i] = p.slope ? p.slope[i] : 0.f;
@@ -559,6 +632,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if ((p.debug & 32) && blockIdx.x == 0 && lane == 0)
       printf("producer: total %lld clk, %d iters, wait(empty) %lld, wait(patch empty) %lld\n",
              clock64() - dbg_t0, dbg_iters, dbg_wait, dbg_pwait);
+  } else if (warp == 10 && p.issuers == 2) {
+    // ------------------------------------------------- second MMA issuer (odd ring stages)
+    mma_issuer_alternate<KSTEPS>(p, 1, ring, tmem_base, bars);
+  } else if (warp == 10) {
+    // single-issuer launch: nothing to do
+  } else if (warp == 1 && p.issuers == 2) {
+    mma_issuer_alternate<KSTEPS>(p, 0, ring, tmem_base, bars);
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     int stage = 0, pb = 0;
@@ -690,11 +770,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     e.cpad = cpad;
     e.sp = reinterpret_cast<const float*>(smem_raw + (params_s - smem_u32(smem_raw)));
     int tile_it = 0;
+    int g_it = 0;                               // global iteration counter (two-issuer accounting)
     TileWalk walk = walk_begin(p);
     int tile, it0, it1;
     for (; walk_next(p, walk, tile, it0, it1); ++tile_it) {
       const int acc = tile_it & 1;
       const uint32_t acc_phase = (tile_it >> 1) & 1u;
+      // two issuers: the segment's first iteration went to issuer (g & 1); the other one has a
+      // partial accumulator too iff the segment has at least two iterations
+      const int first_w = g_it & 1;
+      const bool both = p.issuers == 2 && it1 - it0 >= 2;
+      g_it += it1 - it0;
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
       const int wb = mt % p.tiles_w; mt /= p.tiles_w;
@@ -717,18 +803,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.acc_cols;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.acc_cols +
+                             (p.issuers == 2 ? first_w * p.N_tile : 0);
+      const uint32_t taddr2 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.acc_cols +
+                              (first_w ^ 1) * p.N_tile;           // the other issuer's accumulator
       const int cn0 = nt * p.N_tile;
       uint32_t va[16], vb[16];
       int c = half;
+      // two issuers: v = chunk of issuer A (+ chunk of issuer B), synchronous
+      auto load_sum = [&](uint32_t (&v)[16], int chunk) {
+        __syncwarp();
+        tmem_ld16_async(taddr + chunk * 16, v);
+        if (both) {
+          uint32_t t2[16];
+          tmem_ld16_async(taddr2 + chunk * 16, t2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t2[j]));
+        } else {
+          tmem_ld_wait();
+        }
+      };
       if (it0 > 0) {
         // TAIL of a tile whose first iterations belong to the previous CTA: park the raw
         // accumulators, laid out [chunk][row][16] so that a warp writes 2 KB runs.
         float4* ws = reinterpret_cast<float4*>(p.sk_ws + static_cast<size_t>(blockIdx.x) * 128 * p.N_tile);
         for (; c < nchunks; c += 2) {
-          __syncwarp();
-          tmem_ld16_async(taddr + c * 16, va);
-          tmem_ld_wait();
+          load_sum(va, c);
           float4* dst = ws + (c * 128 + row) * 4;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -776,6 +877,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + f.w);
         }
       };
+      if (p.issuers == 2) {
+        for (; c < nchunks; c += 2) {
+          load_sum(va, c);
+          add_partial(va, c);
+          if (p.swap) epilogue_chunk_swap(p, e.sp, cpad, va, sw_cout, st, c * 16);
+          else epilogue_chunk(p, e, va, cn0 + c * 16);
+        }
+      }
       // software-pipelined TMEM reads: chunk i+2 is in flight while chunk i is stored
       __syncwarp();
       if (c < nchunks) tmem_ld16_async(taddr + c * 16, va);
@@ -1320,7 +1429,14 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     // that three stages fit in half of the SM's shared memory.
     int want = 1;                                   // 0 off, 1 auto, 2 whenever possible
     if (const char* e = getenv("TRB_TC_CTAS")) want = atoi(e);
-    const bool ok = !p.halo && !p.cta2 && !p.swap && p.N_tile <= 128 && 3 * p.sub_bytes <= 100 * 1024;
+    // (two issuing warps in ONE CTA keep full-size ring stages and measured faster — 53.7 vs
+    // 66.4 us on the 7x7 128->128 layer — but need all 512 TMEM columns at N = 128: exclusive)
+    int want_issuers = 0;
+    if (const char* e = getenv("TRB_TC_ISSUERS")) want_issuers = atoi(e);
+    const bool two_issuers = want_issuers && !p.halo && !p.cta2 && p.N_tile <= 128 &&
+                             ceil_div(p.k_blocks, p.sub) >= (want_issuers == 2 ? 2 : 4);
+    const bool ok = !two_issuers && !p.halo && !p.cta2 && !p.swap && p.N_tile <= 128 &&
+                    3 * p.sub_bytes <= 100 * 1024;
     const bool worth = p.k_blocks >= 8 && p.total_tiles >= num_sms() + num_sms() / 2;
     if (ok && (want == 2 || (want == 1 && worth))) {
       plan->ctas_per_sm = 2;
@@ -1329,6 +1445,16 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   }
   if (const char* s = getenv("TRB_TC_SUB")) p.sub = clamp_sub(atoi(s));
   p.iters = ceil_div(p.k_blocks, p.sub);
+  {
+    // Default OFF: measured 12-22 % faster on the N = 128 long-K layers (7x7 128->128: 60.7 vs
+    // 68.8 us; OpenPose net 4.53 vs 4.70 ms) and bit-reproducible, but ArcFace's many-tile
+    // stride-2 128-filter layer (56x56 -> 28x28, batch 256) faults with it and the cause is not
+    // found yet (profiles/r01_two_issuers.txt).  Opt-in for the next round.
+    int want = 0;                                   // 0 one issuer, 1 auto, 2 whenever possible
+    if (const char* e = getenv("TRB_TC_ISSUERS")) want = atoi(e);
+    const bool ok = !p.halo && !p.cta2 && p.iters >= 2 && p.N_tile <= 128;   // 4 accumulators in 512 TMEM columns
+    p.issuers = ok && (want == 2 || (want == 1 && p.iters >= 4)) ? 2 : 1;
+  }
   p.iters_kc = ceil_div(p.taps, p.sub);
   p.stage_bytes = p.sub * p.sub_bytes;
   const uint32_t param_bytes = 5u * p.cout_pad * 4u;
@@ -1348,7 +1474,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   else { p.layout_type = 6; swz = CU_TENSOR_MAP_SWIZZLE_32B; }
   // kind::f16 instruction descriptor: D=f32, A=B=f16, K-major, N>>3, M>>4.
   p.idesc = (1u << 4) | (uint32_t(p.N_tile >> 3) << 17) | (uint32_t(128 >> 4) << 24);
-  p.acc_cols = p.swap ? 256 : p.N_tile;
+  p.acc_cols = p.issuers == 2 ? 2 * p.N_tile : p.swap ? 256 : p.N_tile;
   uint32_t cols = 32;
   while (cols < uint32_t(2 * p.acc_cols)) cols <<= 1;
   p.tmem_cols = cols;
@@ -1406,7 +1532,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   plan->grid = p.cta2 ? 2 * std::min(p.pair_units, num_sms() / 2)
                       : std::min(p.total_tiles, plan->ctas_per_sm * num_sms());
   plan->smem = p.ring_off + p.stages * p.stage_bytes + param_bytes + 1024 /*alignment*/ +
-               256 /*tap table*/ + 8 * (2 * kMaxStages + 10) + 16;
+               256 /*tap table*/ + 8 * (2 * kMaxStages + 12) + 16;
   {
     // Stream-K where whole-tile scheduling leaves SMs idle in the last round.  Measured
     // (profiles/r01_stream_k.txt): the partial-tile hand-over costs ~8 us per launch with
@@ -1471,7 +1597,7 @@ void conv_tc_launch(const ConvTcPlan* plan, cudaStream_t s) {
   static const bool pdl = [] { const char* e = getenv("TRB_TC_PDL"); return !e || atoi(e) != 0; }();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(plan->grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kThreads1);
   cfg.dynamicSmemBytes = plan->smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
