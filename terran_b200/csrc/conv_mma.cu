@@ -26,6 +26,10 @@ namespace trb {
 
 namespace {
 
+#ifndef TRB_MMA_SMALL_CTAS
+#define TRB_MMA_SMALL_CTAS 2   /* 3 measured slower (profiles/r01_retinaface_mma.txt) */
+#endif
+
 enum { MODE_DENSE1 = 0, MODE_DENSE3 = 1, MODE_SEP1 = 2, MODE_SEP2 = 3 };
 
 struct MmaParams {
@@ -65,7 +69,9 @@ struct Geo {
   static constexpr int PAR_FLOATS = 2 * COUT + (SEP ? ((2 * CIN + (9 * CIN + 1) / 2 + 3) & ~3) : 0);
   static constexpr size_t SMEM = size_t(COUT) * WP * 2 + size_t(PAR_FLOATS) * 4 + size_t(WARPS) * WARP_HALFS * 2;
   // Two resident CTAs (16 warps) per SM where shared memory allows: caps registers at 128.
-  static constexpr int MIN_CTAS = (WARPS == 8 && SMEM <= 110 * 1024) ? 2 : 1;
+  // (3 resident CTAs for the small-channel fused layers were measured slower than 2)
+  static constexpr int MIN_CTAS = (SEP && CIN <= 32 && SMEM <= 72 * 1024) ? TRB_MMA_SMALL_CTAS
+                                  : (WARPS == 8 && SMEM <= 110 * 1024) ? 2 : 1;
 };
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
