@@ -1,2 +1,2 @@
-for i in 1 0; do echo "== arcface layers TRB_TC_ISSUERS=$i"; TRB_TC_ISSUERS=$i python scripts/arcface_layers.py; done
-for i in 1 0 1 0; do echo "== net TRB_TC_ISSUERS=$i"; TRB_TC_ISSUERS=$i python scripts/profile_ops.py openpose arcface retinaface --brief | grep -E "^==|k7|tcgen05"; done
+for c in 1024 512; do echo "== TRB_TC_STAGE_CYCLES=$c"; TRB_TC_STAGE_CYCLES=$c python scripts/bench_conv.py; done
+for c in 1024 512 1024 512; do echo "== net TRB_TC_STAGE_CYCLES=$c"; TRB_TC_STAGE_CYCLES=$c python scripts/profile_ops.py openpose arcface retinaface --brief | grep -E "^==|tcgen05"; done

@@ -79,6 +79,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a);
 void conv_tc_plan_destroy(ConvTcPlan* p);
 void conv_tc_launch(const ConvTcPlan* p, cudaStream_t s);
 double conv_tc_plan_flops(const ConvTcPlan* p);
+int conv_tc_last_timeout();   // pipeline wait that timed out before a trap (0 = none)
 
 // conv_direct.cu
 void conv_direct_launch(const ConvArgs& a, cudaStream_t s);

@@ -1227,11 +1227,15 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
+// Pipeline-timeout code written by a trapping kernel.  Mapped pinned host memory: the host can
+// still read it after the trap has killed the context (device allocations are gone by then).
+int* g_err_host = nullptr;
 int* tc_error_flag() {
   static int* flag = nullptr;
   if (!flag) {
-    TR_CUDA(cudaMalloc(&flag, sizeof(int)));
-    TR_CUDA(cudaMemset(flag, 0, sizeof(int)));
+    TR_CUDA(cudaHostAlloc(&g_err_host, sizeof(int), cudaHostAllocMapped));
+    *g_err_host = 0;
+    TR_CUDA(cudaHostGetDevicePointer(&flag, g_err_host, 0));
   }
   return flag;
 }
@@ -1423,7 +1427,14 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   const int mma_cycles = (p.KC / 16) * std::max(p.N_tile / 2, 8);     // per k-block
   const int k_per_group = p.halo ? p.taps : p.k_blocks;
   auto clamp_sub = [&](int v) { return std::max(1, std::min(std::min(kMaxSub, v), k_per_group)); };
-  p.sub = clamp_sub(std::min(ceil_div(512, mma_cycles), int(65536 / p.sub_bytes)));
+  // A stage carries ~1024 cycles of tensor work within 96 KB (two stages still fit): the
+  // issuing thread's per-stage cost (~500-600 cycles, lesson 5) is amortised over more MMAs.
+  // Measured against the 512-cycle / 64 KB rule (profiles/r01_stage_size.txt): N = 256 layers
+  // +2.5..5 %, halo layers at 92x163 +10..13 %, nothing slower.
+  int stage_cycles = 1024;
+  if (const char* e = getenv("TRB_TC_STAGE_CYCLES")) stage_cycles = atoi(e);
+  const int stage_cap = stage_cycles > 512 ? 98304 : 65536;
+  p.sub = clamp_sub(std::min(ceil_div(stage_cycles, mma_cycles), int(stage_cap / p.sub_bytes)));
   {
     // Two CTAs per SM for narrow filter tiles (see conv_tc_kernel): one k-block per stage so
     // that three stages fit in half of the SM's shared memory.
@@ -1444,6 +1455,12 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     }
   }
   if (const char* s = getenv("TRB_TC_SUB")) p.sub = clamp_sub(atoi(s));
+  {
+    // two stages (+ the halo patches, parameters, barriers) must fit in the SM's 227 KB
+    const uint32_t patches = p.halo ? 2 * round_up(((p.swap ? p.bw : 16) + 2 * a.pad) * 16 * 128, 1024) : 0;
+    const uint32_t limit = plan->ctas_per_sm == 2 ? 108u * 1024 : 224u * 1024;
+    while (p.sub > 1 && patches + 2u * p.sub * p.sub_bytes + 5u * p.cout_pad * 4u + 2048u > limit) --p.sub;
+  }
   p.iters = ceil_div(p.k_blocks, p.sub);
   {
     // Default OFF: measured 12-22 % faster on the N = 128 long-K layers (7x7 128->128: 60.7 vs
@@ -1568,6 +1585,10 @@ void conv_tc_plan_destroy(ConvTcPlan* p) {
 }
 
 double conv_tc_plan_flops(const ConvTcPlan* p) { return p->flops; }
+
+// 0, or the code of the mbarrier wait that timed out (1 ring empty, 2 tmem empty, 3 ring full,
+// 4 tmem full, 5 patch empty, 6 patch full, 9 stream-K partial) in a kernel that then trapped.
+int conv_tc_last_timeout() { return g_err_host ? *reinterpret_cast<volatile int*>(g_err_host) : 0; }
 
 void conv_tc_launch(const ConvTcPlan* plan, cudaStream_t s) {
   if (plan->p.cta2) {

@@ -557,7 +557,9 @@ int tr_conv2d(const void* in_dev, int N, int H, int W, int in_cs, int in_coff, i
     TR_CUDA(cudaEventRecord(e1, s));
     cudaError_t err = cudaStreamSynchronize(s);
     if (plan) conv_tc_plan_destroy(plan);
-    TR_CUDA(err);
+    if (err != cudaSuccess)
+      fail(std::string("conv launch failed: ") + cudaGetErrorString(err) + " (pipeline timeout code " +
+           std::to_string(conv_tc_last_timeout()) + ")");
     float t = 0.f;
     TR_CUDA(cudaEventElapsedTime(&t, e0, e1));
     cudaEventDestroy(e0);
