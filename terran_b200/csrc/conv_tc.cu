@@ -370,7 +370,9 @@ __device__ __forceinline__ void epilogue_chunk_swap(const TcParams& p, const flo
 // an issuer without work in a (one-iteration) segment arrives plainly.
 template <int KSTEPS>
 __device__ __forceinline__ void mma_issuer_alternate(const TcParams& p, int w, uint32_t ring,
-                                                     uint32_t tmem_base, uint32_t bars) {
+                                                     uint32_t tmem_base, uint32_t bars, int* prog) {
+  const int lane_id = threadIdx.x & 31;
+  int mine = 0;                                  // my full-barrier waits that have passed
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + a); };
@@ -389,6 +391,7 @@ __device__ __forceinline__ void mma_issuer_alternate(const TcParams& p, int w, u
     const uint32_t acc_phase = (tile_it >> 1) & 1u;
     const int n_it = it1 - it0;
     const int first = ((g & 1) == w) ? 0 : 1;   // my first iteration within the segment
+    const int gstart = g;
     g += n_it;
     mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);   // (also: never lap the previous use)
     if (first >= n_it) {                         // a one-iteration segment owned by the other issuer
@@ -399,8 +402,31 @@ __device__ __forceinline__ void mma_issuer_alternate(const TcParams& p, int w, u
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t d_tmem = tmem_base + acc * p.acc_cols + w * p.N_tile;
     for (int i = first; i < n_it; i += 2) {
+      const int gi = gstart + i;                 // global iteration index (ring position)
       const int nsub = min(p.sub, p.k_blocks - (it0 + i) * p.sub);
+      // With an odd number of stages a stage changes owner every ring cycle: the stage's
+      // previous phase (global iteration gi - stages) belongs to the OTHER issuer.  If that one
+      // has not seen its data yet, the barrier is still one phase behind and a parity wait for
+      // this phase would pass spuriously.  Each issuer therefore publishes how many of its
+      // full-barrier waits have passed, and waits for the other's count where it matters.
+      if ((p.stages & 1) && gi >= p.stages) {
+        const int need = (gi - p.stages - (w ^ 1)) / 2 + 1;       // the other's iteration ordinal
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile int*>(prog + (w ^ 1)) < need) {
+          if (clock64() - t0 > 4000000000LL) {
+            if (p.err) atomicExch(p.err, 8);
+            __threadfence_system();
+            __trap();
+          }
+        }
+        __threadfence_block();
+      }
       mbar_wait(full_bar(stage), phase, p.err, 3);
+      if (p.stages & 1) {
+        __threadfence_block();
+        if (lane_id == 0) *reinterpret_cast<volatile int*>(prog + w) = ++mine;
+        else ++mine;
+      }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
         uint32_t a_lo = a_lo0 + stage * stage_step;
@@ -452,6 +478,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
   auto pfull_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 6 + b); };
   auto pempty_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 8 + b); };
+  // two-issuer progress words (see mma_issuer_alternate)
+  int* prog = reinterpret_cast<int*>(smem_raw + (bars + 8u * (2 * kMaxStages + 10) - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -469,6 +497,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(pfull_bar(a), 1);
       mbar_init(pempty_bar(a), 1);
     }
+    prog[0] = 0; prog[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -634,11 +663,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
              clock64() - dbg_t0, dbg_iters, dbg_wait, dbg_pwait);
   } else if (warp == 10 && p.issuers == 2) {
     // ------------------------------------------------- second MMA issuer (odd ring stages)
-    mma_issuer_alternate<KSTEPS>(p, 1, ring, tmem_base, bars);
+    mma_issuer_alternate<KSTEPS>(p, 1, ring, tmem_base, bars, prog);
   } else if (warp == 10) {
     // single-issuer launch: nothing to do
   } else if (warp == 1 && p.issuers == 2) {
-    mma_issuer_alternate<KSTEPS>(p, 0, ring, tmem_base, bars);
+    mma_issuer_alternate<KSTEPS>(p, 0, ring, tmem_base, bars, prog);
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     int stage = 0, pb = 0;
@@ -1442,7 +1471,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     if (const char* e = getenv("TRB_TC_CTAS")) want = atoi(e);
     // (two issuing warps in ONE CTA keep full-size ring stages and measured faster — 53.7 vs
     // 66.4 us on the 7x7 128->128 layer — but need all 512 TMEM columns at N = 128: exclusive)
-    int want_issuers = 0;
+    int want_issuers = 1;
     if (const char* e = getenv("TRB_TC_ISSUERS")) want_issuers = atoi(e);
     const bool two_issuers = want_issuers && !p.halo && !p.cta2 && p.N_tile <= 128 &&
                              ceil_div(p.k_blocks, p.sub) >= (want_issuers == 2 ? 2 : 4);
@@ -1453,6 +1482,8 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
       plan->ctas_per_sm = 2;
       p.sub = 1;
     }
+    // two issuers own alternate stages: keep at least three of them (<= 64 KB each)
+    if (two_issuers) p.sub = clamp_sub(std::min(p.sub, int(65536 / p.sub_bytes)));
   }
   if (const char* s = getenv("TRB_TC_SUB")) p.sub = clamp_sub(atoi(s));
   {
@@ -1463,13 +1494,16 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   }
   p.iters = ceil_div(p.k_blocks, p.sub);
   {
-    // Default OFF: measured 12-22 % faster on the N = 128 long-K layers (7x7 128->128: 60.7 vs
-    // 68.8 us; OpenPose net 4.53 vs 4.70 ms) and bit-reproducible, but ArcFace's many-tile
-    // stride-2 128-filter layer (56x56 -> 28x28, batch 256) faults with it and the cause is not
-    // found yet (profiles/r01_two_issuers.txt).  Opt-in for the next round.
-    int want = 0;                                   // 0 one issuer, 1 auto, 2 whenever possible
+    // Measured (profiles/r01_two_issuers.txt): N = 128 long-K layers 12-22 % faster (7x7 128->128
+    // 68.8 -> 60.7 us), OpenPose forward 4.70 -> 4.47 ms, ArcFace 10.4 -> 9.7 ms, bit-reproducible.
+    // Two hazards found and closed on the way: (1) combined with two CTAs per SM each CTA wanted
+    // all 512 TMEM columns (now exclusive); (2) with an odd stage count a stage changes owner
+    // every ring cycle and a parity wait passes spuriously when the other issuer lags a whole
+    // phase (now ordered by the progress words in mma_issuer_alternate).
+    int want = 1;                                   // 0 one issuer, 1 auto, 2 whenever possible
     if (const char* e = getenv("TRB_TC_ISSUERS")) want = atoi(e);
-    const bool ok = !p.halo && !p.cta2 && p.iters >= 2 && p.N_tile <= 128;   // 4 accumulators in 512 TMEM columns
+    const bool ok = !p.halo && !p.cta2 && p.iters >= 2 && p.N_tile <= 128 &&   // 4 accumulators in 512 TMEM columns,
+                    plan->ctas_per_sm == 1;                                     // which one CTA per SM can have
     p.issuers = ok && (want == 2 || (want == 1 && p.iters >= 4)) ? 2 : 1;
   }
   p.iters_kc = ceil_div(p.taps, p.sub);
