@@ -1,0 +1,83 @@
+"""CPU: the layer programs emitted by ``terran_b200/weights.py`` — executed by the torch
+interpreter in ``tests/program_interpreter.py`` exactly as the C ABI specifies the ops — agree
+with the oracle's restatement of the reference ``nn.Module`` graphs.  This pins the whole
+weight-ingestion path (checkpoint key layout, BN folding, filter re-indexing, fused heads,
+depthwise+1x1 pairing, concat-free channel slices) without a GPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets
+from terran_b200 import synth, weights
+from tests.program_interpreter import Interpreter
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+
+
+@pytest.mark.parametrize('fused', [True, False], ids=['fused', 'unfused'])
+def test_retinaface_program_matches_oracle(fused):
+    """retinaface/model.py:53-341 vs the 13 TR_OP_SEPCONV (or 13 + 13 unfused) backbone ops,
+    the FPN with up-sampled residuals, the context slices and the fused fp32 heads."""
+    sd = synth.retinaface_state_dict()
+    P, roles = weights.retinaface_program(sd, fused=fused)
+    rng = np.random.default_rng(0)
+    img = torch.from_numpy(rng.integers(0, 256, (2, 64, 96, 3), dtype=np.uint8))     # model order (BGR)
+    bufs = Interpreter(P, round_activations=False).run(img)
+    want = nets.retinaface_forward(sd, img.float().permute(0, 3, 1, 2))
+    for li, head in enumerate(roles['heads']):                                      # s32, s16, s8
+        got = bufs[head].permute(0, 3, 1, 2)                                        # (N, 32, h, w)
+        prob, bbox, lmk = want[3 * li:3 * li + 3]
+        assert got.shape[2:] == bbox.shape[2:]
+        # fp16-rounded weights, fp32 activations: a few 1e-3 of the tensor's scale
+        assert _rel(got[:, 4:12], bbox) < 5e-3
+        assert _rel(got[:, 12:32], lmk) < 5e-3
+        n, a, h, w = got[:, :4].shape
+        p = torch.softmax(got[:, :4].reshape(n, 2, -1, w), dim=1).reshape(n, a, h, w)
+        assert (p - prob).abs().max() < 2e-2                                        # class gain x30 in the synthetic heads
+
+
+def test_retinaface_fused_and_unfused_programs_agree():
+    sd = synth.retinaface_state_dict()
+    rng = np.random.default_rng(1)
+    img = torch.from_numpy(rng.integers(0, 256, (1, 70, 90, 3), dtype=np.uint8))
+    outs = []
+    for fused in (True, False):
+        P, roles = weights.retinaface_program(sd, fused=fused)
+        bufs = Interpreter(P).run(img)                 # fp16 activations like the kernels
+        outs.append([bufs[h] for h in roles['heads']])
+    for a, b in zip(*outs):
+        # same arithmetic except the depthwise filters (fp16 copy in the fused kernel)
+        assert _rel(a[..., 4:], b[..., 4:]) < 5e-3
+
+
+def test_openpose_program_matches_oracle():
+    """openpose/model.py:27-141: merged first layers of the two branches, concat written in
+    place into the 192-channel buffer [PAF | pad | heat | pad | trunk], re-indexed 7x7 filters."""
+    sd = synth.openpose_state_dict()
+    P, roles = weights.openpose_program(sd)
+    rng = np.random.default_rng(2)
+    img = torch.from_numpy(rng.integers(0, 256, (1, 48, 64, 3), dtype=np.uint8))     # RGB as stored
+    bufs = Interpreter(P, round_activations=False).run(img)
+    x = img.float().permute(0, 3, 1, 2) / 255.0 - 0.5
+    paf, heat = nets.openpose_forward(sd, x)
+    maps = bufs[roles['maps']].permute(0, 3, 1, 2)
+    assert _rel(maps[:, roles['paf_coff']:roles['paf_coff'] + 38], paf) < 5e-3
+    assert _rel(maps[:, roles['heat_coff']:roles['heat_coff'] + 19], heat) < 5e-3
+
+
+def test_arcface_program_matches_oracle():
+    """arcface/model.py:4-97 at reduced depth: input affine on in-bounds taps, pre-conv BN
+    carried as the producer's second output, shortcut convs, BN2d folded into the permuted FC."""
+    units = (1, 2, 1, 1)
+    sd = synth.arcface_state_dict(units=units)
+    P, roles = weights.arcface_program(sd, units=units)
+    rng = np.random.default_rng(3)
+    img = torch.from_numpy(rng.integers(0, 256, (2, 112, 112, 3), dtype=np.uint8))   # model order (BGR)
+    bufs = Interpreter(P, round_activations=False).run(img)
+    want = nets.arcface_forward(sd, img.float().permute(0, 3, 1, 2), units=units)
+    got = bufs[roles['embedding']].reshape(2, 512)
+    cos = torch.nn.functional.cosine_similarity(got, want, dim=1)
+    assert (cos > 0.9999).all(), cos
+    assert _rel(got, want) < 5e-3
