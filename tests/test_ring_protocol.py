@@ -113,3 +113,145 @@ def test_odd_stage_count_without_progress_words_reproduces_the_hazard():
     """The fault seen on the GPU: a parity wait passing one phase early."""
     bad = [simulate(3, 40, seed, progress_words=False) for seed in range(300)]
     assert any(b is not None for b in bad)
+
+
+def simulate_segments(stages, segments, seed, max_steps=400000):
+    """The whole two-issuer pipeline: ring + double-buffered accumulators handed to the
+    epilogue (``tmem_full`` with two arrivals per use, ``tmem_empty`` released by the epilogue;
+    an issuer without work in a one-iteration segment arrives plainly after its tmem_empty
+    wait).  ``segments`` = iterations per (tile, stream-K range).  Checks that the epilogue
+    reads an accumulator only when every MMA of the segment has retired, that no MMA touches an
+    accumulator the epilogue has not released, and that each issuer's first MMA of a segment
+    overwrites (accumulate = 0) while the others accumulate."""
+    rng = random.Random(seed)
+    total = sum(segments)
+    full = [MBarrier() for _ in range(stages)]
+    empty = [MBarrier() for _ in range(stages)]
+    tfull = [MBarrier(2), MBarrier(2)]
+    tempty = [MBarrier(1), MBarrier(1)]
+    content = [None] * stages
+    prog = [0, 0]
+    events = []
+    # accumulator model: per (buffer, issuer) the set of iterations summed so far; owner flag
+    acc_sum = [[set(), set()], [set(), set()]]
+    acc_busy = [False, False]                # True while the epilogue reads the buffer
+    retired = set()                          # iterations whose MMAs have completed
+    done_segments = []
+
+    def producer():
+        for g in range(total):
+            s, ph = g % stages, (g // stages) & 1
+            while not empty[s].test_wait(ph ^ 1):
+                yield
+            events.append(('land', (s, g)))
+            yield
+
+    def issuer(w):
+        mine, g0 = 0, 0
+        for t, n_it in enumerate(segments):
+            a, aph = t & 1, (t >> 1) & 1
+            first = 0 if (g0 & 1) == w else 1
+            while not tempty[a].test_wait(aph ^ 1):
+                yield
+            if first >= n_it:
+                tfull[a].arrive()                     # plain arrive: no work in this segment
+                g0 += n_it
+                yield
+                continue
+            last = None
+            for i in range(first, n_it, 2):
+                g = g0 + i
+                s, ph = g % stages, (g // stages) & 1
+                if (stages & 1) and g >= stages:
+                    need = (g - stages - (w ^ 1)) // 2 + 1
+                    while prog[w ^ 1] < need:
+                        yield
+                while not full[s].test_wait(ph):
+                    yield
+                mine += 1
+                prog[w] = mine
+                if content[s] != g:
+                    raise Violation(f'issuer {w} consumed stage {s} holding {content[s]} at iteration {g}')
+                if acc_busy[a]:
+                    raise Violation(f'issuer {w} wrote accumulator {a} while the epilogue reads it')
+                if i == first:
+                    acc_sum[a][w] = {g}               # accumulate = 0
+                else:
+                    acc_sum[a][w].add(g)
+                yield
+                events.append(('commit', (s, g)))
+                last = g
+            events.append(('tfull', (a, last, w)))    # commit(tmem_full) after my last MMA
+            g0 += n_it
+            yield
+
+    def epilogue():
+        g0 = 0
+        for t, n_it in enumerate(segments):
+            a, aph = t & 1, (t >> 1) & 1
+            while not tfull[a].test_wait(aph):
+                yield
+            acc_busy[a] = True
+            first_w = g0 & 1
+            both = n_it >= 2
+            got = set(acc_sum[a][first_w]) | (set(acc_sum[a][first_w ^ 1]) if both else set())
+            want = set(range(g0, g0 + n_it))
+            if got != want:
+                raise Violation(f'segment {t}: epilogue read {sorted(got)} instead of {sorted(want)}')
+            if not want <= retired:
+                raise Violation(f'segment {t}: epilogue started before MMAs {sorted(want - retired)} retired')
+            yield
+            acc_busy[a] = False
+            tempty[a].arrive()
+            done_segments.append(t)
+            g0 += n_it
+            yield
+
+    actors = {'producer': producer(), 'issuer0': issuer(0), 'issuer1': issuer(1), 'epilogue': epilogue()}
+    try:
+        for _ in range(max_steps):
+            choices = list(actors) + ['event'] * min(len(events), 2)
+            if not choices:
+                return None if len(done_segments) == len(segments) else 'stopped early'
+            pick = rng.choice(choices)
+            if pick == 'event':
+                # tensor-pipe completions of ONE issuing thread retire in its issue order
+                idx = rng.randrange(len(events))
+                kind, payload = events[idx]
+                if kind != 'land':
+                    w = payload[1] & 1 if kind == 'commit' else payload[2]
+                    idx = next(i for i, (k, pl) in enumerate(events)
+                               if (k == 'commit' and (pl[1] & 1) == w) or (k == 'tfull' and pl[2] == w))
+                    kind, payload = events[idx]
+                events.pop(idx)
+                if kind == 'land':
+                    s, g = payload
+                    content[s] = g
+                    full[s].arrive()
+                elif kind == 'commit':
+                    s, g = payload
+                    retired.add(g)
+                    content[s] = None
+                    empty[s].arrive()
+                else:
+                    tfull[payload[0]].arrive()
+                continue
+            try:
+                next(actors[pick])
+            except StopIteration:
+                del actors[pick]
+        return 'no progress (deadlock or live-lock)'
+    except Violation as v:
+        return str(v)
+
+
+@pytest.mark.parametrize('stages', [2, 3, 4])
+def test_two_issuer_pipeline_with_accumulator_handover(stages):
+    shapes = [[9] * 6, [5, 5, 5, 5], [1, 9, 1, 2, 3, 1, 1, 7], [4, 9, 9, 5], [2] * 9, [1] * 7]
+    for segments in shapes:
+        for seed in range(60):
+            assert simulate_segments(stages, segments, seed) is None, (stages, segments, seed)
+    rng = random.Random(7)
+    for seed in range(120):
+        segments = [rng.randint(1, 11) for _ in range(rng.randint(3, 9))]
+        assert simulate_segments(stages, segments, seed) is None, (stages, segments, seed)
