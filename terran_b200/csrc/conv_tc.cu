@@ -453,6 +453,118 @@ __device__ __forceinline__ void mma_issuer_alternate(const TcParams& p, int w, u
   }
 }
 
+// The halo-mode counterpart of mma_issuer_alternate: the A (or, in swap mode, B) operand of
+// every tap is a shifted window of the resident patch, the ring carries filter blocks only.
+// A tile is kchunks chunk-steps of iters_kc ring iterations; issuer `w` owns every other GLOBAL
+// iteration.  Both issuers wait for the step's patch (pfull, non-consuming) and BOTH release it
+// (pempty is initialised with count 2; an issuer without an iteration in a step arrives plainly
+// after its pfull wait, so it can never lap the patch's previous use).
+template <int KSTEPS>
+__device__ __forceinline__ void mma_issuer_alternate_halo(const TcParams& p, int w, uint32_t base,
+                                                          uint32_t ring, uint32_t tmem_base,
+                                                          uint32_t bars, uint32_t tab_s, int* prog) {
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + 2 + a); };
+  auto pfull_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 6 + b); };
+  auto pempty_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 8 + b); };
+  const int lane_id = threadIdx.x & 31;
+  const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
+  const uint32_t halo_hi = umma_desc_hi(2048, p.layout_type);
+  const uint32_t a_lo0 = umma_desc_lo(ring);
+  const uint32_t stage_step = p.stage_bytes >> 4;
+  int stage = w % p.stages;
+  uint32_t phase = (w / p.stages) & 1u;
+  int mine = 0, g = 0, q = 0, tile_it = 0;       // g: global ring iteration, q: global chunk-step
+  const int n_tile = p.kchunks * p.iters_kc;     // ring iterations per tile
+  TileWalk walk = walk_begin(p);
+  int tile, it0, it1;
+  for (; walk_next(p, walk, tile, it0, it1); ++tile_it) {
+    const int acc = tile_it & 1;
+    const uint32_t acc_phase = (tile_it >> 1) & 1u;
+    const int first_tile = ((g & 1) == w) ? 0 : 1;
+    mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 2);
+    if (first_tile >= n_tile) {                   // a one-iteration tile owned by the other issuer
+      mbar_wait(pfull_bar(q & 1), (q >> 1) & 1u, p.err, 6);
+      if (elect_one()) { mbar_arrive(pempty_bar(q & 1)); mbar_arrive(tfull_bar(acc)); }
+      __syncwarp();
+      g += n_tile; q += p.kchunks;
+      continue;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t d_tmem = tmem_base + acc * p.acc_cols + w * p.N_tile;
+    const int g_tile = g;
+    int last_mine = -1;                           // my last iteration index within the tile
+    for (int i = first_tile; i < n_tile; i += 2) last_mine = i;
+    bool started = false;
+    for (int kc = 0; kc < p.kchunks; ++kc, ++q) {
+      const int pb = q & 1;
+      mbar_wait(pfull_bar(pb), (q >> 1) & 1u, p.err, 6);
+      const uint32_t patch_lo = umma_desc_lo(base + pb * p.patch_bytes);
+      const int gq = g_tile + kc * p.iters_kc;    // global index of the step's first iteration
+      const int first = ((gq & 1) == w) ? 0 : 1;
+      int last_step = -1;
+      for (int it = first; it < p.iters_kc; it += 2) last_step = it;
+      if (last_step < 0) {                        // no iteration of mine in this step
+        if (elect_one()) mbar_arrive(pempty_bar(pb));
+        __syncwarp();
+        continue;
+      }
+      for (int it = first; it < p.iters_kc; it += 2) {
+        const int gi = gq + it;
+        const int tap = it * p.sub;
+        const int nsub = min(p.sub, p.taps - tap);
+        if ((p.stages & 1) && gi >= p.stages) {   // see mma_issuer_alternate
+          const int need = (gi - p.stages - (w ^ 1)) / 2 + 1;
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile int*>(prog + (w ^ 1)) < need) {
+            if (clock64() - t0 > 4000000000LL) {
+              if (p.err) atomicExch(p.err, 8);
+              __threadfence_system();
+              __trap();
+            }
+          }
+          __threadfence_block();
+        }
+        mbar_wait(full_bar(stage), phase, p.err, 3);
+        if (p.stages & 1) {
+          __threadfence_block();
+          if (lane_id == 0) *reinterpret_cast<volatile int*>(prog + w) = ++mine;
+          else ++mine;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t b_lo0 = a_lo0 + stage * stage_step;
+          uint32_t accumulate = started ? 1u : 0u;
+          for (int j = 0; j < nsub; ++j) {
+            uint32_t tap_off;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tap_off) : "r"(tab_s + 4u * (tap + j)));
+            const uint32_t a_lo = patch_lo + tap_off;
+            const uint32_t b_lo = b_lo0 + j * (p.b_bytes >> 4);
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+              if (p.swap)
+                umma_f16(d_tmem, b_lo + 2 * k, desc_hi, a_lo + 2 * k, halo_hi, p.idesc, accumulate);
+              else
+                umma_f16(d_tmem, a_lo + 2 * k, halo_hi, b_lo + 2 * k, desc_hi, p.idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(empty_bar(stage));
+          if (it == last_step) umma_commit(pempty_bar(pb));
+          if (kc * p.iters_kc + it == last_mine) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        started = true;
+        stage += 2;
+        if (stage >= p.stages) { stage -= p.stages; phase ^= 1u; }
+      }
+    }
+    g += n_tile;
+  }
+}
+
 // MINB = 2: two CTAs co-resident per SM (<= 96 registers, <= ~110 KB smem, <= 256 TMEM
 // columns each).  tcgen05.mma issue costs the single issuing thread ~50-66 cycles per
 // instruction plus ~500 cycles of barrier/commit latency per ring stage (measured with the
@@ -495,7 +607,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tfull_bar(a), p.issuers);
       mbar_init(tempty_bar(a), kEpiWarps);
       mbar_init(pfull_bar(a), 1);
-      mbar_init(pempty_bar(a), 1);
+      mbar_init(pempty_bar(a), p.issuers);
     }
     prog[0] = 0; prog[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -663,11 +775,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
              clock64() - dbg_t0, dbg_iters, dbg_wait, dbg_pwait);
   } else if (warp == 10 && p.issuers == 2) {
     // ------------------------------------------------- second MMA issuer (odd ring stages)
-    mma_issuer_alternate<KSTEPS>(p, 1, ring, tmem_base, bars, prog);
+    if (p.halo) mma_issuer_alternate_halo<KSTEPS>(p, 1, base, ring, tmem_base, bars, tab_s, prog);
+    else mma_issuer_alternate<KSTEPS>(p, 1, ring, tmem_base, bars, prog);
   } else if (warp == 10) {
     // single-issuer launch: nothing to do
   } else if (warp == 1 && p.issuers == 2) {
-    mma_issuer_alternate<KSTEPS>(p, 0, ring, tmem_base, bars, prog);
+    if (p.halo) mma_issuer_alternate_halo<KSTEPS>(p, 0, base, ring, tmem_base, bars, tab_s, prog);
+    else mma_issuer_alternate<KSTEPS>(p, 0, ring, tmem_base, bars, prog);
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     int stage = 0, pb = 0;
@@ -807,9 +921,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t acc_phase = (tile_it >> 1) & 1u;
       // two issuers: the segment's first iteration went to issuer (g & 1); the other one has a
       // partial accumulator too iff the segment has at least two iterations
+      const int seg_iters = p.halo ? p.kchunks * p.iters_kc : it1 - it0;
       const int first_w = g_it & 1;
-      const bool both = p.issuers == 2 && it1 - it0 >= 2;
-      g_it += it1 - it0;
+      const bool both = p.issuers == 2 && seg_iters >= 2;
+      g_it += seg_iters;
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
       const int wb = mt % p.tiles_w; mt /= p.tiles_w;
@@ -1502,9 +1617,18 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     // phase (now ordered by the progress words in mma_issuer_alternate).
     int want = 1;                                   // 0 one issuer, 1 auto, 2 whenever possible
     if (const char* e = getenv("TRB_TC_ISSUERS")) want = atoi(e);
-    const bool ok = !p.halo && !p.cta2 && p.iters >= 2 && p.N_tile <= 128 &&   // 4 accumulators in 512 TMEM columns,
-                    plan->ctas_per_sm == 1;                                     // which one CTA per SM can have
-    p.issuers = ok && (want == 2 || (want == 1 && p.iters >= 4)) ? 2 : 1;
+    // Halo layers: implemented (mma_issuer_alternate_halo), opt-in through TRB_TC_ISSUERS_HALO
+    // until it has had the stress runs the non-halo path had.
+    static const bool halo_ok = [] {
+      const char* e = getenv("TRB_TC_ISSUERS_HALO");
+      const char* r = getenv("TRB_TC_ROTATE");      // (the halo issuers walk the taps unrotated)
+      return e && atoi(e) != 0 && !(r && atoi(r) != 0);
+    }();
+    const bool ok = (!p.halo || (halo_ok && !p.swap)) && !p.cta2 && p.iters >= 2 &&
+                    p.N_tile <= 128 &&            // 4 accumulators in 512 TMEM columns,
+                    plan->ctas_per_sm == 1;       // which one CTA per SM can have
+    const int per_tile = p.halo ? p.kchunks * ceil_div(p.taps, p.sub) : p.iters;
+    p.issuers = ok && (want == 2 || (want == 1 && per_tile >= 4)) ? 2 : 1;
   }
   p.iters_kc = ceil_div(p.taps, p.sub);
   p.stage_bytes = p.sub * p.sub_bytes;
