@@ -1,5 +1,6 @@
-export TRB_TC_ISSUERS_HALO=1
-for h in 3 1 2; do echo "== tests TRB_TC_ISSUERS=2 TRB_TC_HALO=$h: $(TRB_TC_ISSUERS=2 TRB_TC_HALO=$h timeout 120 python -m pytest tests/test_gpu_ops.py -q -m gpu --tb=line -k 'tcgen05 or fp32' 2>&1 | tail -1)"; done
-echo "== microbench halo issuers ON"; timeout 120 python scripts/bench_conv.py "vgg 3x3 64" "vgg 3x3 128->128" "arcface 3x3 64" "arcface 3x3 128" "retina 3x3"
-echo "== microbench halo issuers OFF"; TRB_TC_ISSUERS_HALO=0 timeout 120 python scripts/bench_conv.py "vgg 3x3 64" "vgg 3x3 128->128" "arcface 3x3 64" "arcface 3x3 128" "retina 3x3"
-echo "== nets halo issuers ON"; timeout 200 python scripts/profile_ops.py openpose arcface --brief | grep -E "^==|rror"
+#!/bin/bash
+# A/B of conv_tc plan-selection switches inside ONE gpurun call (the pool's boxes differ by ~12 %).
+# Usage: bash scripts/matrix_swap.sh VAR "v1 v2 ..." [bench_conv.py filters...]
+VAR=${1:-TRB_TC_ISSUERS}; VALS=${2:-"1 0"}; shift 2
+for v in $VALS; do echo "== $VAR=$v"; env $VAR=$v python scripts/bench_conv.py "$@"; done
+for v in $VALS $VALS; do echo "== nets $VAR=$v"; env $VAR=$v python scripts/profile_ops.py openpose arcface retinaface --brief | grep -E "^==|tcgen05|rror"; done
