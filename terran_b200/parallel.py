@@ -112,6 +112,37 @@ def gather_rows(counts, rows, dst=0):
     return out
 
 
+def gather_faces(faces_per_frame, dst=0):
+    """Gather ``Detection`` results of this rank's frame shard to ``dst`` in frame order.
+    faces_per_frame: list (local frames) of lists of face dicts (``bbox`` int32 (4,),
+    ``landmarks`` int32 (5,2), ``score`` float32).  Returns the list over ALL frames on ``dst``
+    (None elsewhere).  Pixel coordinates travel as float32, exact below 2**24."""
+    counts = [len(f) for f in faces_per_frame]
+    rows = np.zeros((sum(counts), 15), np.float32)
+    i = 0
+    for faces in faces_per_frame:
+        for f in faces:
+            rows[i, :4] = f['bbox']
+            rows[i, 4:14] = np.asarray(f['landmarks']).reshape(-1)
+            rows[i, 14] = f['score']
+            i += 1
+    frames = gather_rows(counts, rows, dst=dst)
+    if frames is None:
+        return None
+    return [[{'bbox': r[:4].astype(np.int32), 'landmarks': r[4:14].astype(np.int32).reshape(5, 2),
+              'score': np.float32(r[14])} for r in fr] for fr in frames]
+
+
+def track_sharded(tracker, faces_per_frame, dst=0):
+    """Face tracking needs frame ORDER (caveat): the detections of every rank's
+    shard are gathered to ``dst`` and fed to ``tracker`` (a ``terran_b200.tracking.Sort``) one
+    frame after the other there.  Returns the tracked faces per frame on ``dst``, None elsewhere."""
+    frames = gather_faces(faces_per_frame, dst=dst)
+    if frames is None:
+        return None
+    return [tracker.update(faces) for faces in frames]
+
+
 def sharded_call(fn, frames, rank=None, world_size=None):
     """Apply ``fn`` (a model ``call``) to this rank's contiguous shard of
     ``frames``; returns (lo, hi, results)."""

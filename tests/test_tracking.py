@@ -3,6 +3,8 @@ reference's own ``Sort`` by ``tests/golden/sort_tracking.npz`` (made by
 ``oracle/make_golden_track.py`` from ``/root/reference/terran/tracking/face.py``); the product's
 vectorised tracker must reproduce the oracle's identities, filtering and output order."""
 import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -116,3 +118,54 @@ def test_face_tracking_wrapper_and_factory(monkeypatch):
     assert (t.tracker.max_age, t.tracker.min_hits) == (7, 5)
     t = face_tracking()                                    # upstream crashes here (video is None)
     assert (t.tracker.max_age, t.tracker.min_hits) == (30, 6)
+
+
+TRACK_WORKER = """
+import sys
+sys.path.insert(0, {root!r})
+import numpy as np
+from oracle import track
+from terran_b200 import parallel
+from terran_b200.tracking import Sort
+
+rank, world, _ = parallel.init_from_env('gloo')
+seq = track.synthetic_sequence(11, frames=33, people=5)
+for faces in seq:
+    for f in faces:
+        f['landmarks'] = np.tile(f['bbox'][:2], (5, 1)).astype(np.int32)
+lo, hi = parallel.shard_range(len(seq), rank, world)
+tracked = parallel.track_sharded(Sort(max_age=4, min_hits=2), seq[lo:hi])
+if rank == 0:
+    id0 = Sort.next_id
+    s = Sort(max_age=4, min_hits=2)
+    want = [s.update([dict((k, v) for k, v in f.items() if k != 'person') for f in faces]) for faces in seq]
+    assert len(tracked) == len(want) == 33
+    for a, b in zip(tracked, want):
+        assert len(a) == len(b)
+        for fa, fb in zip(a, b):
+            # two trackers of one process: ids differ by the offset between the two runs
+            assert (fa['track'] is None) == (fb['track'] is None)
+            assert np.array_equal(fa['bbox'], fb['bbox']) and np.array_equal(fa['landmarks'], fb['landmarks'])
+            assert fa['bbox'].dtype == np.int32 and fa['score'] == fb['score']
+    ids_a = [f['track'] for fr in tracked for f in fr if f['track'] is not None]
+    ids_b = [f['track'] for fr in want for f in fr if f['track'] is not None]
+    assert len(ids_a) > 20 and [i - min(ids_a) for i in ids_a] == [i - min(ids_b) for i in ids_b]
+    print('TRACK_OK')
+else:
+    assert tracked is None
+"""
+
+
+def test_two_rank_gloo_tracking_consumes_gathered_frames_in_order(tmp_path):
+    """Frames shard across ranks, tracking runs on rank 0 over the gathered detections in frame
+    order and equals single-process tracking of the whole sequence."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / 'worker.py'
+    script.write_text(TRACK_WORKER.format(root=root))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='', OMP_NUM_THREADS='1')
+    r = subprocess.run(
+        [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+         '--master-addr', '127.0.0.1', '--master-port', '29733', str(script)],
+        capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'TRACK_OK' in r.stdout
