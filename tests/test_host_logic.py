@@ -296,3 +296,25 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU port timed on host cores) prints ONE JSON line with
+    the arm's keys: same metric / unit / config as the GPU arm, a cpu_baseline describing the
+    run and an e2e block without device traffic."""
+    import json
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='', OMP_NUM_THREADS='4')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                        '--steps', '1', '--warmup', '0'], capture_output=True, text=True, env=env,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'frames/s' and d['higher_is_better'] is True
+    assert d['metric'].startswith('frames/sec end-to-end (detect+pose)')
+    assert d['value'] > 0 and d['steps'] == 1 and d['n_gpus'] == 1
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['value'] == d['value'] and 'sample' in d['cpu_baseline']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}
