@@ -196,6 +196,23 @@ def per_config_throughput(det_model, pose_model, frames, dev, steps):
     out = {}
     out['retinaface_1080p_b32'] = dict(
         timed(lambda: det_model.detect_device(resize_short_side(frames, 416)[0]), 32), unit='frames/s')
+    try:
+        # HBM roofline of the RetinaFace conv stack (the layers are byte-bound):
+        # algorithmic bytes of the layer program (each tensor once per op that touches it)
+        # over the back-to-back time of the net alone.
+        from terran_b200.weights import program_traffic
+        small = resize_short_side(frames, 416)[0]
+        net = timed(lambda: det_model.forward(small), 32)
+        nbytes, _ = program_traffic(det_model.net.program, int(small.shape[0]), int(small.shape[1]),
+                                    int(small.shape[2]))
+        peaks = measured_peaks()
+        gbs = nbytes / (net['ms_per_step'] * 1e-3) / 1e9
+        out['retinaface_1080p_b32']['conv_stack'] = {
+            'ms_per_step': net['ms_per_step'], 'launches': det_model.net.stats()['launches'],
+            'algorithmic_mb_per_frame': nbytes / int(small.shape[0]) / 1e6, 'bound': 'hbm',
+            'achieved_gbs': gbs, 'peak_gbs': peaks['hbm_gbs'], 'frac': gbs / peaks['hbm_gbs']}
+    except Exception as e:                      # never let the extra figure break the bench line
+        out['retinaface_1080p_b32']['conv_stack'] = {'error': str(e)[:200]}
     f720 = torch.from_numpy(np.random.default_rng(1).integers(
         0, 256, (16, 720, 1280, 3), dtype=np.uint8)).to(dev)
     out['openpose_720p_b16'] = dict(timed(lambda: pose_model.estimate_device(f720), 16), unit='frames/s')

@@ -405,6 +405,55 @@ def openpose_program(sd):
     return P, {'maps': cat[(6 + 1) % 2], 'paf_coff': 0, 'heat_coff': 40}
 
 
+def program_traffic(program, N, H, W):
+    """Algorithmic HBM traffic of one run of ``program`` on an (N, H, W, 3) uint8 batch: per op
+    the bytes it must read (input view, residual, filters + per-channel parameters) and write
+    (output views), each tensor counted once per op that touches it — the model behind the
+    HBM roofline of the RetinaFace stack (42.6 MB/frame layer-wise,
+    20.1 MB/frame for a block-fused plan at 416x739).  Shapes follow the executor's inference
+    (``csrc/net.cu::build_plan``).  Returns (total_bytes, [(op_index, read, written)])."""
+    dims = [None] * len(program.buffers)
+    per_op = []
+    for i, d in enumerate(program.ops):
+        if d.in_ < 0:
+            n, h, w = N, H, W
+        else:
+            n, h, w = dims[d.in_]
+        esz = lambda b: 4 if program.buffers[b][1] else 2
+        if d.type in (nat.TR_OP_STEM, nat.TR_OP_CONV, nat.TR_OP_DWCONV, nat.TR_OP_SEPCONV):
+            oh, ow = (h + 2 * d.pad - d.k) // d.stride + 1, (w + 2 * d.pad - d.k) // d.stride + 1
+            dims[d.out] = (n, oh, ow)
+            if d.out2 >= 0:
+                dims[d.out2] = (n, oh, ow)
+            rd = n * h * w * (3 if d.type == nat.TR_OP_STEM else d.in_c * esz(d.in_))
+            if d.type == nat.TR_OP_STEM:
+                rd += d.out_c * 27 * 4
+            elif d.type == nat.TR_OP_CONV:
+                rd += d.cout_pad * d.k * d.k * d.in_c * 2
+            elif d.type == nat.TR_OP_DWCONV:
+                rd += 9 * d.in_c * 4
+            else:
+                rd += 9 * d.in_c * 2 + d.cout_pad * d.in_c * 2 + 2 * d.in_c * 4
+            rd += 2 * max(d.cout_pad, d.out_c) * 4                      # scale / shift
+            if d.res >= 0:
+                rn, rh, rw = dims[d.res]
+                rd += n * oh * ow * d.out_c * 2 if not d.res_up2 else rn * rh * rw * d.out_c * 2
+            wr = n * oh * ow * d.out_c * esz(d.out)
+            if d.out2 >= 0:
+                wr += n * oh * ow * d.out_c * 2
+        elif d.type == nat.TR_OP_MAXPOOL:
+            dims[d.out] = (n, h // 2, w // 2)
+            rd, wr = n * h * w * d.in_c * 2, n * (h // 2) * (w // 2) * d.out_c * 2
+        elif d.type == nat.TR_OP_COPY:
+            dims[d.out] = (n, h, w)
+            rd = wr = n * h * w * d.in_c * 2
+        else:                                                            # view: no traffic
+            dims[d.out] = (n, 1, 1)
+            rd = wr = 0
+        per_op.append((i, rd, wr))
+    return sum(r + w for _, r, w in per_op), per_op
+
+
 # ----------------------------------------------------------------------- Net
 
 class Net:

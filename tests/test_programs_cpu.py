@@ -81,3 +81,22 @@ def test_arcface_program_matches_oracle():
     cos = torch.nn.functional.cosine_similarity(got, want, dim=1)
     assert (cos > 0.9999).all(), cos
     assert _rel(got, want) < 5e-3
+
+
+def test_program_traffic_model_of_the_retinaface_stack():
+    """Algorithmic bytes per frame at the benchmark shape (32 x 416 x 739): the fused program
+    must be close to SURVEY.md 8d's block-fused figure (20.1 MB/frame) and well below the
+    layer-wise one (42.6 MB/frame), which the unfused program reproduces."""
+    sd = synth.retinaface_state_dict()
+    fused, _ = weights.retinaface_program(sd, fused=True)
+    plain, _ = weights.retinaface_program(sd, fused=False)
+    bf, per_op = weights.program_traffic(fused, 32, 416, 739)
+    bp, _ = weights.program_traffic(plain, 32, 416, 739)
+    mb_f, mb_p = bf / 32 / 1e6, bp / 32 / 1e6
+    assert 18.0 < mb_f < 30.0, mb_f
+    assert 38.0 < mb_p < 48.0, mb_p
+    assert len(per_op) == len(fused.ops) and all(r > 0 and w > 0 for _, r, w in per_op)
+    # shapes inferred like the executor: three head maps of ceil(H/stride) x ceil(W/stride)
+    _, per = weights.program_traffic(fused, 1, 416, 739)
+    heads = [w for (i, _, w) in per if fused.buffers[fused.ops[i].out][1]]
+    assert sorted(heads) == [13 * 24 * 32 * 4, 26 * 47 * 32 * 4, 52 * 93 * 32 * 4]
