@@ -90,8 +90,12 @@ class PerceptionPipeline:
     the synchronous per-batch loop of the reference's ``examples/video.py``,
     software-pipelined."""
 
-    def __init__(self, detection, estimation, device=default_device):
+    def __init__(self, detection, estimation, device=default_device, tracker=None):
+        """tracker: optional ``terran_b200.tracking.Sort``; ``run`` then feeds it the faces of
+        every frame in stream order (tracking is the one consumer that needs frame order) and
+        yields the faces with their ``track`` field (reference: ``examples/match.py:31-40``)."""
         self.detection, self.estimation = detection, estimation
+        self.tracker = tracker
         self.device_index = cuda_index(device)
         self.streams = [torch.cuda.Stream(device=self.device_index) for _ in range(2)]
 
@@ -116,10 +120,16 @@ class PerceptionPipeline:
         for frames in batches:
             current = self.submit(frames)
             if previous is not None:
-                yield previous.result()
+                yield self._tracked(previous.result())
             previous = current
         if previous is not None:
-            yield previous.result()
+            yield self._tracked(previous.result())
+
+    def _tracked(self, result):
+        if self.tracker is None:
+            return result
+        faces, poses = result
+        return [self.tracker.update(f) for f in faces], poses
 
     def close(self):
         pass
