@@ -255,3 +255,169 @@ def test_two_issuer_pipeline_with_accumulator_handover(stages):
     for seed in range(120):
         segments = [rng.randint(1, 11) for _ in range(rng.randint(3, 9))]
         assert simulate_segments(stages, segments, seed) is None, (stages, segments, seed)
+
+
+def simulate_halo(stages, tiles, kchunks, iters_kc, seed, max_steps=400000):
+    """Halo-path two-issuer protocol (``mma_issuer_alternate_halo``): per chunk-step a resident
+    patch in one of two buffers (``pfull`` armed by the TMA, ``pempty`` released by BOTH
+    issuers: count 2, plain arrive by an issuer without an iteration in the step), filter
+    blocks through the ring, the producer requesting the next step's patch one step ahead."""
+    rng = random.Random(seed)
+    full = [MBarrier() for _ in range(stages)]
+    empty = [MBarrier() for _ in range(stages)]
+    pfull = [MBarrier(), MBarrier()]
+    pempty = [MBarrier(2), MBarrier(2)]
+    tfull = [MBarrier(2), MBarrier(2)]
+    tempty = [MBarrier(1), MBarrier(1)]
+    content = [None] * stages
+    patch = [None, None]                     # chunk-step whose patch a buffer holds
+    reading = [0, 0]                         # MMAs in flight that read the buffer
+    prog = [0, 0]
+    events = []
+    n_tile = kchunks * iters_kc
+    steps_total = tiles * kchunks
+    done = []
+
+    def producer():
+        issued = 0
+
+        def issue_patch(q):
+            b, ph = q & 1, (q >> 1) & 1
+            while not pempty[b].test_wait(ph ^ 1):
+                yield
+            if reading[b]:
+                raise Violation(f'patch buffer {b} overwritten while MMAs read it')
+            events.append(('patch', (b, q)))
+
+        g = 0
+        for q in range(steps_total):
+            if issued == q:
+                yield from issue_patch(q)
+                issued += 1
+            for it in range(iters_kc):
+                if it == min(stages, iters_kc - 1) and issued == q + 1 and q + 1 < steps_total:
+                    yield from issue_patch(q + 1)
+                    issued += 1
+                s, ph = g % stages, (g // stages) & 1
+                while not empty[s].test_wait(ph ^ 1):
+                    yield
+                events.append(('land', (s, g)))
+                g += 1
+                yield
+
+    def issuer(w):
+        mine, g, q = 0, 0, 0
+        for t in range(tiles):
+            a, aph = t & 1, (t >> 1) & 1
+            first_tile = 0 if (g & 1) == w else 1
+            while not tempty[a].test_wait(aph ^ 1):
+                yield
+            if first_tile >= n_tile:
+                while not pfull[q & 1].test_wait((q >> 1) & 1):
+                    yield
+                pempty[q & 1].arrive()
+                tfull[a].arrive()
+                g += n_tile
+                q += kchunks
+                yield
+                continue
+            last_mine = max(range(first_tile, n_tile, 2))
+            for kc in range(kchunks):
+                b = q & 1
+                while not pfull[b].test_wait((q >> 1) & 1):
+                    yield
+                if patch[b] != q:
+                    raise Violation(f'issuer {w} step {q}: patch buffer holds {patch[b]}')
+                gq = g + kc * iters_kc
+                first = 0 if (gq & 1) == w else 1
+                its = list(range(first, iters_kc, 2))
+                if not its:
+                    pempty[b].arrive()
+                    q += 1
+                    yield
+                    continue
+                for it in its:
+                    gi = gq + it
+                    s, ph = gi % stages, (gi // stages) & 1
+                    if (stages & 1) and gi >= stages:
+                        need = (gi - stages - (w ^ 1)) // 2 + 1
+                        while prog[w ^ 1] < need:
+                            yield
+                    while not full[s].test_wait(ph):
+                        yield
+                    mine += 1
+                    prog[w] = mine
+                    if content[s] != gi:
+                        raise Violation(f'issuer {w} consumed stage {s} holding {content[s]} at {gi}')
+                    reading[b] += 1
+                    yield
+                    events.append(('commit', (s, gi, b)))
+                    if it == its[-1]:
+                        events.append(('pempty', (b, gi, w)))
+                    if kc * iters_kc + it == last_mine:
+                        events.append(('tfull', (a, gi, w)))
+                    yield
+                q += 1
+            g += n_tile
+
+    def epilogue():
+        for t in range(tiles):
+            a, aph = t & 1, (t >> 1) & 1
+            while not tfull[a].test_wait(aph):
+                yield
+            yield
+            tempty[a].arrive()
+            done.append(t)
+            yield
+
+    actors = {'producer': producer(), 'issuer0': issuer(0), 'issuer1': issuer(1), 'epilogue': epilogue()}
+
+    def issuer_of(kind, payload):
+        return payload[1] & 1 if kind == 'commit' else payload[2]
+
+    try:
+        for _ in range(max_steps):
+            choices = list(actors) + ['event'] * min(len(events), 2)
+            if not choices:
+                return None if len(done) == tiles else 'stopped early'
+            pick = rng.choice(choices)
+            if pick == 'event':
+                idx = rng.randrange(len(events))
+                kind, payload = events[idx]
+                if kind in ('commit', 'pempty', 'tfull'):        # one thread's completions are ordered
+                    w = issuer_of(kind, payload)
+                    idx = next(i for i, (k, pl) in enumerate(events)
+                               if k in ('commit', 'pempty', 'tfull') and issuer_of(k, pl) == w)
+                    kind, payload = events[idx]
+                events.pop(idx)
+                if kind == 'land':
+                    content[payload[0]] = payload[1]
+                    full[payload[0]].arrive()
+                elif kind == 'patch':
+                    patch[payload[0]] = payload[1]
+                    pfull[payload[0]].arrive()
+                elif kind == 'commit':
+                    s, gi, b = payload
+                    content[s] = None
+                    reading[b] -= 1
+                    empty[s].arrive()
+                elif kind == 'pempty':
+                    pempty[payload[0]].arrive()
+                else:
+                    tfull[payload[0]].arrive()
+                continue
+            try:
+                next(actors[pick])
+            except StopIteration:
+                del actors[pick]
+        return 'no progress (deadlock or live-lock)'
+    except Violation as v:
+        return str(v)
+
+
+@pytest.mark.parametrize('stages', [2, 3, 4])
+def test_halo_two_issuer_protocol(stages):
+    for kchunks, iters_kc in [(1, 3), (2, 3), (2, 25), (1, 1), (2, 1), (3, 2), (1, 5)]:
+        for seed in range(40):
+            r = simulate_halo(stages, 5, kchunks, iters_kc, seed)
+            assert r is None, (stages, kchunks, iters_kc, seed, r)
