@@ -196,10 +196,77 @@ def golden_openpose():
     np.savez_compressed(os.path.join(GOLDEN, 'openpose_parse.npz'), **fx)
 
 
+def golden_baseline():
+    """Fixtures at the BASELINE.json batch sizes, produced by the unmodified reference:
+    C3 = Recognition on 256 crops of 112x112 (the bench's crops), C4/C5 = Estimation on 720p
+    noise frames with the peak-calibrated OpenPose checkpoint (humans in every frame), C2 =
+    Detection on four 1080p noise frames."""
+    from terran.face.detection import Detection
+    from terran.face.detection.retinaface import RetinaFace
+    from terran.face.recognition import Recognition
+    from terran.face.recognition.arcface import ArcFace
+    from terran.pose import Estimation
+    from terran.pose.openpose import OpenPose
+
+    # -- C3: 256 crops
+    crops = np.random.default_rng(2).integers(0, 256, (256, 112, 112, 3), dtype=np.uint8)
+    rec = Recognition(device=torch.device('cpu'), lazy=True)
+    rec.model = ArcFace(device=torch.device('cpu'))
+    ref = np.asarray(rec(list(crops)), np.float32)
+    sd = synth.arcface_state_dict()
+    x = torch.from_numpy(crops[:4].transpose(0, 3, 1, 2)[:, ::-1].astype(np.float32).copy())
+    raw = nets.arcface_forward(sd, x).numpy()
+    assert report('arcface b256 (first 4) normalised', ref[:4],
+                  raw / np.linalg.norm(raw, axis=1, keepdims=True)) < 1e-6
+    np.savez_compressed(os.path.join(GOLDEN, 'arcface_embed_b256.npz'), normalised=ref,
+                        crops_seed=np.array(2))
+
+    # -- C4: Estimation with humans (checkpoint swapped for the calibrated one)
+    sdp = synth.openpose_state_dict(peaks=True)
+    wrapper = OpenPose(device=torch.device('cpu'))
+    wrapper.model.load_state_dict(sdp)
+    est = Estimation(device=torch.device('cpu'), lazy=True)
+    est.model = wrapper
+    frames = np.random.default_rng(1).integers(0, 256, (2, 720, 1280, 3), dtype=np.uint8)
+    ref = est(frames)
+    import cv2
+    s = 184 / 720
+    small = np.stack([cv2.resize(f, (int(1280 * s), int(720 * s)), interpolation=cv2.INTER_LINEAR)
+                      for f in frames])
+    xin = torch.from_numpy(small.transpose(0, 3, 1, 2).astype(np.float32) / 255.0 - 0.5)
+    paf, heat = nets.openpose_forward(sdp, xin)
+    ora = pose.parse(paf.numpy(), heat.numpy(), s)
+    fx = {'frames_seed': np.array(1)}
+    for n, (r, o) in enumerate(zip(ref, ora)):
+        print(f'  Estimation 720p frame {n}: reference {len(r)} humans, oracle {len(o)}')
+        assert len(r) == len(o) and len(r) > 0
+        for a, b in zip(r, o):
+            assert np.array_equal(a['keypoints'], b['keypoints'])
+            assert abs(a['score'] - b['score']) < 1e-5
+        fx[f'kp{n}'] = np.stack([a['keypoints'] for a in r])
+        fx[f'score{n}'] = np.array([a['score'] for a in r], np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, 'openpose_estimation_720p.npz'), **fx)
+
+    # -- C2: Detection on 1080p frames
+    wrapper = RetinaFace(device=torch.device('cpu'))
+    wrapper.model = Contiguous(wrapper.model)
+    det = Detection(device=torch.device('cpu'), lazy=True)
+    det.model = wrapper
+    frames = np.random.default_rng(0).integers(0, 256, (4, 1080, 1920, 3), dtype=np.uint8)
+    ref = det(frames)
+    fx = {'frames_seed': np.array(0)}
+    for n, faces in enumerate(ref):
+        print(f'  Detection 1080p frame {n}: {len(faces)} faces')
+        fx[f'bbox{n}'] = np.stack([f['bbox'] for f in faces])
+        fx[f'landmarks{n}'] = np.stack([f['landmarks'] for f in faces])
+        fx[f'score{n}'] = np.stack([f['score'] for f in faces])
+    np.savez_compressed(os.path.join(GOLDEN, 'retinaface_detection_1080p.npz'), **fx)
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     import_reference()
-    which = sys.argv[1:] or ['retinaface', 'arcface', 'openpose']
+    which = sys.argv[1:] or ['retinaface', 'arcface', 'openpose', 'baseline']
     for name in which:
         print(f'[{name}]')
         globals()['golden_' + name]()

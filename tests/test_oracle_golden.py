@@ -190,3 +190,59 @@ def test_openpose_parse_edge_cases():
     assert pose.parse_frame(z_paf, h, 1.0) == []
     # zero-length pair (same location for src/dst part) -> NaN score, rejected
     assert pose.segment_points(5, 5) == [5] * 10
+
+
+# ---- fixtures at the BASELINE batch sizes (oracle/make_golden.py::golden_baseline)
+
+def test_baseline_c3_oracle_matches_reference_256_crops(golden):
+    """First rows of the reference's 256-crop embedding batch (the rest is the same
+    function of independent crops)."""
+    g = golden('arcface_embed_b256.npz')
+    crops = np.random.default_rng(int(g['crops_seed'])).integers(0, 256, (256, 112, 112, 3),
+                                                                 dtype=np.uint8)
+    sel = [0, 100, 255]
+    x = torch.from_numpy(crops[sel].transpose(0, 3, 1, 2)[:, ::-1].astype(np.float32).copy())
+    raw = nets.arcface_forward(synth.arcface_state_dict(), x).numpy()
+    want = g['normalised']
+    assert want.shape == (256, 512)
+    np.testing.assert_allclose(raw / np.linalg.norm(raw, axis=1, keepdims=True), want[sel],
+                               rtol=0, atol=1e-6)
+
+
+def test_baseline_c4_oracle_estimation_with_humans_matches_reference(golden):
+    """The reference's own ``Estimation`` on 720p noise frames with the peak-calibrated
+    checkpoint finds 6 and 9 humans; the oracle (cv2 resize -> net -> parse) reproduces
+    them exactly."""
+    import cv2
+    g = golden('openpose_estimation_720p.npz')
+    frames = np.random.default_rng(int(g['frames_seed'])).integers(0, 256, (2, 720, 1280, 3),
+                                                                   dtype=np.uint8)
+    sd = synth.openpose_state_dict(peaks=True)
+    s = 184 / 720
+    small = np.stack([cv2.resize(f, (int(1280 * s), int(720 * s)), interpolation=cv2.INTER_LINEAR)
+                      for f in frames[:1]])
+    x = torch.from_numpy(small.transpose(0, 3, 1, 2).astype(np.float32) / 255.0 - 0.5)
+    paf, heat = nets.openpose_forward(sd, x)
+    out = pose.parse(paf.numpy(), heat.numpy(), s)[0]
+    assert len(out) == len(g['kp0']) >= 4
+    for o, k, sc in zip(out, g['kp0'], g['score0']):
+        np.testing.assert_array_equal(o['keypoints'], k)
+        assert abs(o['score'] - sc) < 1e-5
+
+
+def test_baseline_c2_oracle_detection_1080p_matches_reference(golden, retina_sd):
+    import cv2
+    g = golden('retinaface_detection_1080p.npz')
+    frames = np.random.default_rng(int(g['frames_seed'])).integers(0, 256, (4, 1080, 1920, 3),
+                                                                   dtype=np.uint8)[:2]
+    s = 416 / 1080
+    small = np.stack([cv2.resize(f, (int(1920 * s), int(1080 * s)), interpolation=cv2.INTER_LINEAR)
+                      for f in frames])
+    x = torch.from_numpy(small.astype(np.float32)).permute(0, 3, 1, 2).flip(1)
+    heads = [h.numpy() for h in nets.retinaface_forward(retina_sd, x)]
+    out = detect.resize_out(detect.model_call(heads, *small.shape[1:3]), s)
+    for n, faces in enumerate(out):
+        assert len(faces) == len(g[f'score{n}']) > 10
+        np.testing.assert_array_equal(np.stack([f['bbox'] for f in faces]), g[f'bbox{n}'])
+        np.testing.assert_array_equal(np.stack([f['landmarks'] for f in faces]), g[f'landmarks{n}'])
+        np.testing.assert_array_equal(np.array([f['score'] for f in faces]), g[f'score{n}'])
