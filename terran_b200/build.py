@@ -22,6 +22,7 @@ COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC']
 #: fp32 operation order bit for bit, so fused multiply-add contraction is off.
 SOURCES = {
     'conv_tc.cu': [],
+    'conv_patch.cu': [],
     'conv_direct.cu': [],
     'conv_mma.cu': [],
     'detect_post.cu': ['-fmad=false'],

@@ -80,6 +80,15 @@ void conv_tc_plan_destroy(ConvTcPlan* p);
 void conv_tc_launch(const ConvTcPlan* p, cudaStream_t s);
 double conv_tc_plan_flops(const ConvTcPlan* p);
 int conv_tc_last_timeout();   // pipeline wait that timed out before a trap (0 = none)
+int* conv_tc_error_flag();    // device-visible word a trapping kernel writes its timeout code to
+
+// conv_patch.cu — tcgen05 kernel with filters on M and a resident input patch on N
+bool conv_patch_eligible(const ConvArgs& a);
+struct ConvPatchPlan;
+ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag);
+void conv_patch_plan_destroy(ConvPatchPlan* p);
+void conv_patch_launch(const ConvPatchPlan* p, cudaStream_t s);
+void conv_patch_plan_describe(const ConvPatchPlan* p, int* axis, int* R, int* tiles, int* stages);
 
 // conv_direct.cu
 void conv_direct_launch(const ConvArgs& a, cudaStream_t s);

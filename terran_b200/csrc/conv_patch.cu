@@ -1,0 +1,468 @@
+// Implicit-GEMM convolution on tcgen05, "filters on M, pixels from a resident patch on N".
+//
+//   D^T[cout, pixel] = sum over channel chunks kc and taps (r,s) of
+//                      W_tap,kc[cout, 64] * X_patch(r,s)[pixel, 64]^T
+//
+// Why a second tensor-core kernel (measured in round 1, profiles/r01_swap_modes.txt and
+// r01_conv_microbench_v2_debugmodes.txt): conv_tc_kernel loads one im2col window per filter
+// tap, so a 7x7 layer pulls every input pixel 49 times through L2 -> shared memory
+// (738 MB per launch for 9 MB of operands); with the TMA half or the MMA half of the pipeline
+// alone the 7x7 128->128 layer takes the same 47 us — the L2 -> SM operand supply, not the tensor
+// pipe, bounds every layer whose per-SM tile is 128 x 128.  Here
+//   * the input patch of an output tile INCLUDING the filter halo is loaded once per
+//     64-channel chunk and stays resident; every tap's B operand is a UMMA descriptor whose
+//     start address is shifted inside that patch (rows of 16 pixels = 2048 B = the
+//     descriptor's group stride, so an 8-pixel group never straddles a patch row);
+//   * the FILTER block (128 couts x 64 channels = 16 KB per tap and chunk) is the only operand
+//     that streams, through a deep ring;
+//   * the 128 output channels sit on the UMMA M dimension and the pixels on N, so N = 8 R can
+//     be chosen per layer (R rows of 8 pixels, N <= 256): one instruction carries up to twice
+//     the work of the N = 128 tile, and L2 -> SM traffic per flop drops with N.
+// TMEM holds D^T (lane = cout, column = pixel); the epilogue thread of a lane owns one output
+// channel, so per-channel parameters are registers and a warp writes 64-byte runs.
+//
+// Warp roles (352 threads, one CTA per SM, persistent over tiles):
+//   warp 0      filter producer (TMA 2-D, ring of `stages` x `sub` filter blocks) — does NOT wait
+//               for the previous layer (weights are constant): the ring fills during the
+//               previous kernel's tail under programmatic dependent launch
+//   warp 1      TMEM allocator + tcgen05.mma issuer
+//   warps 2-9   epilogue (tcgen05.ld -> scale/shift/act/residual -> HBM), double-buffered TMEM
+//   warp 10     patch producer (TMA 4-D, two patch buffers; waits for the previous layer)
+//
+// Replaces the cuDNN convolutions behind the stride-1 nn.Conv2d layers with >= 128 filters of
+// openpose/model.py:41-95 (and arcface/model.py:11-35 where eligible).
+#include <cudaTypedefs.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace trb {
+
+namespace {
+
+constexpr int kPThreads = 352;
+constexpr int kPEpiWarps = 8;
+constexpr int kPMaxStages = 12;
+constexpr uint32_t kFilterBlock = 128 * 64 * 2;      // one (tap, chunk) filter block: 16 KB
+
+struct PatchParams {
+  int N, H, W;                 // output == input dims (stride 1, "same" padding)
+  int k, pad, taps;
+  int cin_pad, kchunks, in_coff;
+  int cout_tiles;
+  int axis;                    // 0: 8-pixel groups along w, R rows along h;  1: groups along h, R along w
+  int R, NP, PA;               // NP = 8 R pixels per tile (UMMA N); PA = patch pixels per row (8 | 16)
+  int tiles_a, tiles_b, pix_tiles, total_tiles;
+  int sub, iters, stages;      // taps per ring stage, stages per chunk, ring depth
+  uint32_t stage_bytes, patch_bytes, patch_tx, ring_off;
+  uint32_t idesc, tmem_cols;
+  const float* scale; const float* shift; const float* slope;
+  int act;
+  __half* out; int out_cs, out_coff, cout_store;
+  const __half* res; int res_cs, res_coff;
+  float* out_f32;
+  int* err;
+  int pdl_late;
+  int debug;                   // timing experiments: 1 no filter TMA, 2 no MMA, 4 no stores
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7])
+      : "r"(taddr));
+}
+
+struct TileCoord {
+  int ct, n, a0, b0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const PatchParams& p, int tile) {
+  TileCoord t;
+  t.ct = tile / p.pix_tiles;
+  int pt = tile - t.ct * p.pix_tiles;
+  const int ta = pt % p.tiles_a; pt /= p.tiles_a;
+  const int tb = pt % p.tiles_b;
+  t.n = pt / p.tiles_b;
+  t.a0 = ta * 8;
+  t.b0 = tb * p.R;
+  return t;
+}
+
+__global__ void __launch_bounds__(kPThreads, 1)
+conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const PatchParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // two patch buffers first
+  const uint32_t ring = base + p.ring_off;
+  const uint32_t tab_s = ring + p.stages * p.stage_bytes;           // per-tap descriptor offsets
+  const uint32_t bars = tab_s + 512u;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kPMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kPMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kPMaxStages + 2 + a); };
+  auto pfull_bar = [&](int b) { return bars + 8u * (2 * kPMaxStages + 4 + b); };
+  auto pempty_bar = [&](int b) { return bars + 8u * (2 * kPMaxStages + 6 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kPMaxStages + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kPEpiWarps);
+      mbar_init(pfull_bar(a), 1);
+      mbar_init(pempty_bar(a), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 2) {
+    // what tap (r, s) adds to the patch's descriptor start address, in 16-byte units
+    for (int t = lane; t < p.taps; t += 32) {
+      const int r = t / p.k, s = t - r * p.k;
+      const int ta = p.axis == 0 ? s : r, tb = p.axis == 0 ? r : s;
+      const uint32_t v = static_cast<uint32_t>(tb * p.PA + ta) * 8u;
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_s + 4u * t), "r"(v) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  const int grid = gridDim.x;
+  // Every role loop runs with the whole warp converged; one elected lane issues (see
+  // conv_tc.cu, lesson 1: issuing from a divergent region costs ~240 cycles per instruction).
+  if (warp == 0) {
+    // ---------------------------------------------------------- filter producer
+    int stage = 0;
+    uint32_t phase = 0;
+    if (!p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid) {
+      if (p.pdl_late && tile + grid >= p.total_tiles)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+      const int ct = tile / p.pix_tiles;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        int tap = 0;
+        for (int it = 0; it < p.iters; ++it) {
+          const int nsub = min(p.sub, p.taps - tap);
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
+          const uint32_t dst = ring + stage * p.stage_bytes;
+          if (p.debug & 1) {
+            if (elect_one()) mbar_arrive(full_bar(stage));
+          } else if (elect_one()) {
+            mbar_expect_tx(full_bar(stage), nsub * kFilterBlock);
+            for (int j = 0; j < nsub; ++j)
+              tma_load_2d(dst + j * kFilterBlock, &tmW, full_bar(stage),
+                          (tap + j) * p.cin_pad + kc * 64, ct * 128);
+          }
+          __syncwarp();
+          tap += nsub;
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ----------------------------------------------------------- patch producer
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // activations of the previous layer
+    int q = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid) {
+      const TileCoord t = tile_coord(p, tile);
+      for (int kc = 0; kc < p.kchunks; ++kc, ++q) {
+        const int buf = q & 1;
+        mbar_wait(pempty_bar(buf), ((q >> 1) & 1u) ^ 1u, p.err, 5);
+        if (elect_one()) {
+          mbar_expect_tx(pfull_bar(buf), p.patch_tx);
+          tma_load_4d(base + buf * p.patch_bytes, &tmX, pfull_bar(buf), p.in_coff + kc * 64,
+                      t.a0 - p.pad, t.b0 - p.pad, t.n);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------------- MMA issuer
+    int stage = 0, q = 0, tile_it = 0;
+    uint32_t phase = 0;
+    const uint32_t w_hi = umma_desc_hi(1024, 2);                       // filters: 8 rows x 128 B groups
+    const uint32_t x_hi = umma_desc_hi(static_cast<uint32_t>(p.PA) * 128u, 2);   // one patch row per group
+    const uint32_t ring_lo = umma_desc_lo(ring);
+    const uint32_t stage_step = p.stage_bytes >> 4;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++tile_it) {
+      const int acc = tile_it & 1;
+      mbar_wait(tempty_bar(acc), ((tile_it >> 1) & 1u) ^ 1u, p.err, 2);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_base + acc * p.NP;
+      uint32_t accumulate = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc, ++q) {
+        const int buf = q & 1;
+        mbar_wait(pfull_bar(buf), (q >> 1) & 1u, p.err, 6);
+        const uint32_t patch_lo = umma_desc_lo(base + buf * p.patch_bytes);
+        int tap = 0;
+        for (int it = 0; it < p.iters; ++it) {
+          const int nsub = min(p.sub, p.taps - tap);
+          mbar_wait(full_bar(stage), phase, p.err, 3);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            const uint32_t w_lo0 = ring_lo + stage * stage_step;
+            if (!(p.debug & 2)) {
+              for (int j = 0; j < nsub; ++j) {
+                uint32_t tap_off;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tap_off) : "r"(tab_s + 4u * (tap + j)));
+                const uint32_t x_lo = patch_lo + tap_off;
+                const uint32_t w_lo = w_lo0 + j * (kFilterBlock >> 4);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {          // +32 B (two 16-byte units) per K = 16 step
+                  umma_f16(d_tmem, w_lo + 2 * ks, w_hi, x_lo + 2 * ks, x_hi, p.idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+            }
+            umma_commit(empty_bar(stage));
+            if (it == p.iters - 1) {
+              umma_commit(pempty_bar(buf));
+              if (kc == p.kchunks - 1) umma_commit(tfull_bar(acc));
+            }
+          }
+          __syncwarp();
+          tap += nsub;
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ----------------------------------------------------------------- epilogue
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // residual reads / buffer re-use
+    const int ew = warp - 2;
+    const int qd = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                // which half of the pixel groups it takes
+    const int g_begin = half * (p.R >> 1), g_end = g_begin + (p.R >> 1);
+    const int A_dim = p.axis == 0 ? p.W : p.H, B_dim = p.axis == 0 ? p.H : p.W;
+    const long a_step = p.axis == 0 ? 1 : p.W;           // pixel-index step along the group axis
+    const long b_step = p.axis == 0 ? p.W : 1;
+    int tile_it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++tile_it) {
+      const int acc = tile_it & 1;
+      const TileCoord t = tile_coord(p, tile);
+      const int cout = t.ct * 128 + qd * 32 + lane;
+      const float sc = p.scale[cout], sh = p.shift[cout];
+      const float sl = p.slope ? p.slope[cout] : 0.f;
+      const bool c_ok = cout < p.cout_store;
+      const long pix00 = static_cast<long>(t.n) * p.H * p.W + t.a0 * a_step + t.b0 * b_step;
+      mbar_wait(tfull_bar(acc), (tile_it >> 1) & 1u, p.err, 4);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * p.NP;
+      for (int g = g_begin; g < g_end; ++g) {
+        uint32_t v[8];
+        __syncwarp();
+        tmem_ld8_async(taddr + g * 8, v);
+        tmem_ld_wait();
+        if (t.b0 + g >= B_dim || !c_ok || (p.debug & 4)) continue;
+        const long pix0 = pix00 + g * b_step;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (t.a0 + i >= A_dim) break;
+          const long pix = pix0 + i * a_step;
+          float y = fmaf(__uint_as_float(v[i]), sc, sh);
+          if (p.act == ACT_RELU) y = fmaxf(y, 0.f);
+          else if (p.act == ACT_PRELU) y = y >= 0.f ? y : y * sl;
+          if (p.res) y += __half2float(p.res[pix * p.res_cs + p.res_coff + cout]);
+          if (p.out_f32) p.out_f32[pix * p.out_cs + p.out_coff + cout] = y;
+          else p.out[pix * p.out_cs + p.out_coff + cout] = __float2half_rn(y);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(p.tmem_cols) : "memory");
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 patch_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    TR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q));
+    TR_CHECK(q == cudaDriverEntryPointSuccess && ptr, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+}  // namespace
+
+struct ConvPatchPlan {
+  CUtensorMap tmX, tmW;
+  PatchParams p;
+  int grid;
+  uint32_t smem;
+  double flops;
+};
+
+bool conv_patch_eligible(const ConvArgs& a) {
+  if (a.stride != 1 || a.kh != a.kw || !(a.kh & 1) || a.pad != a.kh / 2 || a.kh > 9) return false;
+  if (a.cin_pad % 64 || a.cout_pad % 128) return false;
+  if (a.in.cs % 8 || a.in.coff % 8) return false;
+  if (a.out2.ptr || a.res_up2) return false;
+  if (a.H_out != a.in.H || a.W_out != a.in.W) return false;
+  return true;
+}
+
+ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
+  TR_CHECK(conv_patch_eligible(a), "convolution not eligible for the patch kernel");
+  auto* plan = new ConvPatchPlan();
+  PatchParams& p = plan->p;
+  p = PatchParams{};
+  p.N = a.in.N; p.H = a.H_out; p.W = a.W_out;
+  p.k = a.kh; p.pad = a.pad; p.taps = a.kh * a.kw;
+  p.cin_pad = a.cin_pad; p.kchunks = a.cin_pad / 64; p.in_coff = a.in.coff;
+  p.cout_tiles = a.cout_pad / 128;
+  p.PA = a.pad == 0 ? 8 : 16;
+
+  int sms = 0, dev = 0;
+  TR_CUDA(cudaGetDevice(&dev));
+  TR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+  // Tile geometry: 8-pixel groups along one axis, R (even, <= 32) rows of groups along the
+  // other; pick the (axis, R) that wastes the fewest MMA columns, preferring wide tiles
+  // (N = 8 R >= 192 amortises the filter stream: 16 KB of L2 -> SM traffic per 4 N cycles).
+  const int force_axis = env_int("TRB_PT_AXIS", -1), force_r = env_int("TRB_PT_R", 0);
+  double best = -1.0;
+  const int halo = 2 * a.pad;
+  for (int axis = 0; axis < 2; ++axis) {
+    if (force_axis >= 0 && axis != force_axis) continue;
+    const int A = axis == 0 ? p.W : p.H, B = axis == 0 ? p.H : p.W;
+    for (int R = 2; R <= 32; R += 2) {
+      if (force_r && R != force_r) continue;
+      const uint32_t patch = round_up(p.PA * (R + halo) * 128, 1024);
+      if (2 * patch + 3 * kFilterBlock + 4096 > 227u * 1024) continue;
+      const double util = double(A) / (8.0 * ceil_div(A, 8)) * double(B) / (double(R) * ceil_div(B, R));
+      const double wide = std::min(1.0, (8.0 * R + 64.0) / 256.0);     // N = 192 and up count as full
+      const double score = util * wide + 1e-4 * R;
+      if (score > best) { best = score; p.axis = axis; p.R = R; }
+    }
+  }
+  TR_CHECK(best > 0, "no patch tile fits in shared memory");
+  p.NP = 8 * p.R;
+  const int A = p.axis == 0 ? p.W : p.H, B = p.axis == 0 ? p.H : p.W;
+  p.tiles_a = ceil_div(A, 8);
+  p.tiles_b = ceil_div(B, p.R);
+  p.pix_tiles = p.tiles_a * p.tiles_b * p.N;
+  p.total_tiles = p.pix_tiles * p.cout_tiles;
+  p.patch_tx = p.PA * (p.R + halo) * 128;
+  p.patch_bytes = round_up(p.patch_tx, 1024);
+  p.ring_off = 2 * p.patch_bytes;
+  p.sub = std::max(1, std::min(env_int("TRB_PT_SUB", 1), p.taps));
+  p.iters = ceil_div(p.taps, p.sub);
+  p.stage_bytes = p.sub * kFilterBlock;
+  const uint32_t fixed = p.ring_off + 512 + 8 * (2 * kPMaxStages + 10) + 1024 /*alignment*/;
+  p.stages = std::min(kPMaxStages, int((227u * 1024 - fixed) / p.stage_bytes));
+  p.stages = std::min(p.stages, std::max(2, env_int("TRB_PT_STAGES", kPMaxStages)));
+  TR_CHECK(p.stages >= 2, "filter ring does not fit");
+  p.idesc = (1u << 4) | (uint32_t(p.NP >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+  uint32_t cols = 32;
+  while (cols < uint32_t(2 * p.NP)) cols <<= 1;
+  p.tmem_cols = cols;
+
+  p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.act = a.act;
+  p.out = a.out.ptr; p.out_cs = a.out.cs; p.out_coff = a.out.coff; p.cout_store = a.cout_store;
+  p.res = a.res.ptr; p.res_cs = a.res.cs; p.res_coff = a.res.coff;
+  p.out_f32 = a.out_f32;
+  p.err = err_flag;
+  p.pdl_late = env_int("TRB_TC_PDL_LATE", 1);
+  p.debug = env_int("TRB_PT_DEBUG", 0);
+  TR_CHECK(a.scale && a.shift, "epilogue scale/shift are required");
+  TR_CHECK(a.act != ACT_PRELU || a.slope, "PReLU needs slopes");
+
+  auto encode = patch_encode_fn();
+  const cuuint64_t cs = a.in.cs, W = a.in.W, H = a.in.H, N = a.in.N;
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t box[4] = {64, cuuint32_t(p.PA), cuuint32_t(p.R + halo), 1}, estr[4] = {1, 1, 1, 1};
+  gdim[0] = cs; gdim[3] = N;
+  gstr[2] = H * W * cs * 2;
+  if (p.axis == 0) { gdim[1] = W; gdim[2] = H; gstr[0] = cs * 2; gstr[1] = W * cs * 2; }
+  else             { gdim[1] = H; gdim[2] = W; gstr[0] = W * cs * 2; gstr[1] = cs * 2; }
+  CUresult r = encode(&plan->tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.in.ptr, gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(patch) failed: " + std::to_string(int(r)));
+  const cuuint64_t ktot = cuuint64_t(p.taps) * a.cin_pad;
+  cuuint64_t wdim[2] = {ktot, cuuint64_t(a.cout_pad)};
+  cuuint64_t wstr[1] = {ktot * 2};
+  cuuint32_t wbox[2] = {64, 128};
+  r = encode(&plan->tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(a.w), wdim, wstr, wbox,
+             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(filters) failed: " + std::to_string(int(r)));
+
+  plan->grid = std::min(p.total_tiles, sms);
+  plan->smem = fixed + p.stages * p.stage_bytes;
+  plan->flops = 2.0 * p.N * p.H * p.W * double(a.cout_pad) * p.taps * a.cin_pad;
+  static bool attr_set[16] = {};
+  if (dev < 16 && !attr_set[dev]) {
+    TR_CUDA(cudaFuncSetAttribute(conv_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[dev] = true;
+  }
+  return plan;
+}
+
+void conv_patch_plan_destroy(ConvPatchPlan* p) { delete p; }
+
+void conv_patch_plan_describe(const ConvPatchPlan* plan, int* axis, int* R, int* tiles, int* stages) {
+  *axis = plan->p.axis; *R = plan->p.R; *tiles = plan->p.total_tiles; *stages = plan->p.stages;
+}
+
+void conv_patch_launch(const ConvPatchPlan* plan, cudaStream_t s) {
+  static const bool pdl = env_int("TRB_TC_PDL", 1) != 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(plan->grid);
+  cfg.blockDim = dim3(kPThreads);
+  cfg.dynamicSmemBytes = plan->smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel, plan->tmX, plan->tmW, plan->p));
+}
+
+}  // namespace trb

@@ -33,6 +33,7 @@ struct PreparedOp {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   ConvArgs conv;
   ConvTcPlan* tc = nullptr;
+  ConvPatchPlan* pt = nullptr;   // TR_OP_CONV on the resident-patch tcgen05 kernel
   StemArgs stem;
   DwArgs dw;
   SepArgs sep;
@@ -50,6 +51,7 @@ struct Plan {
   ~Plan() {
     for (auto& o : ops) {
       if (o.tc) conv_tc_plan_destroy(o.tc);
+      if (o.pt) conv_patch_plan_destroy(o.pt);
       if (o.sep_tmp) cudaFree(o.sep_tmp);
       if (o.e0) cudaEventDestroy(o.e0);
       if (o.e1) cudaEventDestroy(o.e1);
@@ -105,6 +107,15 @@ const T* blob_ptr(const tr_net* net, int64_t off) {
 bool mma_enabled() {
   static const bool on = [] { const char* e = getenv("TRB_MMA"); return !e || atoi(e) != 0; }();
   return on;
+}
+
+// TRB_PATCH: 0 = never, 1 = auto (layers where the resident-patch kernel measured faster),
+// 2 = every eligible layer.
+bool patch_wanted(const ConvArgs& a) {
+  static const int mode = [] { const char* e = getenv("TRB_PATCH"); return e ? atoi(e) : 0; }();
+  if (!mode || !conv_patch_eligible(a)) return false;
+  if (mode >= 2) return true;
+  return a.kh >= 3;
 }
 
 View make_view(const Buf& b, int coff, int C) {
@@ -229,7 +240,11 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
         po.mma = !net->force_direct && !d.force_direct && d.engine == TR_ENGINE_MMA && mma_enabled() &&
                  conv_mma_eligible(a);
         const bool use_tc = !po.mma && !net->force_direct && !d.force_direct && conv_tc_eligible(a);
-        if (use_tc) {
+        if (use_tc && patch_wanted(a)) {
+          po.pt = conv_patch_plan_create(a, conv_tc_error_flag());
+          plan->tc_flops += po.flops;
+          plan->tc_launches++;
+        } else if (use_tc) {
           void*& scratch = net->sk_scratch[d.lane == 1];
           if (!scratch) {
             TR_CUDA(cudaMalloc(&scratch, conv_tc_sk_scratch_bytes()));
@@ -354,7 +369,8 @@ void run_plan(tr_net* net, Plan* plan, const uint8_t* image, int64_t sn, int64_t
         break;
       }
       case TR_OP_CONV:
-        if (po.tc) conv_tc_launch(po.tc, s);
+        if (po.pt) conv_patch_launch(po.pt, s);
+        else if (po.tc) conv_tc_launch(po.tc, s);
         else if (po.mma) conv_mma_launch(po.conv, s);
         else conv_direct_launch(po.conv, s);
         break;
@@ -504,7 +520,7 @@ int tr_net_profile(tr_net* net, float* ms, int32_t* is_tc, double* flops, int ca
       TR_CUDA(cudaEventSynchronize(po.e1));
       if (n < cap) {
         TR_CUDA(cudaEventElapsedTime(ms + n, po.e0, po.e1));
-        is_tc[n] = po.tc ? 1 : 0;
+        is_tc[n] = (po.tc || po.pt) ? 1 : 0;
         flops[n] = po.flops;
       }
       ++n;
@@ -542,12 +558,14 @@ int tr_conv2d(const void* in_dev, int N, int H, int W, int in_cs, int in_coff, i
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     ConvTcPlan* plan = nullptr;
     if (use_tc == 1) plan = conv_tc_plan_create(a);
+    ConvPatchPlan* pplan = use_tc == 3 ? conv_patch_plan_create(a, conv_tc_error_flag()) : nullptr;
     if (use_tc == 2) TR_CHECK(conv_mma_eligible(a), "layer not supported by the mma.sync kernel");
     cudaEvent_t e0, e1;
     TR_CUDA(cudaEventCreate(&e0));
     TR_CUDA(cudaEventCreate(&e1));
     auto once = [&] {
       if (plan) conv_tc_launch(plan, s);
+      else if (pplan) conv_patch_launch(pplan, s);
       else if (use_tc == 2) conv_mma_launch(a, s);
       else conv_direct_launch(a, s);
     };
@@ -557,6 +575,7 @@ int tr_conv2d(const void* in_dev, int N, int H, int W, int in_cs, int in_coff, i
     TR_CUDA(cudaEventRecord(e1, s));
     cudaError_t err = cudaStreamSynchronize(s);
     if (plan) conv_tc_plan_destroy(plan);
+    if (pplan) conv_patch_plan_destroy(pplan);
     if (err != cudaSuccess)
       fail(std::string("conv launch failed: ") + cudaGetErrorString(err) + " (pipeline timeout code " +
            std::to_string(conv_tc_last_timeout()) + ")");
