@@ -30,6 +30,17 @@ struct Error : std::runtime_error {
     if (!(cond)) ::trb::fail(std::string("check failed: ") + #cond + ": " + (msg)); \
   } while (0)
 
+// Per-device caches (function attributes, constant tables, SM counts) are indexed by the
+// CUDA device ordinal: every model class accepts an arbitrary device=.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) fail(std::string("cudaGetDevice -> ") + cudaGetErrorString(e));
+  if (dev < 0 || dev >= kMaxDevices) fail("device ordinal out of range: " + std::to_string(dev));
+  return dev;
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

@@ -34,6 +34,7 @@
 #include <cudaTypedefs.h>
 
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -46,6 +47,7 @@ constexpr int kPThreads = 352;
 constexpr int kPEpiWarps = 8;
 constexpr int kPMaxStages = 12;
 constexpr uint32_t kFilterBlock = 128 * 64 * 2;      // one (tap, chunk) filter block: 16 KB
+constexpr uint32_t kOutStage = 2 * 4096;             // per team: 16 pixels x 128 couts fp16
 
 struct PatchParams {
   int N, H, W;                 // output == input dims (stride 1, "same" padding)
@@ -57,6 +59,7 @@ struct PatchParams {
   int tiles_a, tiles_b, pix_tiles, total_tiles;
   int sub, iters, stages;      // taps per ring stage, stages per chunk, ring depth
   uint32_t stage_bytes, patch_bytes, patch_tx, ring_off;
+  int tma_store;               // 1: epilogue transposes through smem and stores with TMA (UTMASTG)
   uint32_t idesc, tmem_cols;
   const float* scale; const float* shift; const float* slope;
   int act;
@@ -65,7 +68,9 @@ struct PatchParams {
   float* out_f32;
   int* err;
   int pdl_late;
-  int debug;                   // timing experiments: 1 no filter TMA, 2 no MMA, 4 no stores
+  unsigned long long* trace;   // debug & 32: globaltimer stamps of CTA 0, 16 per launch
+  int debug;                   // timing experiments: 1 no filter TMA, 2 no MMA, 4 no stores,
+                               // 8 no ring-release handshake (with 1), 16 no full-barrier waits (with 1)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
@@ -85,6 +90,18 @@ __device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&v)[8])
       : "r"(taddr));
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// debug & 32: one lane of CTA 0 stamps event `ev` of this launch
+#define PT_STAMP(ev)                                                             \
+  do {                                                                           \
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0)                   \
+      p.trace[1 + 16 * (trace_slot & 63) + (ev)] = global_ns();                  \
+  } while (0)
+
 struct TileCoord {
   int ct, n, a0, b0;
 };
@@ -102,11 +119,12 @@ __device__ __forceinline__ TileCoord tile_coord(const PatchParams& p, int tile) 
 
 __global__ void __launch_bounds__(kPThreads, 1)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                  const PatchParams p) {
+                  const __grid_constant__ CUtensorMap tmO, const PatchParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // two patch buffers first
   const uint32_t ring = base + p.ring_off;
-  const uint32_t tab_s = ring + p.stages * p.stage_bytes;           // per-tap descriptor offsets
+  const uint32_t stage_out = ring + p.stages * p.stage_bytes;       // epilogue staging: 2 teams x 4 KB
+  const uint32_t tab_s = stage_out + kOutStage;                     // per-tap descriptor offsets
   const uint32_t bars = tab_s + 512u;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kPMaxStages + s); };
@@ -118,10 +136,17 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  volatile unsigned* trace_slot_s =
+      reinterpret_cast<volatile unsigned*>(smem_raw + (bars + 8u * (2 * kPMaxStages + 9) - smem_u32(smem_raw)));
+  if (p.trace && threadIdx.x == 0) {
+    *trace_slot_s = blockIdx.x == 0 ? static_cast<unsigned>(atomicAdd(p.trace, 1ULL)) : 0u;
+    if (blockIdx.x == 0) p.trace[1 + 16 * (*trace_slot_s & 63) + 0] = global_ns();
+  }
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -154,6 +179,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  const unsigned trace_slot = p.trace ? *trace_slot_s : 0u;
+  if (warp == 3) PT_STAMP(1);                               // prologue done
 
   const int grid = gridDim.x;
   // Every role loop runs with the whole warp converged; one elected lane issues (see
@@ -171,7 +198,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         int tap = 0;
         for (int it = 0; it < p.iters; ++it) {
           const int nsub = min(p.sub, p.taps - tap);
-          mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
+          if (!(p.debug & 8)) mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
           const uint32_t dst = ring + stage * p.stage_bytes;
           if (p.debug & 1) {
             if (elect_one()) mbar_arrive(full_bar(stage));
@@ -190,6 +217,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   } else if (warp == 10) {
     // ----------------------------------------------------------- patch producer
     asm volatile("griddepcontrol.wait;" ::: "memory");      // activations of the previous layer
+    PT_STAMP(2);                                            // previous grid complete
     int q = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid) {
       const TileCoord t = tile_coord(p, tile);
@@ -221,11 +249,12 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int kc = 0; kc < p.kchunks; ++kc, ++q) {
         const int buf = q & 1;
         mbar_wait(pfull_bar(buf), (q >> 1) & 1u, p.err, 6);
+        if (q == 0) PT_STAMP(3);                            // first patch landed
         const uint32_t patch_lo = umma_desc_lo(base + buf * p.patch_bytes);
         int tap = 0;
         for (int it = 0; it < p.iters; ++it) {
           const int nsub = min(p.sub, p.taps - tap);
-          mbar_wait(full_bar(stage), phase, p.err, 3);
+          if (!(p.debug & 16)) mbar_wait(full_bar(stage), phase, p.err, 3);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
             const uint32_t w_lo0 = ring_lo + stage * stage_step;
@@ -242,7 +271,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 }
               }
             }
-            umma_commit(empty_bar(stage));
+            if (!(p.debug & 8)) umma_commit(empty_bar(stage));
             if (it == p.iters - 1) {
               umma_commit(pempty_bar(buf));
               if (kc == p.kchunks - 1) umma_commit(tfull_bar(acc));
@@ -253,56 +282,116 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
+      PT_STAMP(4);                                          // all MMAs of a tile issued
     }
   } else {
     // ----------------------------------------------------------------- epilogue
     asm volatile("griddepcontrol.wait;" ::: "memory");      // residual reads / buffer re-use
     const int ew = warp - 2;
     const int qd = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                // which half of the pixel groups it takes
-    const int g_begin = half * (p.R >> 1), g_end = g_begin + (p.R >> 1);
+    const int team = ew >> 2;                // which half of the pixel groups its four warps take
+    const int g_begin = team * (p.R >> 1), g_end = g_begin + (p.R >> 1);
     const int A_dim = p.axis == 0 ? p.W : p.H, B_dim = p.axis == 0 ? p.H : p.W;
-    const long a_step = p.axis == 0 ? 1 : p.W;           // pixel-index step along the group axis
-    const long b_step = p.axis == 0 ? p.W : 1;
+    const int a_step = p.axis == 0 ? 1 : p.W;             // pixel-index step along the group axis
+    const int b_step = p.axis == 0 ? p.W : 1;
+    const uint32_t my_stage = stage_out + team * 4096u;   // [16 pixels][128 couts] fp16
+    const bool store_leader = (ew & 3) == 0 && lane == 0;
     int tile_it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++tile_it) {
       const int acc = tile_it & 1;
       const TileCoord t = tile_coord(p, tile);
-      const int cout = t.ct * 128 + qd * 32 + lane;
+      const int cl = qd * 32 + lane;                       // cout within the tile
+      const int cout = t.ct * 128 + cl;
       const float sc = p.scale[cout], sh = p.shift[cout];
-      const float sl = p.slope ? p.slope[cout] : 0.f;
-      const bool c_ok = cout < p.cout_store;
-      const long pix00 = static_cast<long>(t.n) * p.H * p.W + t.a0 * a_step + t.b0 * b_step;
+      // one activation formula: y = max(y, 0) + neg * min(y, 0)   (ReLU 0, PReLU slope, none 1)
+      const float neg = p.act == ACT_RELU ? 0.f : (p.act == ACT_PRELU ? p.slope[cout] : 1.f);
       mbar_wait(tfull_bar(acc), (tile_it >> 1) & 1u, p.err, 4);
+      if (warp == 2) PT_STAMP(5);                           // accumulator complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * p.NP;
-      for (int g = g_begin; g < g_end; ++g) {
-        uint32_t v[8];
-        __syncwarp();
-        tmem_ld8_async(taddr + g * 8, v);
-        tmem_ld_wait();
-        if (t.b0 + g >= B_dim || !c_ok || (p.debug & 4)) continue;
-        const long pix0 = pix00 + g * b_step;
+      if (p.tma_store) {
+        // Two groups (16 pixels) at a time: TMEM -> registers -> [pixel][cout] tile in shared
+        // memory (a warp writes 64 contiguous bytes per pixel: conflict-free) -> one TMA store
+        // per 8-pixel group (2 KB runs in HBM; the tensor map clips the ragged border).
+        for (int g = g_begin; g < g_end; g += 2) {
+          uint32_t v[16];
+          __syncwarp();
+          tmem_ld16_async(taddr + g * 8, v);
+          tmem_ld_wait();
+          uint32_t h[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (t.a0 + i >= A_dim) break;
-          const long pix = pix0 + i * a_step;
-          float y = fmaf(__uint_as_float(v[i]), sc, sh);
-          if (p.act == ACT_RELU) y = fmaxf(y, 0.f);
-          else if (p.act == ACT_PRELU) y = y >= 0.f ? y : y * sl;
-          if (p.res) y += __half2float(p.res[pix * p.res_cs + p.res_coff + cout]);
-          if (p.out_f32) p.out_f32[pix * p.out_cs + p.out_coff + cout] = y;
-          else p.out[pix * p.out_cs + p.out_coff + cout] = __float2half_rn(y);
+          for (int i = 0; i < 8; ++i) {
+            float y0 = fmaf(__uint_as_float(v[2 * i]), sc, sh);
+            float y1 = fmaf(__uint_as_float(v[2 * i + 1]), sc, sh);
+            y0 = fmaf(fminf(y0, 0.f), neg, fmaxf(y0, 0.f));
+            y1 = fmaf(fminf(y1, 0.f), neg, fmaxf(y1, 0.f));
+            const __half2 hh = __floats2half2_rn(y0, y1);   // .x = pixel 2i, .y = pixel 2i + 1
+            h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
+          // the previous store of this team has finished READING the staging tile
+          if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
+          const uint32_t dst = my_stage + cl * 2u;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + (2 * i) * 256u),
+                         "h"(static_cast<unsigned short>(h[i] & 0xffffu)) : "memory");
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + (2 * i + 1) * 256u),
+                         "h"(static_cast<unsigned short>(h[i] >> 16)) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
+          if (store_leader && !(p.debug & 4)) {
+#pragma unroll
+            for (int gg = 0; gg < 2; ++gg) {
+              const int b = t.b0 + g + gg;
+              if (g + gg < g_end && b < B_dim) {
+                const int cw = p.axis == 0 ? t.a0 : b, ch = p.axis == 0 ? b : t.a0;
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                    ::"l"(&tmO), "r"(my_stage + gg * 2048u), "r"(p.out_coff + t.ct * 128), "r"(cw),
+                      "r"(ch), "r"(t.n) : "memory");
+              }
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else {
+        const bool c_ok = cout < p.cout_store;
+        const unsigned pix00 = static_cast<unsigned>(t.n) * p.H * p.W + t.a0 * a_step + t.b0 * b_step;
+        const int na = min(8, A_dim - t.a0);
+        for (int g = g_begin; g < g_end; ++g) {
+          uint32_t v[8];
+          __syncwarp();
+          tmem_ld8_async(taddr + g * 8, v);
+          tmem_ld_wait();
+          if (t.b0 + g >= B_dim || !c_ok || (p.debug & 4)) continue;
+          const unsigned pix0 = pix00 + g * b_step;
+          const unsigned o0 = pix0 * p.out_cs + p.out_coff + cout, os = a_step * p.out_cs;
+          const unsigned r0 = pix0 * p.res_cs + p.res_coff + cout, rs = a_step * p.res_cs;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < na) {
+              float y = fmaf(__uint_as_float(v[i]), sc, sh);
+              y = fmaf(fminf(y, 0.f), neg, fmaxf(y, 0.f));
+              if (p.res) y += __half2float(p.res[r0 + i * rs]);
+              if (p.out_f32) p.out_f32[o0 + i * os] = y;
+              else p.out[o0 + i * os] = __float2half_rn(y);
+            }
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (warp == 2) PT_STAMP(6);                           // epilogue of a tile done
     }
+    if (p.tma_store && store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (warp == 3) PT_STAMP(7);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -330,7 +419,8 @@ int env_int(const char* name, int dflt) {
 }  // namespace
 
 struct ConvPatchPlan {
-  CUtensorMap tmX, tmW;
+  unsigned long long* trace = nullptr;
+  CUtensorMap tmX, tmW, tmO;
   PatchParams p;
   int grid;
   uint32_t smem;
@@ -357,8 +447,8 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   p.cout_tiles = a.cout_pad / 128;
   p.PA = a.pad == 0 ? 8 : 16;
 
-  int sms = 0, dev = 0;
-  TR_CUDA(cudaGetDevice(&dev));
+  int sms = 0;
+  const int dev = current_device();
   TR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
   // Tile geometry: 8-pixel groups along one axis, R (even, <= 32) rows of groups along the
@@ -373,7 +463,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
     for (int R = 2; R <= 32; R += 2) {
       if (force_r && R != force_r) continue;
       const uint32_t patch = round_up(p.PA * (R + halo) * 128, 1024);
-      if (2 * patch + 3 * kFilterBlock + 4096 > 227u * 1024) continue;
+      if (2 * patch + 3 * kFilterBlock + kOutStage + 4096 > 227u * 1024) continue;
       const double util = double(A) / (8.0 * ceil_div(A, 8)) * double(B) / (double(R) * ceil_div(B, R));
       const double wide = std::min(1.0, (8.0 * R + 64.0) / 256.0);     // N = 192 and up count as full
       const double score = util * wide + 1e-4 * R;
@@ -390,10 +480,10 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   p.patch_tx = p.PA * (p.R + halo) * 128;
   p.patch_bytes = round_up(p.patch_tx, 1024);
   p.ring_off = 2 * p.patch_bytes;
-  p.sub = std::max(1, std::min(env_int("TRB_PT_SUB", 1), p.taps));
+  p.sub = std::max(1, std::min(env_int("TRB_PT_SUB", 2), p.taps));
   p.iters = ceil_div(p.taps, p.sub);
   p.stage_bytes = p.sub * kFilterBlock;
-  const uint32_t fixed = p.ring_off + 512 + 8 * (2 * kPMaxStages + 10) + 1024 /*alignment*/;
+  const uint32_t fixed = p.ring_off + kOutStage + 512 + 8 * (2 * kPMaxStages + 10) + 1024 /*alignment*/;
   p.stages = std::min(kPMaxStages, int((227u * 1024 - fixed) / p.stage_bytes));
   p.stages = std::min(p.stages, std::max(2, env_int("TRB_PT_STAGES", kPMaxStages)));
   TR_CHECK(p.stages >= 2, "filter ring does not fit");
@@ -409,8 +499,15 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   p.err = err_flag;
   p.pdl_late = env_int("TRB_TC_PDL_LATE", 1);
   p.debug = env_int("TRB_PT_DEBUG", 0);
+  if (p.debug & 32) {
+    TR_CUDA(cudaMalloc(&plan->trace, (1 + 16 * 64) * 8));
+    TR_CUDA(cudaMemset(plan->trace, 0, (1 + 16 * 64) * 8));
+    p.trace = plan->trace;
+  }
   TR_CHECK(a.scale && a.shift, "epilogue scale/shift are required");
   TR_CHECK(a.act != ACT_PRELU || a.slope, "PReLU needs slopes");
+  TR_CHECK(double(p.N) * p.H * p.W * std::max(a.out.cs, a.res.cs) < 4.0e9,
+           "activation tensor too large for 32-bit element offsets");
 
   auto encode = patch_encode_fn();
   const cuuint64_t cs = a.in.cs, W = a.in.W, H = a.in.H, N = a.in.N;
@@ -433,18 +530,53 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(filters) failed: " + std::to_string(int(r)));
 
+  // TMA-store epilogue: plain fp16 output of whole 128-channel tiles (no residual); the 4-D map
+  // {C, W, H, N} clips the ragged border of the 8-pixel groups.
+  p.tma_store = env_int("TRB_PT_TMA_STORE", 1) && !a.res.ptr && !a.out_f32 && a.cout_store % 128 == 0 &&
+                a.out.cs % 8 == 0 && a.out.coff % 8 == 0;
+  plan->tmO = plan->tmW;
+  if (p.tma_store) {
+    const cuuint64_t ocs = a.out.cs;
+    cuuint64_t odim[4] = {ocs, W, H, N};
+    cuuint64_t ostr[3] = {ocs * 2, W * ocs * 2, H * W * ocs * 2};
+    cuuint32_t obox[4] = {128, cuuint32_t(p.axis == 0 ? 8 : 1), cuuint32_t(p.axis == 0 ? 1 : 8), 1};
+    r = encode(&plan->tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.out.ptr, odim, ostr, obox, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(output) failed: " + std::to_string(int(r)));
+  }
+
   plan->grid = std::min(p.total_tiles, sms);
   plan->smem = fixed + p.stages * p.stage_bytes;
   plan->flops = 2.0 * p.N * p.H * p.W * double(a.cout_pad) * p.taps * a.cin_pad;
-  static bool attr_set[16] = {};
-  if (dev < 16 && !attr_set[dev]) {
+  static bool attr_set[kMaxDevices] = {};
+  if (!attr_set[dev]) {
     TR_CUDA(cudaFuncSetAttribute(conv_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev] = true;
   }
   return plan;
 }
 
-void conv_patch_plan_destroy(ConvPatchPlan* p) { delete p; }
+void conv_patch_plan_destroy(ConvPatchPlan* p) {
+  if (p->trace) {
+    // CTA 0's event times relative to its kernel entry, and the gap to the previous launch's end
+    std::vector<unsigned long long> h(1 + 16 * 64);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h.data(), p->trace, h.size() * 8, cudaMemcpyDeviceToHost);
+    const int n = int(std::min<unsigned long long>(h[0], 64));
+    printf("patch trace (CTA 0, us from kernel entry): gap_prev prologue dep_wait patch0 mma_issued acc_done epi_done end\n");
+    for (int i = 0; i < n; ++i) {
+      const unsigned long long* e = &h[1 + 16 * i];
+      const double gap = i ? (double(e[0]) - double(h[1 + 16 * (i - 1) + 7])) / 1e3 : 0.0;
+      printf("  launch %2d: %7.2f", i, gap);
+      for (int k = 1; k <= 7; ++k) printf(" %7.2f", e[k] ? (double(e[k]) - double(e[0])) / 1e3 : -1.0);
+      printf("\n");
+    }
+    fflush(stdout);
+    cudaFree(p->trace);
+  }
+  delete p;
+}
 
 void conv_patch_plan_describe(const ConvPatchPlan* plan, int* axis, int* R, int* tiles, int* stages) {
   *axis = plan->p.axis; *R = plan->p.R; *tiles = plan->p.total_tiles; *stages = plan->p.stages;
@@ -462,7 +594,7 @@ void conv_patch_launch(const ConvPatchPlan* plan, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel, plan->tmX, plan->tmW, plan->p));
+  TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel, plan->tmX, plan->tmW, plan->tmO, plan->p));
 }
 
 }  // namespace trb

@@ -1254,23 +1254,21 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 // still read it after the trap has killed the context (device allocations are gone by then).
 int* g_err_host = nullptr;
 int* tc_error_flag() {
-  static int* flag = nullptr;
-  if (!flag) {
-    TR_CUDA(cudaHostAlloc(&g_err_host, sizeof(int), cudaHostAllocMapped));
+  static int* flag[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!g_err_host) {
+    TR_CUDA(cudaHostAlloc(&g_err_host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
     *g_err_host = 0;
-    TR_CUDA(cudaHostGetDevicePointer(&flag, g_err_host, 0));
   }
-  return flag;
+  if (!flag[dev]) TR_CUDA(cudaHostGetDevicePointer(&flag[dev], g_err_host, 0));
+  return flag[dev];
 }
 
 int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    TR_CUDA(cudaGetDevice(&dev));
-    TR_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-  }
-  return n;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!n[dev]) TR_CUDA(cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev));
+  return n[dev];
 }
 
 using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const TcParams);
@@ -1279,11 +1277,12 @@ KernelFn kernel_for(int kc, int ctas_per_sm) {
   KernelFn fn = ctas_per_sm == 2
                     ? (kc == 64 ? conv_tc_kernel<4, 2> : (kc == 32 ? conv_tc_kernel<2, 2> : conv_tc_kernel<1, 2>))
                     : (kc == 64 ? conv_tc_kernel<4, 1> : (kc == 32 ? conv_tc_kernel<2, 1> : conv_tc_kernel<1, 1>));
-  static bool attr_set[6] = {false, false, false, false, false, false};
+  static bool attr_set[kMaxDevices][6] = {};
   const int slot = (kc == 64 ? 0 : (kc == 32 ? 1 : 2)) + (ctas_per_sm == 2 ? 3 : 0);
-  if (!attr_set[slot]) {
+  const int dev = current_device();
+  if (!attr_set[dev][slot]) {
     TR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[slot] = true;
+    attr_set[dev][slot] = true;
   }
   return fn;
 }
@@ -1631,11 +1630,12 @@ int conv_tc_last_timeout() { return g_err_host ? *reinterpret_cast<volatile int*
 
 void conv_tc_launch(const ConvTcPlan* plan, cudaStream_t s) {
   if (plan->p.cta2) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!attr_set[dev]) {
       TR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024));
-      attr_set = true;
+      attr_set[dev] = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(plan->grid);

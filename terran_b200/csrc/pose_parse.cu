@@ -432,19 +432,22 @@ size_t pose_workspace_bytes(int N) {
 void pose_parse_launch(const float* paf, const float* heat, int N, int h, int w, double scale,
                        void* workspace, const PoseOut& out, cudaStream_t s) {
   if (N == 0) return;
-  static bool table_set = false;
+  // __constant__ memory and function attributes live per device / context
+  const int dev = current_device();
+  static bool table_set[kMaxDevices] = {};
   static float gain = 0.f;
-  if (!table_set) {
+  if (!table_set[dev]) {
     float tab[32];
     bicubic_table_host(tab);
     TR_CUDA(cudaMemcpyToSymbol(c_bicubic, tab, sizeof(tab)));
+    float gmax = 0.f;
     for (int ph = 0; ph < 8; ++ph) {
       float a = 0.f;
       for (int k = 0; k < 4; ++k) a += fabsf(tab[ph * 4 + k]);
-      gain = std::max(gain, a);
+      gmax = std::max(gmax, a);
     }
-    gain = gain * gain * 1.001f;
-    table_set = true;
+    gain = gmax * gmax * 1.001f;
+    table_set[dev] = true;
   }
   PoseParams p{};
   p.bicubic_gain = gain;
@@ -462,11 +465,11 @@ void pose_parse_launch(const float* paf, const float* heat, int N, int h, int w,
   TR_CUDA(cudaMemsetAsync(p.peak_cnt, 0, size_t(N) * 18 * 4, s));
   TR_CUDA(cudaMemsetAsync(out.status, 0, size_t(N) * 4, s));
   const size_t smem = size_t(15) * p.Wu * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  static size_t smem_set[kMaxDevices] = {};
+  if (smem > 48 * 1024 && smem > smem_set[dev]) {
     TR_CUDA(cudaFuncSetAttribute(pose_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(smem)));
-    smem_set = smem;
+    smem_set[dev] = smem;
   }
   pose_peaks_kernel<<<dim3(h, 18, N), 256, smem, s>>>(p);
   TR_CUDA(cudaGetLastError());

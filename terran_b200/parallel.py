@@ -40,6 +40,58 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def gpu_numa_cpus(device_index):
+    """(numa node, cpu ids) of the NUMA node the GPU's PCIe root hangs off, read from sysfs
+    (``/sys/bus/pci/devices/<bus id>/numa_node`` and ``/sys/devices/system/node/nodeN/cpulist``);
+    (None, None) when the platform does not say."""
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f'/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node'
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None, None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            spec = f.read().strip()
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None, None
+    cpus = []
+    for part in spec.split(','):
+        if '-' in part:
+            a, b = part.split('-')
+            cpus.extend(range(int(a), int(b) + 1))
+        elif part:
+            cpus.append(int(part))
+    return node, cpus
+
+
+def bind_to_gpu_numa(device_index, local_world=1):
+    """Pin this process to the CPUs of its GPU's NUMA node — its own slice of them when several
+    of the ``local_world`` ranks (GPU i = local rank i) share the node — BEFORE it allocates
+    pinned staging buffers, so that the host->device copies of every rank read local memory
+    instead of all ranks streaming from node 0.  Returns a dict describing the binding
+    (reported by bench.py); a no-op when the topology is unknown or the mask cannot change."""
+    node, cpus = gpu_numa_cpus(device_index)
+    info = {'numa_node': node, 'cpus': None}
+    if not cpus:
+        return info
+    peers = [i for i in range(max(local_world, device_index + 1)) if gpu_numa_cpus(i)[0] == node]
+    try:
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return info
+        share = max(1, len(allowed) // max(1, len(peers)))
+        slot = peers.index(device_index) if device_index in peers else 0
+        mine = allowed[slot * share:(slot + 1) * share] or allowed
+        os.sched_setaffinity(0, mine)
+        info['cpus'] = f'{mine[0]}-{mine[-1]} ({len(mine)})'
+    except (OSError, AttributeError):
+        pass
+    return info
+
+
 def _comm_device():
     if dist.is_initialized() and dist.get_backend() == 'nccl':
         return torch.device('cuda', torch.cuda.current_device())
