@@ -70,6 +70,12 @@ typedef struct tr_op_desc {
   int64_t dw_w16_off;               /* the same filter rounded to fp16 (fused kernel operand) */
   int32_t engine;                   /* TR_OP_CONV: TR_ENGINE_* */
   int32_t reserved;
+  /* TR_OP_CONV, 3x3 pad 1 stride 1: [9][cout_pad] fp32 border-class shifts replacing the
+   * shift vector, class = 3 * (first / inner / last output row) + (first / inner / last
+   * column).  How a BatchNorm that PRECEDES a zero-padded conv is folded into it exactly
+   * (arcface/model.py:11-14): its scale goes into the filters, its shift becomes a term that
+   * depends on which taps are in bounds.  -1 = none. */
+  int64_t shift9_off;
 } tr_op_desc;
 
 int tr_net_create(const tr_buffer_desc* buffers, int n_buffers, const tr_op_desc* ops, int n_ops,

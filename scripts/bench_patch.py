@@ -33,6 +33,20 @@ def run(tag, N, H, W, cin, cout, k, env, engine=3, repeat=20):
 
 
 MODE = sys.argv[1] if len(sys.argv) > 1 else 'sweep'
+if MODE == 'sk':
+    for sk in (0, 2):
+        run(f'openpose 7x7 128->128 sk={sk}', 32, 23, 40, 128, 128, 7, {'TRB_PT_SK': sk})
+        run(f'openpose 7x7 185->256 sk={sk}', 32, 23, 40, 192, 256, 7, {'TRB_PT_SK': sk})
+        run(f'vgg 3x3 512->512 @23x40 sk={sk}', 32, 23, 40, 512, 512, 3, {'TRB_PT_SK': sk})
+        run(f'vgg 3x3 256->256 @46x81 sk={sk}', 32, 46, 81, 256, 256, 3, {'TRB_PT_SK': sk})
+        run(f'vgg 3x3 128->128 @92x163 sk={sk}', 32, 92, 163, 128, 128, 3, {'TRB_PT_SK': sk})
+        run(f'openpose 3x3 128->128 @23x40 sk={sk}', 32, 23, 40, 128, 128, 3, {'TRB_PT_SK': sk})
+        run(f'openpose 1x1 128->512 @23x40 sk={sk}', 32, 23, 40, 128, 512, 1, {'TRB_PT_SK': sk})
+        run(f'arcface 3x3 256 @14 sk={sk}', 256, 14, 14, 256, 256, 3, {'TRB_PT_SK': sk})
+        run(f'arcface 3x3 512 @7 sk={sk}', 256, 7, 7, 512, 512, 3, {'TRB_PT_SK': sk})
+        run(f'arcface 3x3 128 @28 sk={sk}', 256, 28, 28, 128, 128, 3, {'TRB_PT_SK': sk})
+    run('trace openpose 7x7 128->128 sk=2', 32, 23, 40, 128, 128, 7, {'TRB_PT_SK': 2, 'TRB_PT_DEBUG': 32}, repeat=6)
+    sys.exit(0)
 if MODE == 'trace':
     run('trace 7x7 128->128 one tile/SM R=24 sub=2', 37, 24, 32, 128, 128, 7, {'TRB_PT_AXIS': 0, 'TRB_PT_R': 24, 'TRB_PT_SUB': 2, 'TRB_PT_DEBUG': 32}, repeat=8)
     run('trace openpose 7x7 128->128 sub=2', 32, 23, 40, 128, 128, 7, {'TRB_PT_SUB': 2, 'TRB_PT_DEBUG': 32}, repeat=8)

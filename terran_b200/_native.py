@@ -50,6 +50,7 @@ class OpDesc(C.Structure):
         ('dw_w_off', C.c_int64), ('dw_scale_off', C.c_int64), ('dw_shift_off', C.c_int64),
         ('dw_w16_off', C.c_int64),
         ('engine', C.c_int32), ('reserved', C.c_int32),
+        ('shift9_off', C.c_int64),
     ]
 
 

@@ -71,6 +71,9 @@ struct ConvArgs {
   const float* slope = nullptr;   // [cout_pad] (PReLU) or null
   const float* scale2 = nullptr;  // [cout_pad] or null
   const float* shift2 = nullptr;
+  // optional [9][cout_pad] border-class shifts replacing `shift` (3x3, pad 1, stride 1):
+  // class = 3 * (first / inner / last output row) + (first / inner / last output column)
+  const float* shift9 = nullptr;
   int cout_pad = 0;   // multiple of 16
   int cout_store = 0; // channels actually written (multiple of 8, <= cout_pad)
   int cin_pad = 0;    // multiple of 16

@@ -22,6 +22,7 @@ struct DirectParams {
   const __half* w; int cin_pad, kh, kw, stride, pad;
   const float* scale; const float* shift; const float* slope;
   const float* scale2; const float* shift2;
+  const float* shift9; int cout_pad;
   int act, H_out, W_out, cout_store;
   __half* out; int out_cs, out_coff;
   __half* out2; int out2_cs, out2_coff;
@@ -72,9 +73,14 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) 
     }
   }
   float y[8];
+  const float* shp = p.shift;
+  if (p.shift9) {
+    const int rc = oh == 0 ? 0 : (oh >= p.H_out - 1 ? 2 : 1), cc = ow == 0 ? 0 : (ow >= p.W_out - 1 ? 2 : 1);
+    shp = p.shift9 + (rc * 3 + cc) * p.cout_pad;
+  }
 #pragma unroll
   for (int o = 0; o < 8; ++o) {
-    const float t = fmaf(acc[o], __ldg(p.scale + c + o), __ldg(p.shift + c + o));
+    const float t = fmaf(acc[o], __ldg(p.scale + c + o), __ldg(shp + c + o));
     y[o] = act_f(t, p.act, p.act == ACT_PRELU ? __ldg(p.slope + c + o) : 0.f);
   }
   if (p.res) {
@@ -578,6 +584,7 @@ void conv_direct_launch(const ConvArgs& a, cudaStream_t s) {
   p.in = a.in.ptr; p.in_cs = a.in.cs; p.in_coff = a.in.coff; p.H = a.in.H; p.W = a.in.W; p.N = a.in.N;
   p.w = a.w; p.cin_pad = a.cin_pad; p.kh = a.kh; p.kw = a.kw; p.stride = a.stride; p.pad = a.pad;
   p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.scale2 = a.scale2; p.shift2 = a.shift2;
+  p.shift9 = a.shift9; p.cout_pad = a.cout_pad;
   p.act = a.act; p.H_out = a.H_out; p.W_out = a.W_out; p.cout_store = a.cout_store;
   p.out = a.out.ptr; p.out_cs = a.out.cs; p.out_coff = a.out.coff;
   p.out2 = a.out2.ptr; p.out2_cs = a.out2.cs; p.out2_coff = a.out2.coff;

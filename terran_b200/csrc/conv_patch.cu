@@ -60,6 +60,15 @@ struct PatchParams {
   int sub, iters, stages;      // taps per ring stage, stages per chunk, ring depth
   uint32_t stage_bytes, patch_bytes, patch_tx, ring_off;
   int tma_store;               // 1: epilogue transposes through smem and stores with TMA (UTMASTG)
+  // Stream-K: the CTAs split the launch's (tile, ring iteration) sequence into equal contiguous
+  // ranges instead of whole tiles, so no SM idles in a last partial round and a launch with
+  // fewer tiles than SMs still uses all of them (split-K).  A range that starts inside a tile
+  // computes that tile's remaining iterations FIRST, parks the raw fp32 accumulator in its
+  // workspace slot and raises its flag; the CTA that owns the tile's first iteration reaches
+  // it LAST in its own range, adds the parked partials in CTA order (deterministic) and runs
+  // the epilogue; the last of the 2 x kPEpiWarps warps that touch a flag re-arms it.
+  int sk, ipt;                 // ipt: ring iterations per tile = kchunks * iters
+  float* sk_ws; int* sk_flags;
   uint32_t idesc, tmem_cols;
   const float* scale; const float* shift; const float* slope;
   int act;
@@ -115,6 +124,40 @@ __device__ __forceinline__ TileCoord tile_coord(const PatchParams& p, int tile) 
   t.a0 = ta * 8;
   t.b0 = tb * p.R;
   return t;
+}
+
+// One CTA's sequence of tile segments [i0, i1) (in ring iterations of the tile).
+struct Walk {
+  long long pos, end;
+  int tile;
+};
+struct Seg {
+  int tile, i0, i1;
+};
+__device__ __forceinline__ Walk walk_begin(const PatchParams& p) {
+  Walk w;
+  const long long total = static_cast<long long>(p.total_tiles) * p.ipt;
+  w.pos = p.sk ? total * blockIdx.x / gridDim.x : 0;
+  w.end = p.sk ? total * (blockIdx.x + 1) / gridDim.x : 0;
+  w.tile = blockIdx.x;
+  return w;
+}
+__device__ __forceinline__ bool walk_next(const PatchParams& p, Walk& w, Seg& s) {
+  if (p.sk) {
+    if (w.pos >= w.end) return false;
+    s.tile = static_cast<int>(w.pos / p.ipt);
+    s.i0 = static_cast<int>(w.pos - static_cast<long long>(s.tile) * p.ipt);
+    s.i1 = static_cast<int>(min(static_cast<long long>(p.ipt), s.i0 + (w.end - w.pos)));
+    w.pos += s.i1 - s.i0;
+    return true;
+  }
+  if (w.tile >= p.total_tiles) return false;
+  s.tile = w.tile; s.i0 = 0; s.i1 = p.ipt;
+  w.tile += gridDim.x;
+  return true;
+}
+__device__ __forceinline__ bool walk_last(const PatchParams& p, const Walk& w) {
+  return p.sk ? w.pos >= w.end : w.tile >= p.total_tiles;
 }
 
 __global__ void __launch_bounds__(kPThreads, 1)
@@ -190,28 +233,29 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     if (!p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid) {
-      if (p.pdl_late && tile + grid >= p.total_tiles)
+    Walk w = walk_begin(p);
+    Seg sg;
+    while (walk_next(p, w, sg)) {
+      if (p.pdl_late && walk_last(p, w))
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-      const int ct = tile / p.pix_tiles;
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        int tap = 0;
-        for (int it = 0; it < p.iters; ++it) {
-          const int nsub = min(p.sub, p.taps - tap);
-          if (!(p.debug & 8)) mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
-          const uint32_t dst = ring + stage * p.stage_bytes;
-          if (p.debug & 1) {
-            if (elect_one()) mbar_arrive(full_bar(stage));
-          } else if (elect_one()) {
-            mbar_expect_tx(full_bar(stage), nsub * kFilterBlock);
-            for (int j = 0; j < nsub; ++j)
-              tma_load_2d(dst + j * kFilterBlock, &tmW, full_bar(stage),
-                          (tap + j) * p.cin_pad + kc * 64, ct * 128);
-          }
-          __syncwarp();
-          tap += nsub;
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      const int ct = sg.tile / p.pix_tiles;
+      int kc = sg.i0 / p.iters, it = sg.i0 - kc * p.iters;
+      for (int i = sg.i0; i < sg.i1; ++i) {
+        const int tap = it * p.sub;
+        const int nsub = min(p.sub, p.taps - tap);
+        mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 1);
+        const uint32_t dst = ring + stage * p.stage_bytes;
+        if (p.debug & 1) {
+          if (elect_one()) mbar_arrive(full_bar(stage));
+        } else if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), nsub * kFilterBlock);
+          for (int j = 0; j < nsub; ++j)
+            tma_load_2d(dst + j * kFilterBlock, &tmW, full_bar(stage),
+                        (tap + j) * p.cin_pad + kc * 64, ct * 128);
         }
+        __syncwarp();
+        if (++it == p.iters) { it = 0; ++kc; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 10) {
@@ -219,9 +263,12 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     asm volatile("griddepcontrol.wait;" ::: "memory");      // activations of the previous layer
     PT_STAMP(2);                                            // previous grid complete
     int q = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid) {
-      const TileCoord t = tile_coord(p, tile);
-      for (int kc = 0; kc < p.kchunks; ++kc, ++q) {
+    Walk w = walk_begin(p);
+    Seg sg;
+    while (walk_next(p, w, sg)) {
+      const TileCoord t = tile_coord(p, sg.tile);
+      const int kc0 = sg.i0 / p.iters, kc1 = (sg.i1 - 1) / p.iters;   // chunks the segment touches
+      for (int kc = kc0; kc <= kc1; ++kc, ++q) {
         const int buf = q & 1;
         mbar_wait(pempty_bar(buf), ((q >> 1) & 1u) ^ 1u, p.err, 5);
         if (elect_one()) {
@@ -240,49 +287,56 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t x_hi = umma_desc_hi(static_cast<uint32_t>(p.PA) * 128u, 2);   // one patch row per group
     const uint32_t ring_lo = umma_desc_lo(ring);
     const uint32_t stage_step = p.stage_bytes >> 4;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++tile_it) {
+    Walk w = walk_begin(p);
+    Seg sg;
+    for (; walk_next(p, w, sg); ++tile_it) {
       const int acc = tile_it & 1;
       mbar_wait(tempty_bar(acc), ((tile_it >> 1) & 1u) ^ 1u, p.err, 2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + acc * p.NP;
       uint32_t accumulate = 0;
-      for (int kc = 0; kc < p.kchunks; ++kc, ++q) {
-        const int buf = q & 1;
-        mbar_wait(pfull_bar(buf), (q >> 1) & 1u, p.err, 6);
-        if (q == 0) PT_STAMP(3);                            // first patch landed
-        const uint32_t patch_lo = umma_desc_lo(base + buf * p.patch_bytes);
-        int tap = 0;
-        for (int it = 0; it < p.iters; ++it) {
-          const int nsub = min(p.sub, p.taps - tap);
-          if (!(p.debug & 16)) mbar_wait(full_bar(stage), phase, p.err, 3);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (elect_one()) {
-            const uint32_t w_lo0 = ring_lo + stage * stage_step;
-            if (!(p.debug & 2)) {
-              for (int j = 0; j < nsub; ++j) {
-                uint32_t tap_off;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tap_off) : "r"(tab_s + 4u * (tap + j)));
-                const uint32_t x_lo = patch_lo + tap_off;
-                const uint32_t w_lo = w_lo0 + j * (kFilterBlock >> 4);
+      int kc = sg.i0 / p.iters, it = sg.i0 - kc * p.iters;
+      int buf = 0;
+      uint32_t patch_lo = 0;
+      bool need_patch = true;
+      for (int i = sg.i0; i < sg.i1; ++i) {
+        if (need_patch) {                                   // first iteration of a chunk in this segment
+          buf = q & 1;
+          mbar_wait(pfull_bar(buf), (q >> 1) & 1u, p.err, 6);
+          if (q == 0) PT_STAMP(3);                          // first patch landed
+          patch_lo = umma_desc_lo(base + buf * p.patch_bytes);
+          need_patch = false;
+        }
+        const int tap = it * p.sub;
+        const int nsub = min(p.sub, p.taps - tap);
+        const bool chunk_end = it == p.iters - 1 || i == sg.i1 - 1;
+        mbar_wait(full_bar(stage), phase, p.err, 3);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t w_lo0 = ring_lo + stage * stage_step;
+          if (!(p.debug & 2)) {
+            for (int j = 0; j < nsub; ++j) {
+              uint32_t tap_off;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tap_off) : "r"(tab_s + 4u * (tap + j)));
+              const uint32_t x_lo = patch_lo + tap_off;
+              const uint32_t w_lo = w_lo0 + j * (kFilterBlock >> 4);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {          // +32 B (two 16-byte units) per K = 16 step
-                  umma_f16(d_tmem, w_lo + 2 * ks, w_hi, x_lo + 2 * ks, x_hi, p.idesc, accumulate);
-                  accumulate = 1;
-                }
+              for (int ks = 0; ks < 4; ++ks) {            // +32 B (two 16-byte units) per K = 16 step
+                umma_f16(d_tmem, w_lo + 2 * ks, w_hi, x_lo + 2 * ks, x_hi, p.idesc, accumulate);
+                accumulate = 1;
               }
             }
-            if (!(p.debug & 8)) umma_commit(empty_bar(stage));
-            if (it == p.iters - 1) {
-              umma_commit(pempty_bar(buf));
-              if (kc == p.kchunks - 1) umma_commit(tfull_bar(acc));
-            }
           }
-          __syncwarp();
-          tap += nsub;
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          umma_commit(empty_bar(stage));
+          if (chunk_end) umma_commit(pempty_bar(buf));
+          if (i == sg.i1 - 1) umma_commit(tfull_bar(acc));
         }
+        __syncwarp();
+        if (chunk_end) { ++q; need_patch = true; }
+        if (++it == p.iters) { it = 0; ++kc; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
-      PT_STAMP(4);                                          // all MMAs of a tile issued
+      PT_STAMP(4);                                          // all MMAs of a segment issued
     }
   } else {
     // ----------------------------------------------------------------- epilogue
@@ -297,9 +351,11 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t my_stage = stage_out + team * 4096u;   // [16 pixels][128 couts] fp16
     const bool store_leader = (ew & 3) == 0 && lane == 0;
     int tile_it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++tile_it) {
+    Walk w = walk_begin(p);
+    Seg sg;
+    for (; walk_next(p, w, sg); ++tile_it) {
       const int acc = tile_it & 1;
-      const TileCoord t = tile_coord(p, tile);
+      const TileCoord t = tile_coord(p, sg.tile);
       const int cl = qd * 32 + lane;                       // cout within the tile
       const int cout = t.ct * 128 + cl;
       const float sc = p.scale[cout], sh = p.shift[cout];
@@ -309,15 +365,182 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (warp == 2) PT_STAMP(5);                           // accumulator complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * p.NP;
-      if (p.tma_store) {
+      if (sg.i0 > 0) {
+        // Stream-K: a tile whose first iterations belong to an earlier CTA.  Park the raw
+        // accumulator as [group][lane][8]: a warp writes 1 KB runs.
+        float4* ws = reinterpret_cast<float4*>(p.sk_ws + static_cast<size_t>(blockIdx.x) * 128 * p.NP);
+        for (int g = g_begin; g < g_end; ++g) {
+          uint32_t v[8];
+          __syncwarp();
+          tmem_ld8_async(taddr + g * 8, v);
+          tmem_ld_wait();
+          float4* dst = ws + (g * 128 + cl) * 2;
+          __stcg(dst, make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]),
+                                  __uint_as_float(v[3])));
+          __stcg(dst + 1, make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]),
+                                      __uint_as_float(v[6]), __uint_as_float(v[7])));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(tempty_bar(acc));
+          atomicAdd(p.sk_flags + blockIdx.x, 1);
+        }
+        continue;
+      }
+      int n_parts = 0;
+      if (sg.i1 < p.ipt) {
+        // The rest of this tile was the FIRST thing the next CTA(s) computed.
+        const long long total = static_cast<long long>(p.total_tiles) * p.ipt;
+        const long long tile_end = static_cast<long long>(sg.tile + 1) * p.ipt;
+        for (int b = blockIdx.x + 1; b < grid && total * b / grid < tile_end; ++b) ++n_parts;
+        if (lane == 0) {
+          for (int k = 1; k <= n_parts; ++k) {
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile int*>(p.sk_flags + blockIdx.x + k) < kPEpiWarps) {
+              if (clock64() - t0 > 4000000000LL) {
+                if (p.err) atomicExch(p.err, 9);
+                __threadfence_system();
+                __trap();
+              }
+            }
+          }
+          __threadfence();
+        }
+        __syncwarp();
+      }
+      const float* part0 = p.sk_ws + static_cast<size_t>(blockIdx.x + 1) * 128 * p.NP;
+      // v[0..7] += the parked partials of group g, in CTA order
+      auto add_parts = [&](uint32_t* v, int g) {
+        for (int k = 0; k < n_parts; ++k) {
+          const float4* src = reinterpret_cast<const float4*>(part0 + static_cast<size_t>(k) * 128 * p.NP) +
+                              (g * 128 + cl) * 2;
+          const float4 f0 = __ldcg(src), f1 = __ldcg(src + 1);
+          v[0] = __float_as_uint(__uint_as_float(v[0]) + f0.x);
+          v[1] = __float_as_uint(__uint_as_float(v[1]) + f0.y);
+          v[2] = __float_as_uint(__uint_as_float(v[2]) + f0.z);
+          v[3] = __float_as_uint(__uint_as_float(v[3]) + f0.w);
+          v[4] = __float_as_uint(__uint_as_float(v[4]) + f1.x);
+          v[5] = __float_as_uint(__uint_as_float(v[5]) + f1.y);
+          v[6] = __float_as_uint(__uint_as_float(v[6]) + f1.z);
+          v[7] = __float_as_uint(__uint_as_float(v[7]) + f1.w);
+        }
+      };
+      if (p.tma_store && walk_last(p, w)) {
+        // The CTA's LAST segment: nothing overlaps this epilogue, and every MMA of the CTA has
+        // retired, so both patch buffers are free — stage the whole [pixel][cout] tile there
+        // (no per-chunk store/barrier round trips), then issue all TMA stores at once.  The
+        // parked stream-K partials are requested two chunks (32 pixels) ahead.
+        float4 pfA[4], pfB[4];
+        auto fetch = [&](float4 (&pf)[4], int g) {
+          const float4* src = reinterpret_cast<const float4*>(part0) + (g * 128 + cl) * 2;
+          pf[0] = __ldcg(src); pf[1] = __ldcg(src + 1);
+          if (g + 1 < g_end) { pf[2] = __ldcg(src + 256); pf[3] = __ldcg(src + 257); }
+        };
+        auto chunk = [&](int g, const float4 (&pf)[4]) {
+          uint32_t v[16];
+          __syncwarp();
+          tmem_ld16_async(taddr + g * 8, v);
+          tmem_ld_wait();
+          if (n_parts) {
+            const float* f = reinterpret_cast<const float*>(pf);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + f[j]);
+            for (int k = 1; k < n_parts; ++k) {
+              const float* pk = part0 + static_cast<size_t>(k) * 128 * p.NP;
+              for (int gg = 0; gg < 2 && g + gg < g_end; ++gg) {
+                const float4* src = reinterpret_cast<const float4*>(pk) + ((g + gg) * 128 + cl) * 2;
+                const float4 f0 = __ldcg(src), f1 = __ldcg(src + 1);
+                uint32_t* u = v + 8 * gg;
+                u[0] = __float_as_uint(__uint_as_float(u[0]) + f0.x);
+                u[1] = __float_as_uint(__uint_as_float(u[1]) + f0.y);
+                u[2] = __float_as_uint(__uint_as_float(u[2]) + f0.z);
+                u[3] = __float_as_uint(__uint_as_float(u[3]) + f0.w);
+                u[4] = __float_as_uint(__uint_as_float(u[4]) + f1.x);
+                u[5] = __float_as_uint(__uint_as_float(u[5]) + f1.y);
+                u[6] = __float_as_uint(__uint_as_float(u[6]) + f1.z);
+                u[7] = __float_as_uint(__uint_as_float(u[7]) + f1.w);
+              }
+            }
+          }
+          const uint32_t dst = base + static_cast<uint32_t>(g) * 2048u + cl * 2u;
+          const int npx = g + 1 < g_end ? 16 : 8;           // the second group may be the other team's
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i >= npx) break;
+            float y = fmaf(__uint_as_float(v[i]), sc, sh);
+            y = fmaf(fminf(y, 0.f), neg, fmaxf(y, 0.f));
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + i * 256u),
+                         "h"(__half_as_ushort(__float2half_rn(y))) : "memory");
+          }
+        };
+        if (n_parts) {
+          fetch(pfA, g_begin);
+          if (g_begin + 2 < g_end) fetch(pfB, g_begin + 2);
+        }
+        for (int g = g_begin; g < g_end; g += 4) {
+          chunk(g, pfA);
+          if (n_parts && g + 4 < g_end) fetch(pfA, g + 4);
+          if (g + 2 < g_end) {
+            chunk(g + 2, pfB);
+            if (n_parts && g + 6 < g_end) fetch(pfB, g + 6);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 3, 256;" ::: "memory");        // the eight epilogue warps
+        if (warp == 2 && !(p.debug & 4)) {
+          const int b = t.b0 + lane;
+          if (lane < p.R && b < B_dim) {
+            const int cw = p.axis == 0 ? t.a0 : b, ch = p.axis == 0 ? b : t.a0;
+            asm volatile(
+                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                ::"l"(&tmO), "r"(base + static_cast<uint32_t>(lane) * 2048u), "r"(p.out_coff + t.ct * 128),
+                  "r"(cw), "r"(ch), "r"(t.n) : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+      } else if (p.tma_store) {
         // Two groups (16 pixels) at a time: TMEM -> registers -> [pixel][cout] tile in shared
         // memory (a warp writes 64 contiguous bytes per pixel: conflict-free) -> one TMA store
         // per 8-pixel group (2 KB runs in HBM; the tensor map clips the ragged border).
+        // stream-K head: the first parked partial of the NEXT 16 pixels is requested one
+        // iteration ahead, so its L2 latency hides behind the staging / store of this one
+        float4 pf[4];
+        auto fetch_part0 = [&](int g) {
+          const float4* src = reinterpret_cast<const float4*>(part0) + (g * 128 + cl) * 2;
+          pf[0] = __ldcg(src); pf[1] = __ldcg(src + 1);
+          if (g + 1 < g_end) { pf[2] = __ldcg(src + 256); pf[3] = __ldcg(src + 257); }
+        };
+        if (n_parts) fetch_part0(g_begin);
         for (int g = g_begin; g < g_end; g += 2) {
           uint32_t v[16];
           __syncwarp();
           tmem_ld16_async(taddr + g * 8, v);
           tmem_ld_wait();
+          if (n_parts) {
+            const float* f = reinterpret_cast<const float*>(pf);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + f[j]);
+            if (g + 2 < g_end) fetch_part0(g + 2);
+            for (int k = 1; k < n_parts; ++k) {           // split-K over more than two CTAs
+              const float* pk = part0 + static_cast<size_t>(k) * 128 * p.NP;
+              for (int gg = 0; gg < 2 && g + gg < g_end; ++gg) {
+                const float4* src = reinterpret_cast<const float4*>(pk) + ((g + gg) * 128 + cl) * 2;
+                const float4 f0 = __ldcg(src), f1 = __ldcg(src + 1);
+                uint32_t* u = v + 8 * gg;
+                u[0] = __float_as_uint(__uint_as_float(u[0]) + f0.x);
+                u[1] = __float_as_uint(__uint_as_float(u[1]) + f0.y);
+                u[2] = __float_as_uint(__uint_as_float(u[2]) + f0.z);
+                u[3] = __float_as_uint(__uint_as_float(u[3]) + f0.w);
+                u[4] = __float_as_uint(__uint_as_float(u[4]) + f1.x);
+                u[5] = __float_as_uint(__uint_as_float(u[5]) + f1.y);
+                u[6] = __float_as_uint(__uint_as_float(u[6]) + f1.z);
+                u[7] = __float_as_uint(__uint_as_float(u[7]) + f1.w);
+              }
+            }
+          }
           uint32_t h[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -366,6 +589,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tmem_ld8_async(taddr + g * 8, v);
           tmem_ld_wait();
           if (t.b0 + g >= B_dim || !c_ok || (p.debug & 4)) continue;
+          if (n_parts) add_parts(v, g);
           const unsigned pix0 = pix00 + g * b_step;
           const unsigned o0 = pix0 * p.out_cs + p.out_coff + cout, os = a_step * p.out_cs;
           const unsigned r0 = pix0 * p.res_cs + p.res_coff + cout, rs = a_step * p.res_cs;
@@ -383,7 +607,13 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        mbar_arrive(tempty_bar(acc));
+        for (int k = 1; k <= n_parts; ++k) {              // last of the 16 warps re-arms the flag
+          int* flag = p.sk_flags + blockIdx.x + k;
+          if (atomicAdd(flag, 1) == 2 * kPEpiWarps - 1) atomicExch(flag, 0);
+        }
+      }
       if (warp == 2) PT_STAMP(6);                           // epilogue of a tile done
     }
     if (p.tma_store && store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -420,6 +650,7 @@ int env_int(const char* name, int dflt) {
 
 struct ConvPatchPlan {
   unsigned long long* trace = nullptr;
+  void* sk_own = nullptr;
   CUtensorMap tmX, tmW, tmO;
   PatchParams p;
   int grid;
@@ -431,7 +662,7 @@ bool conv_patch_eligible(const ConvArgs& a) {
   if (a.stride != 1 || a.kh != a.kw || !(a.kh & 1) || a.pad != a.kh / 2 || a.kh > 9) return false;
   if (a.cin_pad % 64 || a.cout_pad % 128) return false;
   if (a.in.cs % 8 || a.in.coff % 8) return false;
-  if (a.out2.ptr || a.res_up2) return false;
+  if (a.out2.ptr || a.res_up2 || a.shift9) return false;
   if (a.H_out != a.in.H || a.W_out != a.in.W) return false;
   return true;
 }
@@ -547,6 +778,28 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   }
 
   plan->grid = std::min(p.total_tiles, sms);
+  {
+    // Stream-K where whole-tile scheduling leaves SMs idle: a last partial round (160 tiles on
+    // 148 SMs run as long as 296) or fewer tiles than SMs.
+    const int want = env_int("TRB_PT_SK", 1);               // 0 off, 1 auto, 2 whenever possible
+    p.ipt = p.kchunks * p.iters;
+    const int rounds = ceil_div(p.total_tiles, sms);
+    const double idle = 1.0 - double(p.total_tiles) / (double(rounds) * sms);
+    const bool ok = p.ipt >= 2 && sms < int(2048 / 4) - 1;
+    const bool worth = p.ipt >= 4 && idle >= 0.08;
+    if (ok && (want == 2 || (want == 1 && worth))) {
+      void* scratch = a.sk_scratch;
+      if (!scratch) {
+        TR_CUDA(cudaMalloc(&plan->sk_own, conv_tc_sk_scratch_bytes()));
+        TR_CUDA(cudaMemset(plan->sk_own, 0, 2048));
+        scratch = plan->sk_own;
+      }
+      p.sk = 1;
+      p.sk_flags = static_cast<int*>(scratch);
+      p.sk_ws = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + 2048);
+      plan->grid = int(std::min<long long>(sms, static_cast<long long>(p.total_tiles) * p.ipt));
+    }
+  }
   plan->smem = fixed + p.stages * p.stage_bytes;
   plan->flops = 2.0 * p.N * p.H * p.W * double(a.cout_pad) * p.taps * a.cin_pad;
   static bool attr_set[kMaxDevices] = {};
@@ -558,6 +811,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
 }
 
 void conv_patch_plan_destroy(ConvPatchPlan* p) {
+  if (p->sk_own) cudaFree(p->sk_own);
   if (p->trace) {
     // CTA 0's event times relative to its kernel entry, and the gap to the previous launch's end
     std::vector<unsigned long long> h(1 + 16 * 64);

@@ -64,6 +64,11 @@ struct TcParams {
   // epilogue
   const float* scale; const float* shift; const float* slope;
   const float* scale2; const float* shift2;
+  // Border-class shifts (9 x cout_pad, class = 3 * row class + column class; 0 first, 1 inner,
+  // 2 last row / column): a 3x3 pad-1 conv whose input carries a folded per-channel affine has
+  // an input-independent term that depends on which taps are in bounds (arcface/model.py:11-35).
+  const float* shift9;
+  int param_rows;            // rows of cout_pad floats staged in smem: 5, or 14 with shift9
   int act;
   __half* out; int out_cs, out_coff, cout_store;
   __half* out2; int out2_cs, out2_coff;
@@ -133,7 +138,8 @@ __device__ __forceinline__ bool walk_done(const TcParams& p, const TileWalk& w) 
 }
 
 struct EpiCtx {
-  const float* sp;       // smem params: [5][cout_pad] scale, shift, slope, scale2, shift2
+  const float* sp;       // smem params: [5][cout_pad] scale, shift, slope, scale2, shift2 (+ [9] border shifts)
+  const float* shp;      // this thread's shift row
   int cpad;
   bool valid;
   long pix, rpix;
@@ -149,7 +155,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiCtx& 
     if (c >= p.cout_store) break;
     float y[8];
     const float4* sc4 = reinterpret_cast<const float4*>(e.sp + c);
-    const float4* sh4 = reinterpret_cast<const float4*>(e.sp + e.cpad + c);
+    const float4* sh4 = reinterpret_cast<const float4*>(e.shp + c);
     const float4 s0 = sc4[0], s1 = sc4[1], b0 = sh4[0], b1 = sh4[1];
     const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
     const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -459,7 +465,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t ring = base + p.ring_off;              // halo mode: two patch buffers come first
   const uint32_t params_s = ring + p.stages * p.stage_bytes;
   const int cpad = p.cout_pad <= kMaxParamChannels ? p.cout_pad : 0;
-  const uint32_t tab_s = params_s + 5u * cpad * 4u;   // halo: per-tap descriptor offset of the shifted patch window
+  const uint32_t tab_s = params_s + static_cast<uint32_t>(p.param_rows) * cpad * 4u;   // halo: per-tap descriptor offset of the shifted patch window
   const uint32_t bars = tab_s + 256u;
   // barrier layout: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -513,6 +519,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       sp[2 * cpad + i] = p.slope ? p.slope[i] : 0.f;
       sp[3 * cpad + i] = p.scale2 ? p.scale2[i] : 1.f;
       sp[4 * cpad + i] = p.shift2 ? p.shift2[i] : 0.f;
+      if (p.shift9)
+        for (int k = 0; k < 9; ++k) sp[(5 + k) * cpad + i] = p.shift9[k * cpad + i];
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -823,6 +831,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       e.rpix = e.pix;
       if (p.res && p.res_up2)
         e.rpix = (static_cast<long>(on) * p.res_H + (oh >> 1)) * p.res_W + (ow >> 1);
+      e.shp = e.sp + e.cpad;
+      if (p.shift9) {
+        const int rc = oh == 0 ? 0 : (oh >= p.H_out - 1 ? 2 : 1), cc = ow == 0 ? 0 : (ow >= p.W_out - 1 ? 2 : 1);
+        e.shp = e.sp + (5 + rc * 3 + cc) * e.cpad;
+      }
 
       mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1027,7 +1040,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t params_s = base + p.stages * p.stage_bytes;
   const int cpad = p.cout_pad;
-  const uint32_t bars = params_s + 5u * cpad * 4u;
+  const uint32_t bars = params_s + static_cast<uint32_t>(p.param_rows) * cpad * 4u;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + a); };
@@ -1065,6 +1078,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       sp[2 * cpad + i] = p.slope ? p.slope[i] : 0.f;
       sp[3 * cpad + i] = p.scale2 ? p.scale2[i] : 1.f;
       sp[4 * cpad + i] = p.shift2 ? p.shift2[i] : 0.f;
+      if (p.shift9)
+        for (int k = 0; k < 9; ++k) sp[(5 + k) * cpad + i] = p.shift9[k * cpad + i];
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1200,6 +1215,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       e.rpix = e.pix;
       if (p.res && p.res_up2)
         e.rpix = (static_cast<long>(on) * p.res_H + (oh >> 1)) * p.res_W + (ow >> 1);
+      e.shp = e.sp + e.cpad;
+      if (p.shift9) {
+        const int rc = oh == 0 ? 0 : (oh >= p.H_out - 1 ? 2 : 1), cc = ow == 0 ? 0 : (ow >= p.W_out - 1 ? 2 : 1);
+        e.shp = e.sp + (5 + rc * 3 + cc) * e.cpad;
+      }
 
       mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1330,6 +1350,8 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   p.N_tile = a.cout_pad > 256 ? 256 : a.cout_pad;
   p.n_tiles = a.cout_pad / p.N_tile;
   p.cout_pad = a.cout_pad;
+  p.shift9 = a.shift9;
+  p.param_rows = a.shift9 ? 14 : 5;
 
   // Pick the pixel box {bw, bh, bn} (<= 128 rows) that wastes the fewest MMA rows.
   double best = -1.0;
@@ -1384,7 +1406,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     // parity-tested (tests/test_gpu_ops.py::test_conv_swap_mode) and kept for the next round.
     int want = 0;                                   // 0 off, 1 auto, 2 whenever possible, 3 band variant only
     if (const char* e = getenv("TRB_TC_SWAP")) want = atoi(e);
-    const bool plain_epi = !a.res.ptr && !a.out2.ptr && !a.out_f32;
+    const bool plain_epi = !a.res.ptr && !a.out2.ptr && !a.out_f32 && !a.shift9;
     const bool base_ok = a.stride == 1 && p.KC == 64 && a.cout_pad % 128 == 0 && plain_epi;
     const bool patch_ok = base_ok && a.kh == a.kw && a.kh >= 3 && a.pad == a.kh / 2 && 8 + 2 * a.pad <= 16;
     const bool patch_worth = a.cout_pad == 128 && p.taps >= 25;
@@ -1483,7 +1505,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     // two stages (+ the halo patches, parameters, barriers) must fit in the SM's 227 KB
     const uint32_t patches = p.halo ? 2 * round_up(((p.swap ? p.bw : 16) + 2 * a.pad) * 16 * 128, 1024) : 0;
     const uint32_t limit = plan->ctas_per_sm == 2 ? 108u * 1024 : 224u * 1024;
-    while (p.sub > 1 && patches + 2u * p.sub * p.sub_bytes + 5u * p.cout_pad * 4u + 2048u > limit) --p.sub;
+    while (p.sub > 1 && patches + 2u * p.sub * p.sub_bytes + uint32_t(p.param_rows) * p.cout_pad * 4u + 2048u > limit) --p.sub;
   }
   p.iters = ceil_div(p.k_blocks, p.sub);
   {
@@ -1510,7 +1532,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   }
   p.iters_kc = ceil_div(p.taps, p.sub);
   p.stage_bytes = p.sub * p.sub_bytes;
-  const uint32_t param_bytes = 5u * p.cout_pad * 4u;
+  const uint32_t param_bytes = uint32_t(p.param_rows) * p.cout_pad * 4u;
   if (p.halo) {
     p.patch_tx = ((p.swap ? p.bw : 16) + 2 * a.pad) * 16 * 128;
     p.patch_bytes = round_up(p.patch_tx, 1024);
@@ -1549,6 +1571,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   TR_CHECK(a.scale && a.shift, "epilogue scale/shift are required");
   TR_CHECK(a.act != ACT_PRELU || a.slope, "PReLU needs slopes");
   TR_CHECK(!a.out2.ptr || (a.scale2 && a.shift2), "second output needs scale2/shift2");
+  TR_CHECK(!a.shift9 || (a.kh == 3 && a.pad == 1 && a.stride == 1 && !p.cta2), "border-class shifts are for 3x3 pad-1 stride-1 layers");
 
   // ---- tensor maps
   auto encode = encode_fn();

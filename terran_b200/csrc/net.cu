@@ -109,13 +109,20 @@ bool mma_enabled() {
   return on;
 }
 
-// TRB_PATCH: 0 = never, 1 = auto (layers where the resident-patch kernel measured faster),
-// 2 = every eligible layer.
+// TRB_PATCH: 0 = never, 1 = auto (layers where the resident-patch kernel measured faster,
+// profiles/r02_patch_vs_plain.txt), 2 = every eligible layer.
 bool patch_wanted(const ConvArgs& a) {
-  static const int mode = [] { const char* e = getenv("TRB_PATCH"); return e ? atoi(e) : 0; }();
+  static const int mode = [] { const char* e = getenv("TRB_PATCH"); return e ? atoi(e) : 1; }();
   if (!mode || !conv_patch_eligible(a)) return false;
   if (mode >= 2) return true;
-  return a.kh >= 3;
+  // Measured faster than conv_tc_kernel on every eligible OpenPose layer (1x1, 3x3 and 7x7,
+  // 64..512 input channels) once the map is large enough for the 8 x R tiles to fill their
+  // MMA columns; small maps (ArcFace 14x14 / 7x7) waste too many of them.
+  const int H = a.H_out, W = a.W_out;
+  auto fill = [](int n, int g) { return double(n) / (double(g) * ((n + g - 1) / g)); };
+  const double best = std::max(fill(W, 8) * std::max(fill(H, 24), fill(H, 32)),
+                               fill(H, 8) * std::max(fill(W, 24), fill(W, 32)));
+  return best >= 0.85;
 }
 
 View make_view(const Buf& b, int coff, int C) {
@@ -231,6 +238,8 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
         a.scale = blob_ptr<float>(net, d.scale_off); a.shift = blob_ptr<float>(net, d.shift_off);
         a.slope = blob_ptr<float>(net, d.slope_off);
         a.scale2 = blob_ptr<float>(net, d.scale2_off); a.shift2 = blob_ptr<float>(net, d.shift2_off);
+        a.shift9 = blob_ptr<float>(net, d.shift9_off);
+        TR_CHECK(!a.shift9 || (d.k == 3 && d.pad == 1 && d.stride == 1), "border-class shifts are for 3x3 pad-1 stride-1 convs");
         a.cout_pad = d.cout_pad; a.cout_store = d.out_c; a.cin_pad = d.in_c;
         a.kh = a.kw = d.k; a.stride = d.stride; a.pad = d.pad; a.act = d.act;
         a.H_out = B[d.out].H; a.W_out = B[d.out].W;
@@ -238,7 +247,7 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
                  "channel slice out of range");
         po.flops = 2.0 * B[d.out].N * a.H_out * a.W_out * double(d.cout_real) * d.k * d.k * d.cin_real;
         po.mma = !net->force_direct && !d.force_direct && d.engine == TR_ENGINE_MMA && mma_enabled() &&
-                 conv_mma_eligible(a);
+                 !a.shift9 && conv_mma_eligible(a);
         const bool use_tc = !po.mma && !net->force_direct && !d.force_direct && conv_tc_eligible(a);
         if (use_tc && patch_wanted(a)) {
           po.pt = conv_patch_plan_create(a, conv_tc_error_flag());

@@ -64,16 +64,18 @@ class Program:
                  out2_coff=0, res=-1, res_coff=0, res_up2=0, k=1, stride=1, pad=0, act=0,
                  cout_pad=0, cin_real=0, cout_real=0, force_direct=0, lane=0, sync=0, w_off=-1, scale_off=-1, shift_off=-1, slope_off=-1,
                  scale2_off=-1, shift2_off=-1, in_scale=1.0, in_shift=0.0,
-                 dw_w_off=-1, dw_scale_off=-1, dw_shift_off=-1, dw_w16_off=-1, engine=0, reserved=0)
+                 dw_w_off=-1, dw_scale_off=-1, dw_shift_off=-1, dw_w16_off=-1, engine=0, reserved=0,
+                 shift9_off=-1)
         d.update(kw)
         self.ops.append(nat.OpDesc(**d))
 
     def conv(self, w, scale, shift, in_, out, *, in_coff=0, in_map=None, cin_pad=None,
              out_coff=0, k=None, stride=1, pad=None, act=nat.TR_ACT_NONE, slope=None,
              res=-1, res_coff=0, res_up2=0, out2=-1, scale2=None, shift2=None,
-             force_direct=0, lane=0, sync=0, engine=nat.TR_ENGINE_AUTO):
+             force_direct=0, lane=0, sync=0, engine=nat.TR_ENGINE_AUTO, shift9=None):
         """w: (cout, cin, k, k) fp32 tensor.  ``in_map[c]`` is the position of
-        reference input channel c inside the (padded) input view."""
+        reference input channel c inside the (padded) input view.  ``shift9``: (9, cout)
+        border-class shifts replacing ``shift`` (see ``pre_bn_fold``)."""
         w = w.detach().float().numpy()
         cout, cin, kh, kw_ = w.shape
         k = kh if k is None else k
@@ -91,7 +93,16 @@ class Program:
                  engine=engine, w_off=self.add(packed, np.float16),
                  scale_off=self.add_vec(scale, cout_pad), shift_off=self.add_vec(shift, cout_pad),
                  slope_off=self.add_vec(slope, cout_pad),
-                 scale2_off=self.add_vec(scale2, cout_pad), shift2_off=self.add_vec(shift2, cout_pad))
+                 scale2_off=self.add_vec(scale2, cout_pad), shift2_off=self.add_vec(shift2, cout_pad),
+                 shift9_off=self.add_mat(shift9, cout_pad))
+
+    def add_mat(self, m, n_pad):
+        if m is None:
+            return -1
+        m = np.asarray(m, np.float32)
+        v = np.zeros((m.shape[0], n_pad), np.float32)
+        v[:, :m.shape[1]] = m
+        return self.add(v, np.float32)
 
     def stem(self, w, scale, shift, out, *, stride, act, slope=None, in_scale=1.0, in_shift=0.0,
              out2=-1, scale2=None, shift2=None):
@@ -152,6 +163,29 @@ def bn_fold(sd, prefix, eps, conv_bias=None):
     bias = conv_bias.double() if conv_bias is not None else 0.0
     shift = b + (bias - m) * scale
     return scale.float().numpy(), shift.float().numpy()
+
+
+def pre_bn_fold(w, s0, t0, s1, t1):
+    """Fold a per-channel affine ``x*s0 + t0`` that PRECEDES a zero-padded 3x3 stride-1 conv
+    (and the affine ``y*s1 + t1`` that follows it) into the conv:
+
+        conv_W(pad(x*s0 + t0)) * s1 + t1  =  conv_{W*s0}(pad(x)) * s1 + shift9[class]
+
+    Padding is applied AFTER the first affine, so its shift only reaches the taps that are in
+    bounds: the input-independent term ``sum_{taps in bounds} W[:, :, tap] @ t0`` depends on the
+    output pixel's border class (3 row classes x 3 column classes).  Returns (w * s0,
+    shift9 (9, cout)) with class = 3*row_class + col_class, 0 = first, 1 = inner, 2 = last."""
+    w = w.detach().double()
+    s0, t0 = torch.as_tensor(s0).double(), torch.as_tensor(t0).double()
+    s1, t1 = torch.as_tensor(s1).double(), torch.as_tensor(t1).double()
+    per_tap = torch.einsum('oikl,i->okl', w, t0)            # (cout, 3, 3)
+    shift9 = torch.empty((9, w.shape[0]), dtype=torch.float64)
+    rows = {0: (1, 2), 1: (0, 1, 2), 2: (0, 1)}             # filter rows that stay in bounds
+    for rc, rs in rows.items():
+        for cc, cs in rows.items():
+            term = per_tap[:, list(rs)][:, :, list(cs)].sum((1, 2))
+            shift9[rc * 3 + cc] = term * s1 + t1
+    return (w * s0.view(1, -1, 1, 1)).float(), shift9.float().numpy()
 
 
 # ------------------------------------------------------------------ RetinaFace
@@ -255,22 +289,22 @@ def retinaface_program(sd, fused=None):
 
 def arcface_program(sd, units=ARCFACE_UNITS):
     """Program for reference ``FaceResNet100`` (arcface/model.py:38-97).  Input
-    in model channel order (BGR)."""
+    in model channel order (BGR).
+
+    Every ``Unit`` starts with a BatchNorm in front of a zero-padded 3x3 conv
+    (``body[0]``, ``body[1]``; model.py:11-14).  It is folded into that conv exactly — scale
+    into the filters, shift into nine border-class shift vectors (``pre_bn_fold``) — so the
+    residual stream ``x`` is the only tensor a unit reads and writes: no second, normalised
+    copy of every activation."""
     P = Program()
     e = 2e-5
 
-    def pre_affine(prefix):
-        """BN applied to a tensor before a padded conv, as (scale, shift)."""
-        return bn_fold(sd, prefix, e)
-
     C0 = ARCFACE_CHANNELS[0]
     x = P.buffer(C0)
-    xn = P.buffer(C0)
     s, t = bn_fold(sd, 'initial_layer.1', e)
-    s2, t2 = pre_affine('stages.0.0.body.0')
     P.stem(sd['initial_layer.0.weight'], s, t, x, stride=1, act=nat.TR_ACT_PRELU,
            slope=sd['initial_layer.2.weight'].float().numpy(),
-           in_scale=0.0078125, in_shift=-127.5 * 0.0078125, out2=xn, scale2=s2, shift2=t2)
+           in_scale=0.0078125, in_shift=-127.5 * 0.0078125)
 
     n_stages = len(units)
     for si, n_units in enumerate(units):
@@ -279,31 +313,25 @@ def arcface_program(sd, units=ARCFACE_UNITS):
         y = P.buffer(cout)
         sc = P.buffer(cout)
         xs = [P.buffer(cout), P.buffer(cout)]
-        xns = [P.buffer(cout), P.buffer(cout)]
         for u in range(n_units):
             p = f'stages.{si}.{u}'
             stride = 2 if u == 0 else 1
-            s, t = bn_fold(sd, p + '.body.2', e)
+            s0, t0 = bn_fold(sd, p + '.body.0', e)
+            s1, t1 = bn_fold(sd, p + '.body.2', e)
+            w1, shift9 = pre_bn_fold(sd[p + '.body.1.weight'], s0, t0, s1, t1)
             yb = y_full if u == 0 else y
-            P.conv(sd[p + '.body.1.weight'], s, t, xn, yb, act=nat.TR_ACT_PRELU,
-                   slope=sd[p + '.body.3.weight'].float().numpy())
+            P.conv(w1, s1, shift9[4], x, yb, act=nat.TR_ACT_PRELU,
+                   slope=sd[p + '.body.3.weight'].float().numpy(), shift9=shift9)
             if u == 0:
                 s, t = bn_fold(sd, p + '.shortcut.1', e)
                 P.conv(sd[p + '.shortcut.0.weight'], s, t, x, sc, stride=2)
                 res = sc
             else:
                 res = x
-            last = (si == n_stages - 1 and u == n_units - 1)
-            x_new, xn_new = xs[u & 1], xns[u & 1]
+            x_new = xs[u & 1]
             s, t = bn_fold(sd, p + '.body.5', e)
-            if last:
-                P.conv(sd[p + '.body.4.weight'], s, t, yb, x_new, stride=stride, res=res)
-            else:
-                nxt = f'stages.{si}.{u + 1}' if u + 1 < n_units else f'stages.{si + 1}.0'
-                s2, t2 = pre_affine(nxt + '.body.0')
-                P.conv(sd[p + '.body.4.weight'], s, t, yb, x_new, stride=stride, res=res,
-                       out2=xn_new, scale2=s2, shift2=t2)
-            x, xn = x_new, xn_new
+            P.conv(sd[p + '.body.4.weight'], s, t, yb, x_new, stride=stride, res=res)
+            x = x_new
 
     # final_layer: BN2d (no padding follows -> folded into the FC exactly),
     # Flatten in (C,H,W) order -> permuted to our (H,W,C), Linear, BN1d.

@@ -73,7 +73,18 @@ class Interpreter:
                 cp, k = d.cout_pad, d.k
                 w = self.arr(d.w_off, np.float16, cp * k * k * d.in_c).float().view(cp, k, k, d.in_c).permute(0, 3, 1, 2)
                 y = F.conv2d(x, w, stride=d.stride, padding=d.pad)
-                y = y * self.vec(d.scale_off, cp).view(1, -1, 1, 1) + self.vec(d.shift_off, cp).view(1, -1, 1, 1)
+                y = y * self.vec(d.scale_off, cp).view(1, -1, 1, 1)
+                if getattr(d, 'shift9_off', -1) >= 0:
+                    # border-class shifts: class = 3 * row class + column class (first/inner/last)
+                    assert k == 3 and d.pad == 1 and d.stride == 1
+                    s9 = self.arr(d.shift9_off, np.float32, 9 * cp).view(9, cp)
+                    Hh, Ww = y.shape[2:]
+                    rc = torch.ones(Hh, dtype=torch.long); rc[0] = 0; rc[-1] = 2
+                    cc = torch.ones(Ww, dtype=torch.long); cc[0] = 0; cc[-1] = 2
+                    cls = rc.view(-1, 1) * 3 + cc.view(1, -1)                 # (H, W)
+                    y = y + s9[cls].permute(2, 0, 1).unsqueeze(0)
+                else:
+                    y = y + self.vec(d.shift_off, cp).view(1, -1, 1, 1)
                 y = self._act(y, d.act, self.vec(d.slope_off, cp))[:, :d.out_c]
                 N, _, H, W = y.shape
                 if d.res >= 0:

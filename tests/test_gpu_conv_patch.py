@@ -12,7 +12,8 @@ from tests.gpu_util import conv2d_native, conv2d_reference, describe_mismatch
 pytestmark = pytest.mark.gpu
 
 
-def run_case(nat, N, H, W, cin, cout, k, *, act=1, res=False, out_f32=False, seed=0, env=None):
+def run_case(nat, N, H, W, cin, cout, k, *, act=1, res=False, out_f32=False, seed=0, env=None,
+             repeat=0):
     g = torch.Generator().manual_seed(seed)
     x = (torch.randn((N, H, W, cin), generator=g) * 0.5).half().cuda()
     w = torch.randn((cout, cin, k, k), generator=g) / (cin * k * k) ** 0.5
@@ -26,7 +27,7 @@ def run_case(nat, N, H, W, cin, cout, k, *, act=1, res=False, out_f32=False, see
         os.environ[key] = str(val)
     try:
         out, _ = conv2d_native(nat, x, w, scale, shift, act=act, slope=slope, res=r,
-                               out_f32=out_f32, use_tc=3)
+                               out_f32=out_f32, use_tc=3, repeat=repeat)
     finally:
         for key, val in old.items():
             if val is None:
@@ -37,6 +38,7 @@ def run_case(nat, N, H, W, cin, cout, k, *, act=1, res=False, out_f32=False, see
     tol = 2e-3 if out_f32 else 4e-3
     err = (out.detach().cpu().double() - ref).abs().max().item()
     assert err < tol, describe_mismatch(out, ref, tol)
+    return out
 
 
 @pytest.mark.parametrize('shape', [
@@ -77,3 +79,24 @@ def test_patch_conv_many_tiles_per_cta(native):
     """More tiles than SMs: TMEM double buffering, patch buffer and ring phases wrap."""
     run_case(native, 40, 23, 40, 128, 128, 3)
     run_case(native, 64, 14, 14, 256, 256, 3, act=2, res=True)
+
+
+@pytest.mark.parametrize('shape', [
+    (32, 23, 40, 128, 128, 7),      # 160 tiles on 148 SMs: every CTA hands a partial tile over
+    (2, 23, 40, 128, 128, 7),       # 10 tiles: split-K, each tile summed from ~15 CTAs
+    (5, 23, 40, 192, 256, 3),       # three chunks, two cout tiles
+    (40, 23, 40, 128, 128, 3),      # 200 tiles, short K
+    (3, 9, 10, 64, 128, 1),         # one ring iteration per tile: nothing to split
+])
+def test_patch_conv_stream_k(native, shape):
+    """Stream-K (TRB_PT_SK=2: whenever possible) against the reference, launched several times in
+    a row (the hand-over flags re-arm themselves) and bit-identical to a second run."""
+    a = run_case(native, *shape, env={'TRB_PT_SK': 2}, repeat=3)
+    b = run_case(native, *shape, env={'TRB_PT_SK': 2}, repeat=1)
+    assert torch.equal(a, b)
+
+
+def test_patch_conv_stream_k_epilogues(native):
+    run_case(native, 20, 14, 14, 128, 128, 3, act=2, res=True, env={'TRB_PT_SK': 2}, repeat=2)
+    run_case(native, 3, 23, 40, 128, 128, 3, act=0, out_f32=True, env={'TRB_PT_SK': 2}, repeat=2)
+    run_case(native, 32, 23, 40, 128, 128, 7, env={'TRB_PT_SK': 2, 'TRB_PT_SUB': 1, 'TRB_PT_STAGES': 3})

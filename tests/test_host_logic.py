@@ -42,7 +42,7 @@ def test_op_desc_layout_matches_header(native):
             for n, t in fields]
     got = [(n.rstrip('_'), t) for n, t in native.OpDesc._fields_]
     assert got == want
-    assert C.sizeof(native.OpDesc) == 22 * 4 + 6 * 8 + 2 * 4 + 4 * 8 + 2 * 4
+    assert C.sizeof(native.OpDesc) == 22 * 4 + 6 * 8 + 2 * 4 + 4 * 8 + 2 * 4 + 8
 
 
 def test_no_gpu_calls_fail_loudly(native):
@@ -299,13 +299,15 @@ def test_shard_range_partitions():
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (the CPU port timed on host cores) prints ONE JSON line with
-    the arm's keys: same metric / unit / config as the GPU arm, a cpu_baseline describing the
-    run and an e2e block without device traffic."""
+    """`bench.py --impl reference` (the unmodified reference from baseline/_ref — or, where it
+    is not installed, the oracle port — timed on host cores) prints ONE JSON line with the
+    arm's keys: same metric / unit / config as the GPU arm, a cpu_baseline describing the run
+    and an e2e block without device traffic."""
     import json
     env = dict(os.environ, CUDA_VISIBLE_DEVICES='', OMP_NUM_THREADS='4')
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
-                        '--steps', '1', '--warmup', '0'], capture_output=True, text=True, env=env,
+                        '--steps', '1', '--warmup', '0', '--ref-frames', '2'], capture_output=True,
+                       text=True, env=env,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
@@ -314,7 +316,10 @@ def test_bench_reference_arm_contract():
     assert d['impl'] == 'reference' and d['unit'] == 'frames/s' and d['higher_is_better'] is True
     assert d['metric'].startswith('frames/sec end-to-end (detect+pose)')
     assert d['value'] > 0 and d['steps'] == 1 and d['n_gpus'] == 1
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    from baseline import refarm
+    want_kind = 'reference' if refarm.reference_path() else 'port'
+    assert d['cpu_baseline']['kind'] == want_kind and d['cpu_baseline']['cores'] >= 1
+    assert d['config']['frames_per_gpu'] == 2 and d['config']['people_per_frame'] > 0
     assert d['cpu_baseline']['value'] == d['value'] and 'sample' in d['cpu_baseline']
     assert d['e2e'] == {'value': d['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0}
