@@ -105,6 +105,55 @@ int tr_net_stats(tr_net* net, double* tc_flops, int* tc_launches, int* total_lau
 int tr_net_set_profile(tr_net* net, int enable);
 int tr_net_profile(tr_net* net, float* ms, int32_t* is_tc, double* flops, int cap, int* n_ops);
 
+/* ---- models from a checkpoint, without Python --------------------------------
+ * The layer programs of the three reference models are built by the library itself from the
+ * reference's state_dict, passed as a flat "TRSD" blob of named tensors:
+ *   "TRSD", u32 version (1), u32 count, then per tensor: u16 name length, name, u8 dtype
+ *   (0 = float32, 1 = int64), u8 ndim, i64 dims[ndim], u64 byte count, zero padding to an 8-byte
+ *   boundary, data.   (terran_b200.weights.pack_state_dict writes it from a torch state_dict.)
+ * tr_program_* are host-only (no CUDA call): they replace nn.Module construction +
+ * load_state_dict + BatchNorm folding (retinaface/wrapper.py:16-22, arcface/wrapper.py:13-19,
+ * openpose/wrapper.py:26-34). */
+typedef struct tr_program tr_program;
+/* model: "retinaface" | "arcface" | "openpose"; flags bit 0 (retinaface only): one op per
+ * reference layer instead of the fused depthwise+1x1 program (cross-check). */
+int tr_program_build(const char* model, const void* state_dict_blob, size_t bytes, int flags,
+                     tr_program** out);
+void tr_program_destroy(tr_program* program);
+/* roles8: retinaface = head buffers of stride 32, 16, 8; arcface = embedding buffer;
+ * openpose = maps buffer, PAF channel offset, heat-map channel offset; unused = -1. */
+int tr_program_info(const tr_program* program, int* n_buffers, int* n_ops, size_t* blob_bytes,
+                    int32_t* roles8);
+int tr_program_copy(const tr_program* program, tr_buffer_desc* buffers, tr_op_desc* ops, void* blob);
+int tr_net_create_from_program(const tr_program* program, tr_net** out);
+
+/* Single-call models: tr_*_create builds program + net from the checkpoint blob; tr_*_forward
+ * runs one batch on device-resident inputs and leaves the results on the device.  Scratch
+ * buffers live in the handle (grow-only).
+ *
+ * RetinaFace.call (retinaface/wrapper.py:133-238) on frames already resized by the caller:
+ * frames (N,H,W,3) uint8 RGB; count (N,) int32; det (N,max_det,16) float32 rows
+ * [score, x1,y1,x2,y2, 10 landmark coords, anchor index bits] in score order after NMS. */
+typedef struct tr_model tr_model;
+int tr_retinaface_create(const void* state_dict_blob, size_t bytes, tr_model** out);
+int tr_retinaface_forward(tr_model* model, const uint8_t* frames_dev, int N, int H, int W,
+                          float threshold, double nms_threshold, int max_det, int32_t* count_dev,
+                          float* det_dev, void* stream);
+/* FaceResNet100.forward + L2 normalise (arcface/model.py:87-97, wrapper.py:174-176): crops
+ * (N,112,112,3) uint8 RGB (layout 0) or (N,3,112,112) uint8 BGR as the reference feeds its model
+ * (layout 1); emb (N,512) float32. */
+int tr_arcface_create(const void* state_dict_blob, size_t bytes, tr_model** out);
+int tr_arcface_forward(tr_model* model, const uint8_t* crops_dev, int N, int layout, int normalise,
+                       float* emb_dev, void* stream);
+/* OpenPose.call after the resize (openpose/wrapper.py:207-485): frames (N,H,W,3) uint8 RGB at
+ * network resolution, scale = short_side / min(original H, W); outputs as tr_openpose_parse. */
+int tr_openpose_create(const void* state_dict_blob, size_t bytes, tr_model** out);
+int tr_openpose_forward(tr_model* model, const uint8_t* frames_dev, int N, int H, int W, double scale,
+                        int32_t* count_dev, int32_t* keypoints_dev, double* score_dev,
+                        int32_t* status_dev, void* stream);
+tr_net* tr_model_net(tr_model* model);
+void tr_model_destroy(tr_model* model);
+
 /* ---- single ops (parity tests, roofline micro-benchmarks) ---------------- */
 /* NHWC fp16 convolution with fused scale/shift/activation/residual epilogue.
  * use_tc: 1 = tcgen05 implicit GEMM, 0 = CUDA-core direct kernel, 2 = warp-level mma.sync
@@ -152,6 +201,17 @@ int tr_l2_normalize(const float* in_dev, float* out_dev, int N, int D, void* str
  * data = first two rows of the inverse similarity); image_index: frame of each face. */
 int tr_face_align(const uint8_t* frames_dev, int H, int W, const double* coef_dev,
                   const int32_t* image_index_dev, int F, uint8_t* out_dev, int side, void* stream);
+
+/* The 2x3 inverse similarity (PIL AFFINE data) of every detected face, computed on the device
+ * from the detection rows of tr_retinaface_detect (so detect -> align -> embed needs no host
+ * round trip for landmarks): landmarks are mapped back to frame pixels as Detection.resize_out
+ * does (value / scale, round half to even), then fitted to the 5-point template in closed form
+ * — replaces skimage SimilarityTransform.estimate + np.linalg.inv of arcface/wrapper.py:47-61.
+ * det: (N, max_det, 16) rows, count: (N,) survivors per frame.  Faces are numbered frame by
+ * frame in row order; coef: cap x 6 doubles, image_index: cap, *total: number of faces. */
+int tr_face_similarity(const float* det_dev, const int32_t* count_dev, int N, int max_det, float scale,
+                       int cap, double* coef_dev, int32_t* image_index_dev, int32_t* total_dev,
+                       void* stream);
 
 /* ---- OpenPose parse ---------------------------------------------------------
  * Replaces openpose/wrapper.py:214-483: x8 bicubic up-sampling (fused, never

@@ -15,9 +15,13 @@ SYMBOLS = (
     'tr_net_create', 'tr_net_destroy', 'tr_net_set_mode', 'tr_net_run', 'tr_net_buffer',
     'tr_net_export_nchw', 'tr_net_export_nchw_f32', 'tr_net_stats', 'tr_net_set_profile',
     'tr_net_profile',
+    'tr_program_build', 'tr_program_destroy', 'tr_program_info', 'tr_program_copy',
+    'tr_net_create_from_program',
+    'tr_retinaface_create', 'tr_retinaface_forward', 'tr_arcface_create', 'tr_arcface_forward',
+    'tr_openpose_create', 'tr_openpose_forward', 'tr_model_net', 'tr_model_destroy',
     'tr_conv2d', 'tr_sepconv2d',
     'tr_detect_workspace_bytes', 'tr_retinaface_decode_nms', 'tr_retinaface_detect',
-    'tr_l2_normalize', 'tr_face_align',
+    'tr_l2_normalize', 'tr_face_align', 'tr_face_similarity',
     'tr_pose_workspace_bytes', 'tr_openpose_parse', 'tr_bicubic_table',
     'tr_resize_bilinear_u8',
 )
@@ -87,6 +91,22 @@ def lib():
         L.tr_net_set_profile.argtypes = [vp, i32]
         L.tr_net_profile.argtypes = [vp, C.POINTER(f32), C.POINTER(i32), C.POINTER(f64), i32,
                                      C.POINTER(i32)]
+        L.tr_program_build.argtypes = [C.c_char_p, vp, C.c_size_t, i32, C.POINTER(vp)]
+        L.tr_program_destroy.argtypes = [vp]
+        L.tr_program_destroy.restype = None
+        L.tr_program_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_size_t),
+                                      C.POINTER(C.c_int32)]
+        L.tr_program_copy.argtypes = [vp, C.POINTER(BufferDesc), C.POINTER(OpDesc), vp]
+        L.tr_net_create_from_program.argtypes = [vp, C.POINTER(vp)]
+        for name in ('tr_retinaface_create', 'tr_arcface_create', 'tr_openpose_create'):
+            getattr(L, name).argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        L.tr_retinaface_forward.argtypes = [vp, vp, i32, i32, i32, f32, f64, i32, vp, vp, vp]
+        L.tr_arcface_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+        L.tr_openpose_forward.argtypes = [vp, vp, i32, i32, i32, f64, vp, vp, vp, vp, vp]
+        L.tr_model_net.argtypes = [vp]
+        L.tr_model_net.restype = vp
+        L.tr_model_destroy.argtypes = [vp]
+        L.tr_model_destroy.restype = None
         L.tr_conv2d.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32,
                                 i32, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32,
                                 C.POINTER(f32), vp]
@@ -99,6 +119,7 @@ def lib():
         L.tr_retinaface_detect.argtypes = [vp, C.POINTER(i32), f32, f64, i32, vp, vp, vp, vp, vp]
         L.tr_l2_normalize.argtypes = [vp, vp, i32, i32, vp]
         L.tr_face_align.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, vp]
+        L.tr_face_similarity.argtypes = [vp, vp, i32, i32, f32, i32, vp, vp, vp, vp]
         L.tr_pose_workspace_bytes.argtypes = [i32]
         L.tr_pose_workspace_bytes.restype = C.c_size_t
         L.tr_openpose_parse.argtypes = [vp, vp, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp]

@@ -28,6 +28,7 @@ SOURCES = {
     'detect_post.cu': ['-fmad=false'],
     'pose_parse.cu': ['-fmad=false'],
     'net.cu': [],
+    'program.cu': [],
 }
 
 

@@ -71,6 +71,7 @@ struct PatchParams {
   float* sk_ws; int* sk_flags;
   uint32_t idesc, tmem_cols;
   const float* scale; const float* shift; const float* slope;
+  const float* shift9; int cout_pad;   // optional [9][cout_pad] border-class shifts (see ConvArgs)
   int act;
   __half* out; int out_cs, out_coff, cout_store;
   const __half* res; int res_cs, res_coff;
@@ -359,6 +360,40 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int cl = qd * 32 + lane;                       // cout within the tile
       const int cout = t.ct * 128 + cl;
       const float sc = p.scale[cout], sh = p.shift[cout];
+      // Border-class shifts: the three candidates of a pixel group (its position along the R
+      // axis is fixed) are picked once per group, the one of a pixel by its position along the
+      // 8-pixel axis.  Without shift9 all nine are the plain shift.
+      float s9[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) s9[k] = p.shift9 ? p.shift9[k * p.cout_pad + cout] : sh;
+      auto group_shifts = [&](int g, float& first, float& inner, float& last) {
+        const int b = t.b0 + g;
+        const int bc = b == 0 ? 0 : (b >= B_dim - 1 ? 2 : 1);
+        if (p.axis == 0) {               // b = output row, the 8-pixel axis runs along columns
+          first = bc == 0 ? s9[0] : (bc == 1 ? s9[3] : s9[6]);
+          inner = bc == 0 ? s9[1] : (bc == 1 ? s9[4] : s9[7]);
+          last = bc == 0 ? s9[2] : (bc == 1 ? s9[5] : s9[8]);
+        } else {                         // b = output column, the 8-pixel axis runs along rows
+          first = bc == 0 ? s9[0] : (bc == 1 ? s9[1] : s9[2]);
+          inner = bc == 0 ? s9[3] : (bc == 1 ? s9[4] : s9[5]);
+          last = bc == 0 ? s9[6] : (bc == 1 ? s9[7] : s9[8]);
+        }
+      };
+      auto pixel_shift = [&](int i, float first, float inner, float last) {
+        const int a = t.a0 + i;
+        return a == 0 ? first : (a >= A_dim - 1 ? last : inner);
+      };
+      // Residual (staged paths): the residual tile is first copied into the staging tile with
+      // coalesced 16-byte loads ([pixel][cout] layout, like the output), each thread then adds
+      // its channel's value in fp32 before the single rounding to fp16.  Row r of a staging
+      // block that starts at group g0 is pixel (g0 + r / 8, r % 8).
+      auto res_row_ptr = [&](int g0, int r) -> const __half* {
+        const int gg = g0 + (r >> 3), i = r & 7;
+        const int b = t.b0 + gg, a = t.a0 + i;
+        if (gg >= g_end || b >= B_dim || a >= A_dim) return nullptr;
+        const unsigned pix = static_cast<unsigned>(t.n) * p.H * p.W + a * a_step + b * b_step;
+        return p.res + static_cast<size_t>(pix) * p.res_cs + p.res_coff + t.ct * 128;
+      };
       // one activation formula: y = max(y, 0) + neg * min(y, 0)   (ReLU 0, PReLU slope, none 1)
       const float neg = p.act == ACT_RELU ? 0.f : (p.act == ACT_PRELU ? p.slope[cout] : 1.f);
       mbar_wait(tfull_bar(acc), (tile_it >> 1) & 1u, p.err, 4);
@@ -466,11 +501,20 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
           const uint32_t dst = base + static_cast<uint32_t>(g) * 2048u + cl * 2u;
           const int npx = g + 1 < g_end ? 16 : 8;           // the second group may be the other team's
+          float f0, m0, l0, f1, m1, l1;
+          group_shifts(g, f0, m0, l0);
+          group_shifts(g + 1, f1, m1, l1);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             if (i >= npx) break;
-            float y = fmaf(__uint_as_float(v[i]), sc, sh);
+            const float shi = i < 8 ? pixel_shift(i, f0, m0, l0) : pixel_shift(i - 8, f1, m1, l1);
+            float y = fmaf(__uint_as_float(v[i]), sc, shi);
             y = fmaf(fminf(y, 0.f), neg, fmaxf(y, 0.f));
+            if (p.res) {
+              unsigned short rh;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(rh) : "r"(dst + i * 256u));
+              y += __half2float(__ushort_as_half(rh));
+            }
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + i * 256u),
                          "h"(__half_as_ushort(__float2half_rn(y))) : "memory");
           }
@@ -478,6 +522,19 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (n_parts) {
           fetch(pfA, g_begin);
           if (g_begin + 2 < g_end) fetch(pfB, g_begin + 2);
+        }
+        if (p.res) {
+          // this team's rows of the residual tile -> staging (16 lanes per 256-byte pixel row)
+          const int tid = (ew & 3) * 32 + lane;
+          for (int k = tid; k < (g_end - g_begin) * 8 * 16; k += 128) {
+            const int r = k >> 4, c16 = k & 15;
+            const __half* src = res_row_ptr(g_begin, r);
+            const uint4 rv = src ? __ldg(reinterpret_cast<const uint4*>(src) + c16) : make_uint4(0, 0, 0, 0);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(base + static_cast<uint32_t>(g_begin * 8 + r) * 256u + c16 * 16u),
+                           "r"(rv.x), "r"(rv.y), "r"(rv.z), "r"(rv.w) : "memory");
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
         }
         for (int g = g_begin; g < g_end; g += 4) {
           chunk(g, pfA);
@@ -514,8 +571,18 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           if (g + 1 < g_end) { pf[2] = __ldcg(src + 256); pf[3] = __ldcg(src + 257); }
         };
         if (n_parts) fetch_part0(g_begin);
+        const int tid = (ew & 3) * 32 + lane;
         for (int g = g_begin; g < g_end; g += 2) {
           uint32_t v[16];
+          uint4 rv[2];
+          if (p.res) {                       // requested first: in flight during the TMEM read and the math
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int k = tid + 128 * j;
+              const __half* src = res_row_ptr(g, k >> 4);
+              rv[j] = src ? __ldg(reinterpret_cast<const uint4*>(src) + (k & 15)) : make_uint4(0, 0, 0, 0);
+            }
+          }
           __syncwarp();
           tmem_ld16_async(taddr + g * 8, v);
           tmem_ld_wait();
@@ -541,27 +608,40 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               }
             }
           }
-          uint32_t h[8];
+          float y[16];
+          float f0, m0, l0, f1, m1, l1;
+          group_shifts(g, f0, m0, l0);
+          group_shifts(g + 1, f1, m1, l1);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float y0 = fmaf(__uint_as_float(v[2 * i]), sc, sh);
-            float y1 = fmaf(__uint_as_float(v[2 * i + 1]), sc, sh);
-            y0 = fmaf(fminf(y0, 0.f), neg, fmaxf(y0, 0.f));
-            y1 = fmaf(fminf(y1, 0.f), neg, fmaxf(y1, 0.f));
-            const __half2 hh = __floats2half2_rn(y0, y1);   // .x = pixel 2i, .y = pixel 2i + 1
-            h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+          for (int i = 0; i < 16; ++i) {
+            y[i] = fmaf(__uint_as_float(v[i]), sc,
+                        i < 8 ? pixel_shift(i, f0, m0, l0) : pixel_shift(i - 8, f1, m1, l1));
+            y[i] = fmaf(fminf(y[i], 0.f), neg, fmaxf(y[i], 0.f));
           }
           // the previous store of this team has finished READING the staging tile
           if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
           const uint32_t dst = my_stage + cl * 2u;
+          if (p.res) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + (2 * i) * 256u),
-                         "h"(static_cast<unsigned short>(h[i] & 0xffffu)) : "memory");
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + (2 * i + 1) * 256u),
-                         "h"(static_cast<unsigned short>(h[i] >> 16)) : "memory");
+            for (int j = 0; j < 2; ++j) {
+              const int k = tid + 128 * j;
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+                           ::"r"(my_stage + static_cast<uint32_t>(k >> 4) * 256u + (k & 15) * 16u),
+                             "r"(rv[j].x), "r"(rv[j].y), "r"(rv[j].z), "r"(rv[j].w) : "memory");
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              unsigned short rh;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(rh) : "r"(dst + i * 256u));
+              y[i] += __half2float(__ushort_as_half(rh));
+            }
           }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + i * 256u),
+                         "h"(__half_as_ushort(__float2half_rn(y[i]))) : "memory");
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
           if (store_leader && !(p.debug & 4)) {
@@ -593,10 +673,12 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const unsigned pix0 = pix00 + g * b_step;
           const unsigned o0 = pix0 * p.out_cs + p.out_coff + cout, os = a_step * p.out_cs;
           const unsigned r0 = pix0 * p.res_cs + p.res_coff + cout, rs = a_step * p.res_cs;
+          float f0, m0, l0;
+          group_shifts(g, f0, m0, l0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (i < na) {
-              float y = fmaf(__uint_as_float(v[i]), sc, sh);
+              float y = fmaf(__uint_as_float(v[i]), sc, pixel_shift(i, f0, m0, l0));
               y = fmaf(fminf(y, 0.f), neg, fmaxf(y, 0.f));
               if (p.res) y += __half2float(p.res[r0 + i * rs]);
               if (p.out_f32) p.out_f32[o0 + i * os] = y;
@@ -662,7 +744,8 @@ bool conv_patch_eligible(const ConvArgs& a) {
   if (a.stride != 1 || a.kh != a.kw || !(a.kh & 1) || a.pad != a.kh / 2 || a.kh > 9) return false;
   if (a.cin_pad % 64 || a.cout_pad % 128) return false;
   if (a.in.cs % 8 || a.in.coff % 8) return false;
-  if (a.out2.ptr || a.res_up2 || a.shift9) return false;
+  if (a.out2.ptr || a.res_up2) return false;
+  if (a.shift9 && (a.kh != 3 || a.in.H < 2 || a.in.W < 2)) return false;
   if (a.H_out != a.in.H || a.W_out != a.in.W) return false;
   return true;
 }
@@ -724,6 +807,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   p.tmem_cols = cols;
 
   p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.act = a.act;
+  p.shift9 = a.shift9; p.cout_pad = a.cout_pad;
   p.out = a.out.ptr; p.out_cs = a.out.cs; p.out_coff = a.out.coff; p.cout_store = a.cout_store;
   p.res = a.res.ptr; p.res_cs = a.res.cs; p.res_coff = a.res.coff;
   p.out_f32 = a.out_f32;
@@ -763,8 +847,9 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
 
   // TMA-store epilogue: plain fp16 output of whole 128-channel tiles (no residual); the 4-D map
   // {C, W, H, N} clips the ragged border of the 8-pixel groups.
-  p.tma_store = env_int("TRB_PT_TMA_STORE", 1) && !a.res.ptr && !a.out_f32 && a.cout_store % 128 == 0 &&
-                a.out.cs % 8 == 0 && a.out.coff % 8 == 0;
+  p.tma_store = env_int("TRB_PT_TMA_STORE", 1) && !a.out_f32 && a.cout_store % 128 == 0 &&
+                a.out.cs % 8 == 0 && a.out.coff % 8 == 0 &&
+                (!a.res.ptr || (a.res.cs % 8 == 0 && a.res.coff % 8 == 0));
   plan->tmO = plan->tmW;
   if (p.tma_store) {
     const cuuint64_t ocs = a.out.cs;

@@ -338,6 +338,74 @@ face_align_kernel(const uint8_t* __restrict__ frames, int H, int W, const double
 
 }  // namespace
 
+// Five-point similarity per detected face, on the device: the inverse 2x3 matrix (PIL AFFINE
+// data) that maps the 112x112 crop onto the frame, from the landmarks of the detection rows.
+// In two dimensions the least-squares similarity (Umeyama 1991, what skimage's
+// SimilarityTransform.estimate computes; arcface/wrapper.py:47-61) has a closed form — no SVD:
+// with centred landmarks p and template points q,
+//     a = sum p.q,  b = sum p x q,  rotation = atan2(b, a),  scale = hypot(a, b) / sum |p|^2
+// (hypot(a, b) = S0 + d S1 of Umeyama's diag(1, d), also when the best orthogonal fit would
+// be a reflection).  Landmarks are first mapped back to frame pixels exactly like
+// Detection.resize_out does (float32 value / float32 scale, round half to even), because
+// that is what the reference's extract_features is given.
+__global__ void face_similarity_kernel(const float* __restrict__ det, const int* __restrict__ count,
+                                       int N, int max_det, float scale, int cap,
+                                       double* __restrict__ coef, int* __restrict__ image_index,
+                                       int* __restrict__ total) {
+  // float32 template, x shifted by 8 IN float32 for the 112-wide crop (wrapper.py:39-48)
+  const float txf[5] = {30.2946f + 8.0f, 65.5318f + 8.0f, 48.0252f + 8.0f, 33.5493f + 8.0f, 62.7299f + 8.0f};
+  const float tyf[5] = {51.6963f, 51.5014f, 71.7366f, 92.3655f, 92.2041f};
+  const int n = blockIdx.x;
+  int base = 0;
+  for (int i = 0; i < n; ++i) base += min(count[i], max_det);
+  const int cnt = min(count[n], max_det);
+  if (n == N - 1 && threadIdx.x == 0) *total = base + cnt;
+  for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+    const int f = base + k;
+    if (f >= cap) continue;
+    const float* row = det + (static_cast<long>(n) * max_det + k) * 16;
+    double px[5], py[5], mx = 0, my = 0, qx = 0, qy = 0;
+    for (int j = 0; j < 5; ++j) {
+      px[j] = static_cast<double>(rintf(row[5 + 2 * j] / scale));
+      py[j] = static_cast<double>(rintf(row[6 + 2 * j] / scale));
+      mx += px[j]; my += py[j];
+      qx += static_cast<double>(txf[j]);
+      qy += static_cast<double>(tyf[j]);
+    }
+    mx /= 5; my /= 5; qx /= 5; qy /= 5;
+    double a = 0, b = 0, var = 0;
+    for (int j = 0; j < 5; ++j) {
+      const double ux = px[j] - mx, uy = py[j] - my;
+      const double vx = static_cast<double>(txf[j]) - qx;
+      const double vy = static_cast<double>(tyf[j]) - qy;
+      a += ux * vx + uy * vy;
+      b += ux * vy - uy * vx;
+      var += ux * ux + uy * uy;
+    }
+    double* o = coef + 6 * f;
+    image_index[f] = n;
+    const double nrm = sqrt(a * a + b * b);
+    if (!(var > 0.0) || !(nrm > 0.0)) {           // degenerate landmarks: skimage returns NaNs
+      for (int j = 0; j < 6; ++j) o[j] = nan("");
+      continue;
+    }
+    const double s = nrm / var, c = a / nrm, sn = b / nrm;
+    // forward: q = s R p + t,  R = [[c, -sn], [sn, c]],  t = mu_q - s R mu_p
+    const double t0 = qx - s * (c * mx - sn * my), t1 = qy - s * (sn * mx + c * my);
+    // inverse: p = R^T (q - t) / s
+    const double is = 1.0 / s;
+    o[0] = c * is;  o[1] = sn * is; o[2] = -(c * t0 + sn * t1) * is;
+    o[3] = -sn * is; o[4] = c * is; o[5] = -(-sn * t0 + c * t1) * is;
+  }
+}
+
+void face_similarity_launch(const float* det, const int* count, int N, int max_det, float scale,
+                            int cap, double* coef, int* image_index, int* total, cudaStream_t s) {
+  if (N == 0) return;
+  face_similarity_kernel<<<N, 64, 0, s>>>(det, count, N, max_det, scale, cap, coef, image_index, total);
+  TR_CUDA(cudaGetLastError());
+}
+
 void face_align_launch(const uint8_t* frames, int H, int W, const double* coef,
                        const int* image_index, int F, uint8_t* out, int S, cudaStream_t s) {
   if (F == 0) return;

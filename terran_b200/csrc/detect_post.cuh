@@ -41,6 +41,8 @@ void pose_parse_launch(const float* paf, const float* heat, int N, int h, int w,
 void bicubic_table_host(float out[32]);
 
 // ---- face alignment (PIL-exact inverse affine bilinear warp to (F,3,S,S) BGR)
+void face_similarity_launch(const float* det, const int* count, int N, int max_det, float scale,
+                            int cap, double* coef, int* image_index, int* total, cudaStream_t s);
 void face_align_launch(const uint8_t* frames, int H, int W, const double* coef,
                        const int* image_index, int F, uint8_t* out, int S, cudaStream_t s);
 

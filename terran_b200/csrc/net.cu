@@ -5,6 +5,8 @@
 // activation buffers, builds the TMA tensor maps / launch geometry of each op
 // (a "plan", cached by (N,H,W)) and then a run is a plain sequence of kernel
 // launches on the caller's stream.
+#include <algorithm>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <tuple>
@@ -12,6 +14,7 @@
 
 #include "../../include/terran_b200.h"
 #include "detect_post.cuh"
+#include "program.h"
 
 namespace trb {
 
@@ -119,9 +122,13 @@ bool patch_wanted(const ConvArgs& a) {
   // 64..512 input channels) once the map is large enough for the 8 x R tiles to fill their
   // MMA columns; small maps (ArcFace 14x14 / 7x7) waste too many of them.
   const int H = a.H_out, W = a.W_out;
-  auto fill = [](int n, int g) { return double(n) / (double(g) * ((n + g - 1) / g)); };
-  const double best = std::max(fill(W, 8) * std::max(fill(H, 24), fill(H, 32)),
-                               fill(H, 8) * std::max(fill(W, 24), fill(W, 32)));
+  auto fill8 = [](int n) { return double(n) / (8.0 * ((n + 7) / 8)); };
+  auto fill_r = [](int n) {            // best fill with R in [20, 32] rows per tile (N = 160..256)
+    double best = 0;
+    for (int r = 20; r <= 32; r += 2) best = std::max(best, double(n) / (double(r) * ((n + r - 1) / r)));
+    return best;
+  };
+  const double best = std::max(fill8(W) * fill_r(H), fill8(H) * fill_r(W));
   return best >= 0.85;
 }
 
@@ -700,6 +707,15 @@ int tr_face_align(const uint8_t* frames_dev, int H, int W, const double* coef_de
   });
 }
 
+int tr_face_similarity(const float* det_dev, const int32_t* count_dev, int N, int max_det, float scale,
+                       int cap, double* coef_dev, int32_t* image_index_dev, int32_t* total_dev,
+                       void* stream) {
+  return guarded([&] {
+    face_similarity_launch(det_dev, count_dev, N, max_det, scale, cap, coef_dev, image_index_dev,
+                           total_dev, static_cast<cudaStream_t>(stream));
+  });
+}
+
 size_t tr_pose_workspace_bytes(int N) { return pose_workspace_bytes(N); }
 
 int tr_openpose_parse(const float* paf_dev, const float* heat_dev, int N, int h, int w, double scale,
@@ -713,6 +729,148 @@ int tr_openpose_parse(const float* paf_dev, const float* heat_dev, int N, int h,
 }
 
 void tr_bicubic_table(float out32[32]) { bicubic_table_host(out32); }
+
+
+/* ---- programs and single-call models ------------------------------------- */
+struct tr_program { trb::Program p; };
+
+struct tr_model {
+  int kind = 0;                 // 0 retinaface, 1 arcface, 2 openpose
+  tr_net* net = nullptr;
+  int roles[8];
+  void* ws = nullptr; size_t ws_bytes = 0;      // post-processing workspace
+  float* f0 = nullptr; size_t f0_bytes = 0;     // PAF / raw embedding
+  float* f1 = nullptr; size_t f1_bytes = 0;     // heat maps
+  int32_t* cand = nullptr; size_t cand_bytes = 0;
+  ~tr_model() {
+    if (net) tr_net_destroy(net);
+    for (void* p : {ws, static_cast<void*>(f0), static_cast<void*>(f1), static_cast<void*>(cand)})
+      if (p) cudaFree(p);
+  }
+};
+
+extern "C++" {
+namespace {
+template <class T>
+void grow(T*& ptr, size_t& have, size_t need) {
+  if (have >= need) return;
+  if (ptr) TR_CUDA(cudaFree(ptr));
+  ptr = nullptr; have = 0;
+  TR_CUDA(cudaMalloc(reinterpret_cast<void**>(&ptr), need));
+  have = need;
+}
+
+int model_create(const char* name, int kind, const void* blob, size_t bytes, tr_model** out) {
+  return guarded([&] {
+    auto prog = std::make_unique<tr_program>();
+    trb::program_build(name, blob, bytes, 0, prog->p);
+    auto m = std::make_unique<tr_model>();
+    m->kind = kind;
+    for (int i = 0; i < 8; ++i) m->roles[i] = prog->p.roles[i];
+    if (tr_net_create_from_program(prog.get(), &m->net) != 0) fail(g_last_error);
+    *out = m.release();
+  });
+}
+}  // namespace
+}  // extern "C++"
+
+int tr_program_build(const char* model, const void* state_dict_blob, size_t bytes, int flags,
+                     tr_program** out) {
+  return guarded([&] {
+    auto prog = std::make_unique<tr_program>();
+    trb::program_build(model, state_dict_blob, bytes, flags, prog->p);
+    *out = prog.release();
+  });
+}
+
+void tr_program_destroy(tr_program* program) { delete program; }
+
+int tr_program_info(const tr_program* program, int* n_buffers, int* n_ops, size_t* blob_bytes,
+                    int32_t* roles8) {
+  return guarded([&] {
+    *n_buffers = int(program->p.buffers.size());
+    *n_ops = int(program->p.ops.size());
+    *blob_bytes = program->p.blob.size();
+    for (int i = 0; i < 8; ++i) roles8[i] = program->p.roles[i];
+  });
+}
+
+int tr_program_copy(const tr_program* program, tr_buffer_desc* buffers, tr_op_desc* ops, void* blob) {
+  return guarded([&] {
+    std::copy(program->p.buffers.begin(), program->p.buffers.end(), buffers);
+    std::copy(program->p.ops.begin(), program->p.ops.end(), ops);
+    memcpy(blob, program->p.blob.data(), program->p.blob.size());
+  });
+}
+
+int tr_net_create_from_program(const tr_program* program, tr_net** out) {
+  const trb::Program& p = program->p;
+  return tr_net_create(p.buffers.data(), int(p.buffers.size()), p.ops.data(), int(p.ops.size()),
+                       p.blob.data(), p.blob.size(), out);
+}
+
+int tr_retinaface_create(const void* blob, size_t bytes, tr_model** out) {
+  return model_create("retinaface", 0, blob, bytes, out);
+}
+int tr_arcface_create(const void* blob, size_t bytes, tr_model** out) {
+  return model_create("arcface", 1, blob, bytes, out);
+}
+int tr_openpose_create(const void* blob, size_t bytes, tr_model** out) {
+  return model_create("openpose", 2, blob, bytes, out);
+}
+tr_net* tr_model_net(tr_model* model) { return model->net; }
+void tr_model_destroy(tr_model* model) { delete model; }
+
+int tr_retinaface_forward(tr_model* m, const uint8_t* frames_dev, int N, int H, int W, float threshold,
+                          double nms_threshold, int max_det, int32_t* count_dev, float* det_dev,
+                          void* stream) {
+  return guarded([&] {
+    TR_CHECK(m->kind == 0, "not a RetinaFace model");
+    // model channel order is BGR: start at channel 2 and walk backwards (retinaface/wrapper.py:144-146)
+    if (tr_net_run(m->net, frames_dev + 2, N, H, W, int64_t(H) * W * 3, int64_t(W) * 3, 3, -1, stream)) fail(g_last_error);
+    grow(m->ws, m->ws_bytes, tr_detect_workspace_bytes(N, H, W));
+    grow(m->cand, m->cand_bytes, size_t(N) * 4);
+    if (tr_retinaface_detect(m->net, m->roles, threshold, nms_threshold, max_det, m->ws, count_dev, m->cand,
+                             det_dev, stream)) fail(g_last_error);
+  });
+}
+
+int tr_arcface_forward(tr_model* m, const uint8_t* crops_dev, int N, int layout, int normalise, float* emb_dev,
+                       void* stream) {
+  return guarded([&] {
+    TR_CHECK(m->kind == 1, "not an ArcFace model");
+    const int S = 112;
+    int rc = layout == 0
+                 ? tr_net_run(m->net, crops_dev + 2, N, S, S, int64_t(S) * S * 3, int64_t(S) * 3, 3, -1, stream)
+                 : tr_net_run(m->net, crops_dev, N, S, S, int64_t(3) * S * S, S, 1, int64_t(S) * S, stream);
+    if (rc) fail(g_last_error);
+    if (!normalise) {
+      if (tr_net_export_nchw_f32(m->net, m->roles[0], 0, 512, emb_dev, 0, stream)) fail(g_last_error);
+      return;
+    }
+    grow(m->f0, m->f0_bytes, size_t(N) * 512 * 4);
+    if (tr_net_export_nchw_f32(m->net, m->roles[0], 0, 512, m->f0, 0, stream)) fail(g_last_error);
+    if (tr_l2_normalize(m->f0, emb_dev, N, 512, stream)) fail(g_last_error);
+  });
+}
+
+int tr_openpose_forward(tr_model* m, const uint8_t* frames_dev, int N, int H, int W, double scale,
+                        int32_t* count_dev, int32_t* keypoints_dev, double* score_dev, int32_t* status_dev,
+                        void* stream) {
+  return guarded([&] {
+    TR_CHECK(m->kind == 2, "not an OpenPose model");
+    if (tr_net_run(m->net, frames_dev, N, H, W, int64_t(H) * W * 3, int64_t(W) * 3, 3, 1, stream)) fail(g_last_error);
+    void* ptr; int n, h, w, c;
+    if (tr_net_buffer(m->net, m->roles[0], &ptr, &n, &h, &w, &c)) fail(g_last_error);
+    grow(m->f0, m->f0_bytes, size_t(N) * 38 * h * w * 4);
+    grow(m->f1, m->f1_bytes, size_t(N) * 19 * h * w * 4);
+    if (tr_net_export_nchw(m->net, m->roles[0], m->roles[1], 38, m->f0, stream)) fail(g_last_error);
+    if (tr_net_export_nchw(m->net, m->roles[0], m->roles[2], 19, m->f1, stream)) fail(g_last_error);
+    grow(m->ws, m->ws_bytes, tr_pose_workspace_bytes(N));
+    if (tr_openpose_parse(m->f0, m->f1, N, h, w, scale, m->ws, count_dev, keypoints_dev, score_dev, status_dev,
+                          stream)) fail(g_last_error);
+  });
+}
 
 int tr_resize_bilinear_u8(const uint8_t* src_dev, int N, int H, int W, uint8_t* dst_dev, int h,
                           int w, void* stream) {

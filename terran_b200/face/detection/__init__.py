@@ -64,7 +64,9 @@ class Detection:
                 frames, scales = resize_short_side(to_device_u8(images, idx), self.short_side)
                 if hasattr(model, 'detect_async'):
                     pending = model.detect_async(frames)
-                    return _Deferred(lambda: _first(pending.result(scale=scales), single))
+                    handle = _Deferred(lambda: _first(pending.result(scale=scales), single))
+                    handle.pending, handle.scale = pending, scales     # for device-resident consumers
+                    return handle
             offsets = None
         else:
             if isinstance(images, torch.Tensor):

@@ -108,7 +108,7 @@ class RetinaFace:
         done = torch.cuda.Event()
         done.record()
         self.last_candidates = cand
-        return PendingDetections(self, frames, threshold, max_det, slot, done)
+        return PendingDetections(self, frames, threshold, max_det, slot, done, count, det)
 
     def _host_slot(self, N, max_det):
         """Pinned result buffers, three sets in rotation (a result may still be
@@ -140,9 +140,13 @@ class RetinaFace:
 class PendingDetections:
     """Results of ``RetinaFace.detect_async`` still in flight."""
 
-    def __init__(self, model, frames, threshold, max_det, slot, done):
+    def __init__(self, model, frames, threshold, max_det, slot, done, count_dev=None, det_dev=None):
         self.model, self.frames, self.threshold = model, frames, threshold
         self.max_det, self.slot, self.done = max_det, slot, done
+        #: device copies of (count (N,), rows (N,max_det,16)) for consumers that stay on the
+        #: GPU (``ArcFace.embed_detections``: detect -> align -> embed without a host round trip)
+        self.count_dev, self.det_dev = count_dev, det_dev
+        self.stream = torch.cuda.current_stream()
 
     def arrays(self):
         """(counts (N,), rows (N,R,16)) on the host; blocks until the copy landed."""
@@ -151,8 +155,11 @@ class PendingDetections:
         top = int(counts.max()) if len(counts) else 0
         if top > self.max_det:
             # rare: more survivors than rows were copied — redo synchronously with room
-            with torch.cuda.device(self.model.device_index):
+            with torch.cuda.device(self.model.device_index), torch.cuda.stream(self.stream):
+                # (on the stream the batch was submitted on: the net's activation buffers are
+                # shared with whatever that stream runs next)
                 count, _, det = self.model.detect_device(self.frames, self.threshold, max_det=top)
+                self.count_dev, self.det_dev, self.max_det = count, det, top
                 return count.cpu().numpy(), det.cpu().numpy()
         return counts, self.slot['det'][:, :max(top, 1)].numpy().copy()
 

@@ -66,6 +66,34 @@ def umeyama_similarity(src, dst):
     return T
 
 
+def similarity_coefficients(landmarks, image_size=(112, 112)):
+    """Vectorised ``alignment_coefficients`` for (F,5,2) landmarks -> (F,6) float64, in closed
+    form: in 2-D the least-squares similarity needs no SVD — with centred landmarks p and
+    template points q, ``a = sum p.q``, ``b = sum p x q``, rotation ``atan2(b, a)``, scale
+    ``hypot(a, b) / sum |p|^2`` (= Umeyama's ``S @ d / var``, reflections included).  The same
+    arithmetic runs on the device in ``tr_face_similarity``.  Agrees with
+    ``umeyama_similarity`` + ``np.linalg.inv`` to ~1e-12 (tests/test_host_logic.py)."""
+    template = LANDMARK_TEMPLATE.copy()
+    if image_size[1] == 112:
+        template[:, 0] += 8.0
+    p = np.asarray(landmarks).astype(np.float32).astype(np.float64).reshape(-1, 5, 2)
+    q = template.astype(np.float64)
+    mp, mq = p.mean(1, keepdims=True), q.mean(0, keepdims=True)
+    u, v = p - mp, (q - mq)[None]
+    a = (u * v).sum((1, 2))
+    b = (u[..., 0] * v[..., 1] - u[..., 1] * v[..., 0]).sum(1)
+    var = (u * u).sum((1, 2))
+    nrm = np.hypot(a, b)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        s, c, sn = nrm / var, a / nrm, b / nrm
+        t0 = mq[0, 0] - s * (c * mp[:, 0, 0] - sn * mp[:, 0, 1])
+        t1 = mq[0, 1] - s * (sn * mp[:, 0, 0] + c * mp[:, 0, 1])
+        out = np.stack([c / s, sn / s, -(c * t0 + sn * t1) / s,
+                        -sn / s, c / s, -(-sn * t0 + c * t1) / s], axis=1)
+    out[~((var > 0) & (nrm > 0))] = np.nan
+    return out
+
+
 def alignment_coefficients(landmark, image_size=(112, 112)):
     """The 6 PIL ``AFFINE`` coefficients (first two rows of the inverse
     similarity landmarks -> template) of reference ``preprocess_face`` :39-61."""
@@ -138,12 +166,11 @@ class ArcFace:
         with the PIL warp of the host path); the 2x3 matrices are estimated on the
         host (five points per face)."""
         S = self.image_side
-        coefs, index = [], []
-        for i, faces in enumerate(faces_per_image):
-            for face in faces:
-                coefs.append(alignment_coefficients(face['landmarks'], (S, S)))
-                index.append(i)
+        index = [i for i, faces in enumerate(faces_per_image) for _ in faces]
         F = len(index)
+        coefs = similarity_coefficients(
+            np.stack([face['landmarks'] for faces in faces_per_image for face in faces])
+            if F else np.zeros((0, 5, 2)), (S, S))
         out = torch.empty((F, 3, S, S), dtype=torch.uint8, device=frames.device)
         if F:
             N, H, W, _ = frames.shape
@@ -154,6 +181,39 @@ class ArcFace:
                 C.c_void_p(idx.data_ptr()), F, C.c_void_p(out.data_ptr()), S,
                 nat.current_stream_ptr()))
         return out
+
+    def embed_detections(self, frames, pending, scale):
+        """Device-resident detect -> align -> embed: ``pending`` is the ``PendingDetections`` of
+        ``RetinaFace.detect_async`` on (the resized copy of) ``frames`` (CUDA uint8 (N,H,W,3)),
+        ``scale`` the detector's resize factor.  The 5-point similarity of every face is fitted on
+        the device from the detection rows (``tr_face_similarity``), the crops are warped on the
+        device (``tr_face_align``) and embedded; the landmarks never visit the host — only the
+        per-frame face COUNT does, because the embedding batch size has to be known to launch.
+        Returns (features (F,512) fp32 CUDA, counts (N,) numpy); equals
+        ``call(frames, faces)`` with the faces ``Detection`` returns."""
+        S = self.image_side
+        pending.done.synchronize()                        # the counts are in pinned host memory
+        counts = np.minimum(pending.slot['count'].numpy(), pending.max_det).astype(np.int64)
+        if pending.count_dev is None or int(counts.max(initial=0)) > pending.max_det:
+            raise nat.NativeError('detections are not resident on the device')
+        F = int(counts.sum())
+        dev = frames.device
+        if F == 0:
+            return torch.empty((0, 512), dtype=torch.float32, device=dev), counts
+        N, H, W, _ = frames.shape
+        coef = torch.empty((F, 6), dtype=torch.float64, device=dev)
+        idx = torch.empty(F, dtype=torch.int32, device=dev)
+        total = torch.empty(1, dtype=torch.int32, device=dev)
+        crops = torch.empty((F, 3, S, S), dtype=torch.uint8, device=dev)
+        stream = nat.current_stream_ptr()
+        nat.check(nat.lib().tr_face_similarity(
+            C.c_void_p(pending.det_dev.data_ptr()), C.c_void_p(pending.count_dev.data_ptr()), N,
+            pending.max_det, float(scale), F, C.c_void_p(coef.data_ptr()), C.c_void_p(idx.data_ptr()),
+            C.c_void_p(total.data_ptr()), stream))
+        nat.check(nat.lib().tr_face_align(
+            C.c_void_p(frames.data_ptr()), H, W, C.c_void_p(coef.data_ptr()),
+            C.c_void_p(idx.data_ptr()), F, C.c_void_p(crops.data_ptr()), S, stream))
+        return self.embed_device(crops, 'nchw_bgr'), counts
 
     def call(self, images, faces_per_image=None):
         """Feature extraction (reference ``ArcFace.call`` :109-184)."""

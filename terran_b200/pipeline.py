@@ -90,11 +90,15 @@ class PerceptionPipeline:
     the synchronous per-batch loop of the reference's ``examples/video.py``,
     software-pipelined."""
 
-    def __init__(self, detection, estimation, device=default_device, tracker=None):
+    def __init__(self, detection, estimation, device=default_device, tracker=None, recognition=None):
         """tracker: optional ``terran_b200.tracking.Sort``; ``run`` then feeds it the faces of
         every frame in stream order (tracking is the one consumer that needs frame order) and
         yields the faces with their ``track`` field (reference: ``examples/match.py:31-40``)."""
         self.detection, self.estimation = detection, estimation
+        #: optional ``Recognition``: every detected face is aligned and embedded on the device
+        #: right after detection (reference pipeline shape: ``examples/match.py:29-33``); the
+        #: results then are (faces, features_per_image, poses)
+        self.recognition = recognition
         self.tracker = tracker
         self.device_index = cuda_index(device)
         self.streams = [torch.cuda.Stream(device=self.device_index) for _ in range(2)]
@@ -109,7 +113,34 @@ class PerceptionPipeline:
                 if isinstance(frames, torch.Tensor) and frames.is_cuda:
                     frames.record_stream(stream)     # allocated on the feeder's copy stream
                 handles.append(fn(frames))
+        if self.recognition is not None:
+            handles.insert(1, self._submit_recognition(frames, handles[0]))
         return _PendingPair(handles)
+
+    def _submit_recognition(self, frames, det_handle):
+        """Embed the faces of ``det_handle`` on the detection stream.  Frames that did not go
+        through the device path (lists of images) fall back to the public call."""
+        rec = self.recognition
+        if rec.model is None:
+            rec.model = rec.recognition_cls(device=rec.device)
+        pending = getattr(det_handle, 'pending', None)
+        if pending is None or not hasattr(rec.model, 'embed_detections'):
+            return _Lazy(lambda: rec(frames, det_handle.result()))
+        from terran_b200.frames import to_device_u8
+        with torch.cuda.device(self.device_index), torch.cuda.stream(self.streams[0]):
+            dev_frames = to_device_u8(frames, self.device_index)
+            features, counts = rec.model.embed_detections(dev_frames, pending, det_handle.scale)
+            host = torch.empty(features.shape, dtype=torch.float32).pin_memory()
+            host.copy_(features, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+
+        def finish():
+            done.synchronize()
+            splits = np.cumsum(counts)[:-1]
+            return [np.empty((0, 512)) if not c else part      # (float64 empties, as upstream)
+                    for c, part in zip(counts, np.split(host.numpy(), splits, axis=0))]
+        return _Lazy(finish)
 
     def __call__(self, frames):
         return self.submit(frames).result()
@@ -128,11 +159,21 @@ class PerceptionPipeline:
     def _tracked(self, result):
         if self.tracker is None:
             return result
-        faces, poses = result
-        return [self.tracker.update(f) for f in faces], poses
+        faces, rest = result[0], result[1:]
+        return ([self.tracker.update(f) for f in faces],) + tuple(rest)
 
     def close(self):
         pass
+
+
+class _Lazy:
+    def __init__(self, fn):
+        self._fn, self._done, self._value = fn, False, None
+
+    def result(self):
+        if not self._done:
+            self._value, self._done, self._fn = self._fn(), True, None
+        return self._value
 
 
 class _PendingPair:

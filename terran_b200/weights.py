@@ -155,209 +155,75 @@ class Program:
         self._op(type=nat.TR_OP_VIEW, in_=in_, out=out)
 
 
-def bn_fold(sd, prefix, eps, conv_bias=None):
-    """(scale, shift) of BN(conv + bias) as an affine of the conv output."""
-    g, b = sd[prefix + '.weight'].double(), sd[prefix + '.bias'].double()
-    m, v = sd[prefix + '.running_mean'].double(), sd[prefix + '.running_var'].double()
-    scale = g / torch.sqrt(v + eps)
-    bias = conv_bias.double() if conv_bias is not None else 0.0
-    shift = b + (bias - m) * scale
-    return scale.float().numpy(), shift.float().numpy()
+def pack_state_dict(sd):
+    """Serialise a reference ``state_dict`` into the flat "TRSD" blob the C ABI takes
+    (``include/terran_b200.h``): named float32 / int64 tensors, 8-byte aligned data."""
+    import struct
+    out = bytearray(b'TRSD' + struct.pack('<II', 1, len(sd)))
+    for name, t in sd.items():
+        t = t.detach().cpu()
+        if t.dtype == torch.int64:
+            code, arr = 1, t.numpy()
+        else:
+            code, arr = 0, t.float().numpy()
+        arr = np.ascontiguousarray(arr)
+        nb = name.encode()
+        out += struct.pack('<H', len(nb)) + nb + struct.pack('<BB', code, arr.ndim)
+        out += struct.pack(f'<{arr.ndim}q', *arr.shape) + struct.pack('<Q', arr.nbytes)
+        out += b'\0' * ((-len(out)) % 8)
+        out += arr.tobytes()
+    return bytes(out)
 
 
-def pre_bn_fold(w, s0, t0, s1, t1):
-    """Fold a per-channel affine ``x*s0 + t0`` that PRECEDES a zero-padded 3x3 stride-1 conv
-    (and the affine ``y*s1 + t1`` that follows it) into the conv:
+def native_program(model, sd, flags=0):
+    """Build the layer program of ``model`` ('retinaface' | 'arcface' | 'openpose') from a
+    reference ``state_dict`` with the library's own builder (``csrc/program.cu`` — the same code a
+    non-Python host reaches through ``tr_*_create``).  Host-only: works without a GPU.
+    Returns (Program, roles[8])."""
+    blob = pack_state_dict(sd)
+    buf = np.frombuffer(blob, dtype=np.uint8)            # 8-byte aligned host copy
+    handle = C.c_void_p()
+    nat.check(nat.lib().tr_program_build(model.encode(), C.c_void_p(buf.ctypes.data), len(blob),
+                                         int(flags), C.byref(handle)))
+    try:
+        nb, no, nbytes = C.c_int(), C.c_int(), C.c_size_t()
+        roles = (C.c_int32 * 8)()
+        nat.check(nat.lib().tr_program_info(handle, C.byref(nb), C.byref(no), C.byref(nbytes), roles))
+        bufs = (nat.BufferDesc * nb.value)()
+        ops = (nat.OpDesc * no.value)()
+        data = (C.c_uint8 * nbytes.value)()
+        nat.check(nat.lib().tr_program_copy(handle, bufs, ops, data))
+    finally:
+        nat.lib().tr_program_destroy(handle)
+    P = Program()
+    P.buffers = [(b.channels, b.is_f32) for b in bufs]
+    P.ops = list(ops)
+    P.blob = bytearray(bytes(data))
+    return P, list(roles)
 
-        conv_W(pad(x*s0 + t0)) * s1 + t1  =  conv_{W*s0}(pad(x)) * s1 + shift9[class]
-
-    Padding is applied AFTER the first affine, so its shift only reaches the taps that are in
-    bounds: the input-independent term ``sum_{taps in bounds} W[:, :, tap] @ t0`` depends on the
-    output pixel's border class (3 row classes x 3 column classes).  Returns (w * s0,
-    shift9 (9, cout)) with class = 3*row_class + col_class, 0 = first, 1 = inner, 2 = last."""
-    w = w.detach().double()
-    s0, t0 = torch.as_tensor(s0).double(), torch.as_tensor(t0).double()
-    s1, t1 = torch.as_tensor(s1).double(), torch.as_tensor(t1).double()
-    per_tap = torch.einsum('oikl,i->okl', w, t0)            # (cout, 3, 3)
-    shift9 = torch.empty((9, w.shape[0]), dtype=torch.float64)
-    rows = {0: (1, 2), 1: (0, 1, 2), 2: (0, 1)}             # filter rows that stay in bounds
-    for rc, rs in rows.items():
-        for cc, cs in rows.items():
-            term = per_tap[:, list(rs)][:, :, list(cs)].sum((1, 2))
-            shift9[rc * 3 + cc] = term * s1 + t1
-    return (w * s0.view(1, -1, 1, 1)).float(), shift9.float().numpy()
-
-
-# ------------------------------------------------------------------ RetinaFace
 
 def retinaface_program(sd, fused=None):
-    """Program + roles for reference ``RetinaFace`` (retinaface/model.py:319-341).
-    The stem reads the frame in MODEL channel order (BGR); callers with RGB
-    memory pass a pointer to channel 2 and a channel stride of -1.
-
-    ``fused`` (default: env ``TRB_RETINA_FUSED`` != 0): every depthwise 3x3 of the backbone
-    runs inside the 1x1 conv that consumes it (one ``TR_OP_SEPCONV`` per pair) and the
-    refiner / context / head convs go to the warp-level mma.sync kernel; otherwise one op
-    per reference layer on the tcgen05 / direct kernels."""
+    """Program + roles for reference ``RetinaFace`` (retinaface/model.py:319-341).  The stem
+    reads the frame in MODEL channel order (BGR); callers with RGB memory pass a pointer to
+    channel 2 and a channel stride of -1.  ``fused`` (default: env ``TRB_RETINA_FUSED`` != 0):
+    every depthwise 3x3 of the backbone runs inside the 1x1 conv that consumes it and the
+    small-channel convs go to the warp-level mma.sync kernel; otherwise one op per layer."""
     import os
     if fused is None:
         fused = os.environ.get('TRB_RETINA_FUSED', '1') != '0'
-    P = Program()
-    relu = nat.TR_ACT_RELU
-    engine = nat.TR_ENGINE_MMA if fused else nat.TR_ENGINE_AUTO
-
-    def cbr(pc, pb, in_, out, eps, **kw):
-        s, t = bn_fold(sd, pb, eps, sd.get(pc + '.bias'))
-        w = sd[pc + '.weight']
-        # measured (profiles/r01_retinaface_mma.txt): the warp-level kernel wins where either
-        # channel count is <= 16; the 64-channel 3x3 / lateral 1x1 layers stay on tcgen05
-        eng = engine if min(w.shape[0], w.shape[1]) <= 16 else nat.TR_ENGINE_AUTO
-        P.conv(w, s, t, in_, out, act=relu, engine=eng, **kw)
-
-    b = P.buffer(8)
-    s, t = bn_fold(sd, 'base.first_conv_block.1', 1e-5)
-    P.stem(sd['base.first_conv_block.0.weight'], s, t, b, stride=2, act=relu)
-
-    # The backbone is stem -> dw -> [1x1 -> dw]* -> 1x1 (ConvSepBlock = 1x1 conv_block then
-    # depthwise sep_block, model.py:6-50).  Pair every depthwise with the 1x1 that FOLLOWS it.
-    blocks = [(f'base.scales.{si}.{bi}', cout, stride)
-              for si, bl in enumerate(RETINAFACE_SCALES) for bi, (_cin, cout, stride) in enumerate(bl)]
-    blocks.append(('base.final_conv.0', 256, 1))
-    tap_after = {len(RETINAFACE_SCALES[0]) - 1, len(RETINAFACE_SCALES[0]) + len(RETINAFACE_SCALES[1]) - 1}
-    pending = ('base.first_conv_block.3', 'base.first_conv_block.4', 1)   # (dw conv, dw bn, stride)
-    x, ch = b, 8
-    taps = []
-    pointwise = [(p + '.conv_block.0', p + '.conv_block.1', c) for p, c, _ in blocks]
-    pointwise.append(('base.final_conv.1', 'base.final_conv.2', 256))
-    next_dw = [(p + '.sep_block.0', p + '.sep_block.1', st) for p, _, st in blocks] + [None]
-    for i, ((pc, pb, cout), nxt) in enumerate(zip(pointwise, next_dw)):
-        dwc, dwb, stride = pending
-        ds, dt = bn_fold(sd, dwb, 1e-5)
-        s, t = bn_fold(sd, pb, 1e-5)
-        y = P.buffer(cout)
-        if fused:
-            P.sepconv(sd[dwc + '.weight'], ds, dt, sd[pc + '.weight'], s, t, x, y, stride=stride)
-        else:
-            d = P.buffer(ch)
-            P.dwconv(sd[dwc + '.weight'], ds, dt, x, d, stride=stride)
-            P.conv(sd[pc + '.weight'], s, t, d, y, act=relu)
-        if i in tap_after:
-            taps.append(y)
-        x, ch, pending = y, cout, nxt
-    c32 = x
-    c8, c16 = taps
-
-    e = 2e-5
-    p32 = P.buffer(64)
-    cbr('refiner.conv_stride32.0', 'refiner.conv_stride32.1', c32, p32, e)
-    p16 = P.buffer(64)
-    cbr('refiner.conv_stride16.0', 'refiner.conv_stride16.1', c16, p16, e, res=p32, res_up2=1)
-    a16 = P.buffer(64)
-    cbr('refiner.aggr_stride16.0', 'refiner.aggr_stride16.1', p16, a16, e)
-    p8 = P.buffer(64)
-    cbr('refiner.conv_stride8.0', 'refiner.conv_stride8.1', c8, p8, e, res=a16, res_up2=1)
-    a8 = P.buffer(64)
-    cbr('refiner.aggr_stride8.0', 'refiner.aggr_stride8.1', p8, a8, e)
-
-    heads, ctxs = {}, {}
-    for stride, feat in ((8, a8), (16, a16), (32, p32)):
-        p = f'refiner.context_stride{stride}'
-        ctx = P.buffer(64)
-        red = P.buffer(16)
-        tmp = P.buffer(16)
-        cbr(p + '.context_3x3.0', p + '.context_3x3.1', feat, ctx, e, out_coff=0)
-        cbr(p + '.dimension_reducer.0', p + '.dimension_reducer.1', feat, red, e)
-        cbr(p + '.context_5x5.0', p + '.context_5x5.1', red, ctx, e, out_coff=32)
-        cbr(p + '.context_7x7.0', p + '.context_7x7.1', red, tmp, e)
-        cbr(p + '.context_7x7.3', p + '.context_7x7.4', tmp, ctx, e, out_coff=48)
-        # fused head: [4 class logits | 8 bbox | 20 landmark] -> fp32
-        w = torch.cat([sd[f'outputs.cls_stride{stride}.weight'],
-                       sd[f'outputs.bbox_stride{stride}.weight'],
-                       sd[f'outputs.landmark_stride{stride}.weight']], 0)
-        bias = torch.cat([sd[f'outputs.cls_stride{stride}.bias'],
-                          sd[f'outputs.bbox_stride{stride}.bias'],
-                          sd[f'outputs.landmark_stride{stride}.bias']], 0)
-        head = P.buffer(32, f32=True)
-        P.conv(w, np.ones(32, np.float32), bias.float().numpy(), ctx, head, engine=engine)
-        heads[stride] = head
-        ctxs[stride] = ctx
-    roles = {'heads': [heads[32], heads[16], heads[8]], 'context': ctxs}
-    return P, roles
+    P, roles = native_program('retinaface', sd, flags=0 if fused else 1)
+    return P, {'heads': roles[:3]}
 
 
-# --------------------------------------------------------------------- ArcFace
+def arcface_program(sd, units=None):
+    """Program for reference ``FaceResNet100`` (arcface/model.py:38-97), input in model channel
+    order (BGR).  The depth (units per stage) is read from the checkpoint's keys.  Every
+    ``Unit`` starts with a BatchNorm in front of a zero-padded 3x3 conv (model.py:11-14); it is
+    folded into that conv exactly — scale into the filters, shift into nine border-class shift
+    vectors — so the residual stream is the only tensor a unit reads and writes."""
+    P, roles = native_program('arcface', sd)
+    return P, {'embedding': roles[0]}
 
-def arcface_program(sd, units=ARCFACE_UNITS):
-    """Program for reference ``FaceResNet100`` (arcface/model.py:38-97).  Input
-    in model channel order (BGR).
-
-    Every ``Unit`` starts with a BatchNorm in front of a zero-padded 3x3 conv
-    (``body[0]``, ``body[1]``; model.py:11-14).  It is folded into that conv exactly — scale
-    into the filters, shift into nine border-class shift vectors (``pre_bn_fold``) — so the
-    residual stream ``x`` is the only tensor a unit reads and writes: no second, normalised
-    copy of every activation."""
-    P = Program()
-    e = 2e-5
-
-    C0 = ARCFACE_CHANNELS[0]
-    x = P.buffer(C0)
-    s, t = bn_fold(sd, 'initial_layer.1', e)
-    P.stem(sd['initial_layer.0.weight'], s, t, x, stride=1, act=nat.TR_ACT_PRELU,
-           slope=sd['initial_layer.2.weight'].float().numpy(),
-           in_scale=0.0078125, in_shift=-127.5 * 0.0078125)
-
-    n_stages = len(units)
-    for si, n_units in enumerate(units):
-        cout = ARCFACE_CHANNELS[si + 1]
-        y_full = P.buffer(cout)      # conv1 output of the strided first unit (full res)
-        y = P.buffer(cout)
-        sc = P.buffer(cout)
-        xs = [P.buffer(cout), P.buffer(cout)]
-        for u in range(n_units):
-            p = f'stages.{si}.{u}'
-            stride = 2 if u == 0 else 1
-            s0, t0 = bn_fold(sd, p + '.body.0', e)
-            s1, t1 = bn_fold(sd, p + '.body.2', e)
-            w1, shift9 = pre_bn_fold(sd[p + '.body.1.weight'], s0, t0, s1, t1)
-            yb = y_full if u == 0 else y
-            P.conv(w1, s1, shift9[4], x, yb, act=nat.TR_ACT_PRELU,
-                   slope=sd[p + '.body.3.weight'].float().numpy(), shift9=shift9)
-            if u == 0:
-                s, t = bn_fold(sd, p + '.shortcut.1', e)
-                P.conv(sd[p + '.shortcut.0.weight'], s, t, x, sc, stride=2)
-                res = sc
-            else:
-                res = x
-            x_new = xs[u & 1]
-            s, t = bn_fold(sd, p + '.body.5', e)
-            P.conv(sd[p + '.body.4.weight'], s, t, yb, x_new, stride=stride, res=res)
-            x = x_new
-
-    # final_layer: BN2d (no padding follows -> folded into the FC exactly),
-    # Flatten in (C,H,W) order -> permuted to our (H,W,C), Linear, BN1d.
-    Cl = ARCFACE_CHANNELS[len(units)]
-    s0, t0 = (v.astype(np.float64) for v in bn_fold(sd, 'final_layer.0', e))
-    W = sd['final_layer.3.weight'].double().numpy()
-    hw = W.shape[1] // Cl
-    side = int(round(hw ** 0.5))
-    W = W.reshape(512, Cl, side, side)
-    bias = sd['final_layer.3.bias'].double().numpy() + (W * t0[None, :, None, None]).sum((1, 2, 3))
-    Wf = (W * s0[None, :, None, None]).transpose(0, 2, 3, 1).reshape(512, hw * Cl, 1, 1)
-    g = sd['final_layer.4.weight'].double().numpy()
-    b = sd['final_layer.4.bias'].double().numpy()
-    m = sd['final_layer.4.running_mean'].double().numpy()
-    v = sd['final_layer.4.running_var'].double().numpy()
-    scale = g / np.sqrt(v + e)
-    shift = b + (bias - m) * scale
-    flat = P.buffer(hw * Cl)
-    P.view(x, flat)
-    emb = P.buffer(512, f32=True)
-    P.conv(torch.from_numpy(Wf.astype(np.float32)), scale.astype(np.float32),
-           shift.astype(np.float32), flat, emb, k=1, pad=0)
-    return P, {'embedding': emb}
-
-
-# -------------------------------------------------------------------- OpenPose
 
 #: position of reference concat channel c (cat[PAF 38, heat 19, trunk 128]) in
 #: the padded 192-channel buffer [PAF 0..37 | pad | heat 40..58 | pad | trunk 64..191]
@@ -365,72 +231,10 @@ OPENPOSE_CAT_MAP = np.concatenate([np.arange(38), 40 + np.arange(19), 64 + np.ar
 
 
 def openpose_program(sd):
-    """Program for reference ``BodyPoseModel`` (openpose/model.py:27-141).  The
-    frame is read as stored (RGB, no flip: wrapper.py:116-122)."""
-    P = Program()
-    relu = nat.TR_ACT_RELU
-
-    def one(cout):
-        return np.ones(cout, np.float32)
-
-    cat = [P.buffer(192), P.buffer(192)]
-    x = None
-    ch = 3
-    items = list(OPENPOSE_TRUNK)
-    for i, item in enumerate(items):
-        if item == 'P':
-            y = P.buffer(ch)
-            P.maxpool(x, y, ch)
-            x = y
-            continue
-        name, cin, cout, _k = item
-        w, b = sd[f'model0.{name}.weight'], sd[f'model0.{name}.bias'].float().numpy()
-        if cin == 3:
-            y = P.buffer(cout)
-            # reference: x.astype(f32) / 255.0 - 0.5 (wrapper.py:116-122)
-            P.stem(w, one(cout), b, y, stride=1, act=relu, in_scale=1.0 / 255.0, in_shift=-0.5)
-        elif i == len(items) - 1:
-            P.conv(w, one(cout), b, x, cat[0], out_coff=64, act=relu)
-            P.copy(cat[0], 64, cat[1], 64, 128)
-            y = None
-        else:
-            y = P.buffer(cout)
-            P.conv(w, one(cout), b, x, y, act=relu)
-        x, ch = y, cout
-
-    for stage in range(1, 7):
-        src = cat[0] if stage == 1 else cat[stage % 2]
-        dst = cat[0] if stage == 1 else cat[(stage + 1) % 2]
-        specs = {b: openpose_stage_layers(stage, b) for b in (1, 2)}
-        # The first layer of both branches reads the same tensor: one conv with the two
-        # filter banks stacked (N = 256 fills the UMMA tile; one launch instead of two).
-        (n1, cin, c1, k, _), (n2, _, c2, _, _) = specs[1][0], specs[2][0]
-        w = torch.cat([sd[f'model{stage}_1.{n1}.weight'], sd[f'model{stage}_2.{n2}.weight']], 0)
-        b = torch.cat([sd[f'model{stage}_1.{n1}.bias'], sd[f'model{stage}_2.{n2}.bias']], 0)
-        first = P.buffer(c1 + c2)
-        kw = dict(in_coff=64) if stage == 1 else dict(in_map=OPENPOSE_CAT_MAP, cin_pad=192)
-        # The two branches are independent until the next stage: branch 2 runs on the net's
-        # side stream so that each chain's kernels fill the scheduling tail of the other's.
-        P.conv(w, one(c1 + c2), b.float().numpy(), src, first, act=relu,
-               sync=nat.TR_SYNC_FORK | (nat.TR_SYNC_JOIN if stage > 1 else 0), **kw)
-        for branch in (1, 2):
-            layers = specs[branch]
-            x, x_coff = first, (branch - 1) * c1
-            tmp = [P.buffer(128), P.buffer(128)]
-            for li, (name, cin, cout, k, has_relu) in enumerate(layers):
-                if li == 0:
-                    continue
-                pfx = f'model{stage}_{branch}.{name}'
-                w, b = sd[pfx + '.weight'], sd[pfx + '.bias'].float().numpy()
-                act = relu if has_relu else nat.TR_ACT_NONE
-                if li == len(layers) - 1:
-                    P.conv(w, one(cout), b, x, dst, in_coff=x_coff, out_coff=0 if branch == 1 else 40,
-                           act=act, lane=branch - 1)
-                else:
-                    y = P.buffer(cout) if cout != 128 else tmp[li & 1]
-                    P.conv(w, one(cout), b, x, y, in_coff=x_coff, act=act, lane=branch - 1)
-                    x, x_coff = y, 0
-    return P, {'maps': cat[(6 + 1) % 2], 'paf_coff': 0, 'heat_coff': 40}
+    """Program for reference ``BodyPoseModel`` (openpose/model.py:27-141).  The frame is read as
+    stored (RGB, no flip: wrapper.py:116-122)."""
+    P, roles = native_program('openpose', sd)
+    return P, {'maps': roles[0], 'paf_coff': roles[1], 'heat_coff': roles[2]}
 
 
 def program_traffic(program, N, H, W):

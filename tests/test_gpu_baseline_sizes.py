@@ -274,3 +274,54 @@ def test_c4_estimation_with_humans(native, golden):
     # and one flipped peak re-routes the greedy limb matching of its neighbours; the exact
     # statement about the decode is (1), this one bounds the end-to-end drift.
     assert rec_hit >= 0.7 * rec_total and prec_hit >= 0.7 * prec_total
+
+
+def test_c5_detect_recog_pose_pipeline(native, retina):
+    """BASELINE config 5 on one GPU: detect -> align -> embed device-resident (the landmarks
+    never visit the host) + pose, through ``PerceptionPipeline(recognition=...)``.  The features
+    must equal the reference-shaped calls ``extract_features(frames, face_detection(frames))``
+    of this repo, and — for a few faces — the oracle's ArcFace on crops aligned by the host
+    restatement of the reference's ``preprocess_face`` (Umeyama via SVD + PIL warp)."""
+    from terran_b200.face.detection import Detection
+    from terran_b200.face.recognition import Recognition
+    from terran_b200.face.recognition.arcface import ArcFace
+    from terran_b200.face.recognition.arcface.wrapper import preprocess_face
+    from terran_b200.pipeline import FrameFeeder, PerceptionPipeline
+    from terran_b200.pose import Estimation
+    from terran_b200.pose.openpose import OpenPose
+    dev = torch.device('cuda')
+    det = Detection(device=dev, lazy=True)
+    det.model = retina[0]
+    sd_arc = synth.arcface_state_dict()
+    rec = Recognition(device=dev, lazy=True)
+    rec.model = ArcFace(device=dev, state_dict=sd_arc)
+    est = Estimation(device=dev, lazy=True)
+    est.model = OpenPose(device=dev, state_dict=synth.openpose_state_dict(peaks=True))
+    rng = np.random.default_rng(21)
+    batches = [rng.integers(0, 256, (3, 540, 960, 3), dtype=np.uint8) for _ in range(3)]
+    pipe = PerceptionPipeline(det, est, device=dev, recognition=rec)
+    got = list(pipe.run(FrameFeeder(batches, device=dev)))
+    assert len(got) == 3
+    n_faces = 0
+    for frames, (faces, feats, poses) in zip(batches, got):
+        want_faces = det(frames)
+        want_feats = rec(frames, want_faces)
+        assert [len(f) for f in faces] == [len(f) for f in want_faces]
+        assert sum(len(p) for p in poses) > 0
+        for a, b, fs in zip(feats, want_feats, faces):
+            assert a.shape == (len(fs), 512)
+            n_faces += len(fs)
+            if len(fs):
+                # device closed-form similarity vs the host one: coefficients agree to 1e-12, so
+                # at most a few warped pixels differ by one level
+                assert (a * b).sum(1).min() > 0.9999 and np.abs(a - b).max() < 5e-3
+    assert n_faces > 20
+    # oracle: reference-style host alignment (SVD Umeyama + PIL) + fp32 ArcFace
+    frames, (faces, feats, _) = batches[0], got[0]
+    i = next(k for k, f in enumerate(faces) if len(f) >= 2)
+    crops = np.stack([preprocess_face(frames[i], f['landmarks']) for f in faces[i][:2]])
+    ref = nets.arcface_forward(sd_arc, torch.from_numpy(crops.astype(np.float32))).numpy()
+    ref /= np.linalg.norm(ref, axis=1, keepdims=True)
+    cos = (feats[i][:2] * ref).sum(1)
+    print(f'C5: {n_faces} faces embedded; cosine vs oracle {cos}')
+    assert cos.min() > 0.9999

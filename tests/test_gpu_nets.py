@@ -290,5 +290,7 @@ def test_gpu_face_alignment_matches_pil(native, arc):
     assert [o.shape for o in out] == [(3, 512), (1, 512)]
     host = model.embed_device(torch.from_numpy(np.stack(      # np.stack keeps the transposed strides
         [preprocess_face(frames[0], f['landmarks']) for f in faces[0]])).cuda(), 'nchw_bgr')
-    np.testing.assert_allclose(out[0], host.cpu().numpy(), atol=1e-6)
+    # (a batch of 4 and a batch of 3 take different tile shapes / K splits: fp32 summation order)
+    np.testing.assert_allclose(out[0], host.cpu().numpy(), atol=1e-3)
+    assert (out[0] * host.cpu().numpy()).sum(1).min() > 0.99999
     assert [o.shape for o in rec(frames, [[], []])] == [(0, 512), (0, 512)]

@@ -176,7 +176,7 @@ def test_resized_dims_follow_reference():
 # ------------------------------------------------------------- weight packing
 
 def test_bn_fold_is_exact_affine():
-    from terran_b200.weights import bn_fold
+    from tests.reference_programs import bn_fold
     g = torch.Generator().manual_seed(0)
     sd = {'bn.weight': torch.rand(6, generator=g) + 0.5, 'bn.bias': torch.randn(6, generator=g),
           'bn.running_mean': torch.randn(6, generator=g), 'bn.running_var': torch.rand(6, generator=g) + 0.5}

@@ -100,3 +100,68 @@ def test_program_traffic_model_of_the_retinaface_stack():
     _, per = weights.program_traffic(fused, 1, 416, 739)
     heads = [w for (i, _, w) in per if fused.buffers[fused.ops[i].out][1]]
     assert sorted(heads) == [13 * 24 * 32 * 4, 26 * 47 * 32 * 4, 52 * 93 * 32 * 4]
+
+
+# ---- the library's builder (csrc/program.cu) against its Python restatement
+
+def _compare_programs(P, Q):
+    """Same buffers, same ops (every field incl. blob offsets), fp16 filter blocks bit-equal,
+    fp32 vectors equal to float round-off (C++ and numpy sum in different orders)."""
+    assert P.buffers == Q.buffers
+    assert len(P.ops) == len(Q.ops)
+    names = [f[0] for f in type(P.ops[0])._fields_]
+    for i, (a, b) in enumerate(zip(P.ops, Q.ops)):
+        for n in names:
+            va, vb = getattr(a, n), getattr(b, n)
+            if isinstance(va, float):
+                assert abs(va - vb) <= 1e-7 * max(1.0, abs(vb)), (i, n, va, vb)
+            else:
+                assert va == vb, (i, n, va, vb)
+    assert len(P.blob) == len(Q.blob)
+    pa, qa = np.frombuffer(bytes(P.blob), np.uint8), np.frombuffer(bytes(Q.blob), np.uint8)
+    same = pa == qa
+    if same.all():
+        return 1.0
+    # differing bytes may only sit in fp32 regions and differ by round-off
+    n4 = len(pa) // 4 * 4
+    fa, fb = pa[:n4].view(np.float32), qa[:n4].view(np.float32)
+    bad = np.flatnonzero(fa.view(np.uint32) != fb.view(np.uint32))
+    assert np.allclose(fa[bad], fb[bad], rtol=2e-6, atol=1e-7), np.abs(fa[bad] - fb[bad]).max()
+    return float(same.mean())
+
+
+@pytest.mark.parametrize('model', ['retinaface', 'retinaface-unfused', 'arcface', 'openpose'])
+def test_native_program_builder_matches_python_restatement(native, model):
+    from tests import reference_programs as ref
+    if model.startswith('retinaface'):
+        sd = synth.retinaface_state_dict()
+        fused = model == 'retinaface'
+        P, roles = weights.retinaface_program(sd, fused=fused)
+        Q, qroles = ref.retinaface_program(sd, fused=fused)
+        assert roles['heads'] == qroles['heads']
+    elif model == 'arcface':
+        units = (1, 2, 1, 1)
+        sd = synth.arcface_state_dict(units=units)
+        P, roles = weights.arcface_program(sd)
+        Q, qroles = ref.arcface_program(sd, units=units)
+        assert roles['embedding'] == qroles['embedding']
+    else:
+        sd = synth.openpose_state_dict()
+        P, roles = weights.openpose_program(sd)
+        Q, qroles = ref.openpose_program(sd)
+        assert roles == {k: qroles[k] for k in roles}
+    frac = _compare_programs(P, Q)
+    assert frac > 0.999
+
+
+def test_state_dict_blob_errors(native):
+    import ctypes as C
+    from terran_b200 import _native as nat
+    h = C.c_void_p()
+    bad = np.frombuffer(b'NOPE' + b'\0' * 12, np.uint8)
+    assert nat.lib().tr_program_build(b'retinaface', C.c_void_p(bad.ctypes.data), len(bad), 0, C.byref(h)) != 0
+    assert b'magic' in nat.lib().tr_last_error()
+    with pytest.raises(nat.NativeError, match="no tensor 'base.first_conv_block.1.weight'"):
+        weights.native_program('retinaface', {'x': torch.zeros(3)})
+    with pytest.raises(nat.NativeError, match='unknown model'):
+        weights.native_program('resnet', {'x': torch.zeros(3)})
