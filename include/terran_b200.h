@@ -69,7 +69,10 @@ typedef struct tr_op_desc {
   int64_t dw_w_off, dw_scale_off, dw_shift_off;   /* TR_OP_SEPCONV: depthwise filter [3][3][C] fp32 + BN */
   int64_t dw_w16_off;               /* the same filter rounded to fp16 (fused kernel operand) */
   int32_t engine;                   /* TR_OP_CONV: TR_ENGINE_* */
-  int32_t reserved;
+  /* TR_OP_CONV: grouped convolution.  groups = G > 1: the filter rows and the output channels
+   * are G equal blocks; block g reads input channels [in_coff + g * in_c, +in_c) — how the two
+   * OpenPose branches (same shapes, different inputs) run as ONE launch.  0 / 1 = dense. */
+  int32_t groups;
   /* TR_OP_CONV, 3x3 pad 1 stride 1: [9][cout_pad] fp32 border-class shifts replacing the
    * shift vector, class = 3 * (first / inner / last output row) + (first / inner / last
    * column).  How a BatchNorm that PRECEDES a zero-padded conv is folded into it exactly

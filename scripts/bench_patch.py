@@ -33,6 +33,20 @@ def run(tag, N, H, W, cin, cout, k, env, engine=3, repeat=20):
 
 
 MODE = sys.argv[1] if len(sys.argv) > 1 else 'sweep'
+if MODE == 'dual':
+    for dual in (0, 2):
+        run(f'openpose 7x7 128->128 dual={dual}', 32, 23, 40, 128, 128, 7, {'TRB_PT_DUAL': dual})
+        run(f'openpose 7x7 185->256 dual={dual}', 32, 23, 40, 192, 256, 7, {'TRB_PT_DUAL': dual})
+        run(f'vgg 3x3 512->512 @23x40 dual={dual}', 32, 23, 40, 512, 512, 3, {'TRB_PT_DUAL': dual})
+        run(f'vgg 3x3 256->256 @46x81 dual={dual}', 32, 46, 81, 256, 256, 3, {'TRB_PT_DUAL': dual})
+        run(f'vgg 3x3 128->128 @92x163 dual={dual}', 32, 92, 163, 128, 128, 3, {'TRB_PT_DUAL': dual})
+        run(f'openpose 3x3 128->128 @23x40 dual={dual}', 32, 23, 40, 128, 128, 3, {'TRB_PT_DUAL': dual})
+        run(f'openpose 1x1 128->512 @23x40 dual={dual}', 32, 23, 40, 128, 512, 1, {'TRB_PT_DUAL': dual})
+        run(f'openpose 1x1 128->128 @23x40 dual={dual}', 32, 23, 40, 128, 128, 1, {'TRB_PT_DUAL': dual})
+        run(f'arcface 3x3 128 @28 dual={dual}', 256, 28, 28, 128, 128, 3, {'TRB_PT_DUAL': dual})
+        run(f'arcface 3x3 256 @14 dual={dual}', 256, 14, 14, 256, 256, 3, {'TRB_PT_DUAL': dual})
+    run('trace openpose 7x7 128->128 dual=2', 32, 23, 40, 128, 128, 7, {'TRB_PT_DUAL': 2, 'TRB_PT_DEBUG': 32}, repeat=6)
+    sys.exit(0)
 if MODE == 'sk':
     for sk in (0, 2):
         run(f'openpose 7x7 128->128 sk={sk}', 32, 23, 40, 128, 128, 7, {'TRB_PT_SK': sk})

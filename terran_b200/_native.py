@@ -53,7 +53,7 @@ class OpDesc(C.Structure):
         ('in_scale', C.c_float), ('in_shift', C.c_float),
         ('dw_w_off', C.c_int64), ('dw_scale_off', C.c_int64), ('dw_shift_off', C.c_int64),
         ('dw_w16_off', C.c_int64),
-        ('engine', C.c_int32), ('reserved', C.c_int32),
+        ('engine', C.c_int32), ('groups', C.c_int32),
         ('shift9_off', C.c_int64),
     ]
 
@@ -147,3 +147,19 @@ def init(device_index=0):
 def current_stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class nvtx_range:
+    """``with nvtx_range('detect:net'):`` — an NVTX range around a pipeline stage (shows up in
+    nsys / ncu --nvtx timelines next to the per-op ranges the library pushes itself)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        import torch
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        import torch
+        torch.cuda.nvtx.range_pop()

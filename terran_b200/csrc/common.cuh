@@ -74,6 +74,9 @@ struct ConvArgs {
   // optional [9][cout_pad] border-class shifts replacing `shift` (3x3, pad 1, stride 1):
   // class = 3 * (first / inner / last output row) + (first / inner / last output column)
   const float* shift9 = nullptr;
+  // grouped convolution (conv_patch only; the executor splits it for the other kernels): the
+  // cout_pad filter rows are `groups` equal blocks, block g reads channels in.coff + g * cin_pad
+  int groups = 1;
   int cout_pad = 0;   // multiple of 16
   int cout_store = 0; // channels actually written (multiple of 8, <= cout_pad)
   int cin_pad = 0;    // multiple of 16
@@ -98,6 +101,7 @@ int* conv_tc_error_flag();    // device-visible word a trapping kernel writes it
 
 // conv_patch.cu — tcgen05 kernel with filters on M and a resident input patch on N
 bool conv_patch_eligible(const ConvArgs& a);
+size_t conv_patch_scratch_bytes();
 struct ConvPatchPlan;
 ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag);
 void conv_patch_plan_destroy(ConvPatchPlan* p);

@@ -43,8 +43,8 @@ namespace trb {
 
 namespace {
 
-constexpr int kPThreads = 352;
-constexpr int kPEpiWarps = 8;
+constexpr int kPThreads = 352;            // 8 epilogue warps, one CTA per SM
+constexpr int kPThreadsDual = 224;        // 4 epilogue warps, two CTAs per SM
 constexpr int kPMaxStages = 12;
 constexpr uint32_t kFilterBlock = 128 * 64 * 2;      // one (tap, chunk) filter block: 16 KB
 constexpr uint32_t kOutStage = 2 * 4096;             // per team: 16 pixels x 128 couts fp16
@@ -53,7 +53,7 @@ struct PatchParams {
   int N, H, W;                 // output == input dims (stride 1, "same" padding)
   int k, pad, taps;
   int cin_pad, kchunks, in_coff;
-  int cout_tiles;
+  int cout_tiles, tiles_per_group;   // grouped conv: cout tile ct reads channels in_coff + (ct / tiles_per_group) * cin_pad
   int axis;                    // 0: 8-pixel groups along w, R rows along h;  1: groups along h, R along w
   int R, NP, PA;               // NP = 8 R pixels per tile (UMMA N); PA = patch pixels per row (8 | 16)
   int tiles_a, tiles_b, pix_tiles, total_tiles;
@@ -66,7 +66,13 @@ struct PatchParams {
   // computes that tile's remaining iterations FIRST, parks the raw fp32 accumulator in its
   // workspace slot and raises its flag; the CTA that owns the tile's first iteration reaches
   // it LAST in its own range, adds the parked partials in CTA order (deterministic) and runs
-  // the epilogue; the last of the 2 x kPEpiWarps warps that touch a flag re-arms it.
+  // the epilogue; the last of the 2 x epi_warps warps that touch a flag re-arms it.
+  // Two CTAs per SM ("dual"): each with ONE patch buffer, ONE accumulator (<= 256 TMEM columns),
+  // four epilogue warps and half the shared memory.  Everything a CTA does outside its MMA loop —
+  // launch, barrier / TMEM set-up, waiting for the previous layer, the first patch, the chunk
+  // switch, draining the tensor pipe, the epilogue — runs while the other CTA's MMAs keep the
+  // SM's tensor pipe busy.
+  int epi_warps, nbuf, nacc;
   int sk, ipt;                 // ipt: ring iterations per tile = kchunks * iters
   float* sk_ws; int* sk_flags;
   uint32_t idesc, tmem_cols;
@@ -161,7 +167,8 @@ __device__ __forceinline__ bool walk_last(const PatchParams& p, const Walk& w) {
   return p.sk ? w.pos >= w.end : w.tile >= p.total_tiles;
 }
 
-__global__ void __launch_bounds__(kPThreads, 1)
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmO, const PatchParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -197,7 +204,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kPEpiWarps);
+      mbar_init(tempty_bar(a), p.epi_warps);
       mbar_init(pfull_bar(a), 1);
       mbar_init(pempty_bar(a), 1);
     }
@@ -259,7 +266,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 2 + p.epi_warps) {
     // ----------------------------------------------------------- patch producer
     asm volatile("griddepcontrol.wait;" ::: "memory");      // activations of the previous layer
     PT_STAMP(2);                                            // previous grid complete
@@ -270,11 +277,12 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const TileCoord t = tile_coord(p, sg.tile);
       const int kc0 = sg.i0 / p.iters, kc1 = (sg.i1 - 1) / p.iters;   // chunks the segment touches
       for (int kc = kc0; kc <= kc1; ++kc, ++q) {
-        const int buf = q & 1;
-        mbar_wait(pempty_bar(buf), ((q >> 1) & 1u) ^ 1u, p.err, 5);
+        const int buf = q % p.nbuf;
+        mbar_wait(pempty_bar(buf), ((q / p.nbuf) & 1u) ^ 1u, p.err, 5);
         if (elect_one()) {
           mbar_expect_tx(pfull_bar(buf), p.patch_tx);
-          tma_load_4d(base + buf * p.patch_bytes, &tmX, pfull_bar(buf), p.in_coff + kc * 64,
+          tma_load_4d(base + buf * p.patch_bytes, &tmX, pfull_bar(buf),
+                      p.in_coff + (t.ct / p.tiles_per_group) * p.cin_pad + kc * 64,
                       t.a0 - p.pad, t.b0 - p.pad, t.n);
         }
         __syncwarp();
@@ -291,8 +299,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     Walk w = walk_begin(p);
     Seg sg;
     for (; walk_next(p, w, sg); ++tile_it) {
-      const int acc = tile_it & 1;
-      mbar_wait(tempty_bar(acc), ((tile_it >> 1) & 1u) ^ 1u, p.err, 2);
+      const int acc = tile_it % p.nacc;
+      mbar_wait(tempty_bar(acc), ((tile_it / p.nacc) & 1u) ^ 1u, p.err, 2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + acc * p.NP;
       uint32_t accumulate = 0;
@@ -302,8 +310,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       bool need_patch = true;
       for (int i = sg.i0; i < sg.i1; ++i) {
         if (need_patch) {                                   // first iteration of a chunk in this segment
-          buf = q & 1;
-          mbar_wait(pfull_bar(buf), (q >> 1) & 1u, p.err, 6);
+          buf = q % p.nbuf;
+          mbar_wait(pfull_bar(buf), (q / p.nbuf) & 1u, p.err, 6);
           if (q == 0) PT_STAMP(3);                          // first patch landed
           patch_lo = umma_desc_lo(base + buf * p.patch_bytes);
           need_patch = false;
@@ -344,8 +352,9 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     asm volatile("griddepcontrol.wait;" ::: "memory");      // residual reads / buffer re-use
     const int ew = warp - 2;
     const int qd = warp & 3;                 // TMEM lane quarter this warp may access
-    const int team = ew >> 2;                // which half of the pixel groups its four warps take
-    const int g_begin = team * (p.R >> 1), g_end = g_begin + (p.R >> 1);
+    const int team = ew >> 2;                // teams of four warps split the pixel groups
+    const int per_team = p.R / (p.epi_warps >> 2);
+    const int g_begin = team * per_team, g_end = g_begin + per_team;
     const int A_dim = p.axis == 0 ? p.W : p.H, B_dim = p.axis == 0 ? p.H : p.W;
     const int a_step = p.axis == 0 ? 1 : p.W;             // pixel-index step along the group axis
     const int b_step = p.axis == 0 ? p.W : 1;
@@ -355,17 +364,18 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     Walk w = walk_begin(p);
     Seg sg;
     for (; walk_next(p, w, sg); ++tile_it) {
-      const int acc = tile_it & 1;
+      const int acc = tile_it % p.nacc;
       const TileCoord t = tile_coord(p, sg.tile);
       const int cl = qd * 32 + lane;                       // cout within the tile
       const int cout = t.ct * 128 + cl;
-      const float sc = p.scale[cout], sh = p.shift[cout];
+      const bool c_in = cout < p.cout_pad;                 // (a 64-filter layer fills half a tile)
+      const float sc = c_in ? p.scale[cout] : 0.f, sh = c_in ? p.shift[cout] : 0.f;
       // Border-class shifts: the three candidates of a pixel group (its position along the R
       // axis is fixed) are picked once per group, the one of a pixel by its position along the
       // 8-pixel axis.  Without shift9 all nine are the plain shift.
       float s9[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) s9[k] = p.shift9 ? p.shift9[k * p.cout_pad + cout] : sh;
+      for (int k = 0; k < 9; ++k) s9[k] = (p.shift9 && c_in) ? p.shift9[k * p.cout_pad + cout] : sh;
       auto group_shifts = [&](int g, float& first, float& inner, float& last) {
         const int b = t.b0 + g;
         const int bc = b == 0 ? 0 : (b >= B_dim - 1 ? 2 : 1);
@@ -395,8 +405,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         return p.res + static_cast<size_t>(pix) * p.res_cs + p.res_coff + t.ct * 128;
       };
       // one activation formula: y = max(y, 0) + neg * min(y, 0)   (ReLU 0, PReLU slope, none 1)
-      const float neg = p.act == ACT_RELU ? 0.f : (p.act == ACT_PRELU ? p.slope[cout] : 1.f);
-      mbar_wait(tfull_bar(acc), (tile_it >> 1) & 1u, p.err, 4);
+      const float neg = p.act == ACT_RELU ? 0.f : (p.act == ACT_PRELU && c_in ? p.slope[cout] : 1.f);
+      mbar_wait(tfull_bar(acc), (tile_it / p.nacc) & 1u, p.err, 4);
       if (warp == 2) PT_STAMP(5);                           // accumulator complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * p.NP;
@@ -433,7 +443,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (lane == 0) {
           for (int k = 1; k <= n_parts; ++k) {
             const long long t0 = clock64();
-            while (*reinterpret_cast<volatile int*>(p.sk_flags + blockIdx.x + k) < kPEpiWarps) {
+            while (*reinterpret_cast<volatile int*>(p.sk_flags + blockIdx.x + k) < p.epi_warps) {
               if (clock64() - t0 > 4000000000LL) {
                 if (p.err) atomicExch(p.err, 9);
                 __threadfence_system();
@@ -545,7 +555,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 3, 256;" ::: "memory");        // the eight epilogue warps
+        asm volatile("bar.sync 3, %0;" ::"r"(p.epi_warps * 32) : "memory");     // all epilogue warps
         if (warp == 2 && !(p.debug & 4)) {
           const int b = t.b0 + lane;
           if (lane < p.R && b < B_dim) {
@@ -693,7 +703,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_arrive(tempty_bar(acc));
         for (int k = 1; k <= n_parts; ++k) {              // last of the 16 warps re-arms the flag
           int* flag = p.sk_flags + blockIdx.x + k;
-          if (atomicAdd(flag, 1) == 2 * kPEpiWarps - 1) atomicExch(flag, 0);
+          if (atomicAdd(flag, 1) == 2 * p.epi_warps - 1) atomicExch(flag, 0);
         }
       }
       if (warp == 2) PT_STAMP(6);                           // epilogue of a tile done
@@ -731,6 +741,7 @@ int env_int(const char* name, int dflt) {
 }  // namespace
 
 struct ConvPatchPlan {
+  bool dual = false;
   unsigned long long* trace = nullptr;
   void* sk_own = nullptr;
   CUtensorMap tmX, tmW, tmO;
@@ -740,11 +751,22 @@ struct ConvPatchPlan {
   double flops;
 };
 
+// Stream-K scratch: 2 KB of flags, then one 128 x 256 fp32 accumulator slot per co-resident CTA
+// (two per SM in the dual configuration).
+size_t conv_patch_scratch_bytes() {
+  int sms = 0;
+  TR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device()));
+  return 2048 + size_t(2 * sms) * 128 * 256 * 4;
+}
+
 bool conv_patch_eligible(const ConvArgs& a) {
   if (a.stride != 1 || a.kh != a.kw || !(a.kh & 1) || a.pad != a.kh / 2 || a.kh > 9) return false;
-  if (a.cin_pad % 64 || a.cout_pad % 128) return false;
+  // 64 filters run as half of a 128-row tile: the filter map's rows 64..127 are out of bounds
+  // (TMA zero fill, no traffic) and the output map clips the upper 64 channels
+  if (a.cin_pad % 64 || (a.cout_pad % 128 && a.cout_pad != 64)) return false;
   if (a.in.cs % 8 || a.in.coff % 8) return false;
   if (a.out2.ptr || a.res_up2) return false;
+  if (a.groups > 1 && (a.cout_pad % (128 * a.groups) || a.res.ptr || a.shift9)) return false;
   if (a.shift9 && (a.kh != 3 || a.in.H < 2 || a.in.W < 2)) return false;
   if (a.H_out != a.in.H || a.W_out != a.in.W) return false;
   return true;
@@ -758,7 +780,8 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   p.N = a.in.N; p.H = a.H_out; p.W = a.W_out;
   p.k = a.kh; p.pad = a.pad; p.taps = a.kh * a.kw;
   p.cin_pad = a.cin_pad; p.kchunks = a.cin_pad / 64; p.in_coff = a.in.coff;
-  p.cout_tiles = a.cout_pad / 128;
+  p.cout_tiles = ceil_div(a.cout_pad, 128);
+  p.tiles_per_group = std::max(1, p.cout_tiles / std::max(1, a.groups));
   p.PA = a.pad == 0 ? 8 : 16;
 
   int sms = 0;
@@ -793,17 +816,32 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   p.total_tiles = p.pix_tiles * p.cout_tiles;
   p.patch_tx = p.PA * (p.R + halo) * 128;
   p.patch_bytes = round_up(p.patch_tx, 1024);
-  p.ring_off = 2 * p.patch_bytes;
+  const uint32_t misc = kOutStage + 512 + 8 * (2 * kPMaxStages + 10) + 1024 /*alignment*/;
+  // Two CTAs per SM when one patch buffer + a filter ring of >= 2 x 16 KB fit in half of the SM's
+  // shared memory (TRB_PT_DUAL: 0 never, 1 auto, 2 whenever it fits).
+  {
+    const int want = env_int("TRB_PT_DUAL", 1);
+    const uint32_t half = 113u * 1024;
+    const bool fits = p.patch_bytes + 2 * kFilterBlock + misc <= half;
+    const bool worth = p.kchunks * p.taps >= 8;              // enough MMA work to hide the other CTA behind
+    plan->dual = fits && (want == 2 || (want == 1 && worth));
+  }
+  p.nbuf = plan->dual ? 1 : 2;
+  p.nacc = plan->dual ? 1 : 2;
+  p.epi_warps = plan->dual ? 4 : 8;
+  p.ring_off = p.nbuf * p.patch_bytes;
+  const uint32_t budget = plan->dual ? 113u * 1024 : 227u * 1024;
+  const uint32_t fixed = p.ring_off + misc;
   p.sub = std::max(1, std::min(env_int("TRB_PT_SUB", 2), p.taps));
+  while (p.sub > 1 && fixed + 2u * p.sub * kFilterBlock > budget) --p.sub;
   p.iters = ceil_div(p.taps, p.sub);
   p.stage_bytes = p.sub * kFilterBlock;
-  const uint32_t fixed = p.ring_off + kOutStage + 512 + 8 * (2 * kPMaxStages + 10) + 1024 /*alignment*/;
-  p.stages = std::min(kPMaxStages, int((227u * 1024 - fixed) / p.stage_bytes));
+  p.stages = std::min(kPMaxStages, int((budget - fixed) / p.stage_bytes));
   p.stages = std::min(p.stages, std::max(2, env_int("TRB_PT_STAGES", kPMaxStages)));
   TR_CHECK(p.stages >= 2, "filter ring does not fit");
   p.idesc = (1u << 4) | (uint32_t(p.NP >> 3) << 17) | (uint32_t(128 >> 4) << 24);
   uint32_t cols = 32;
-  while (cols < uint32_t(2 * p.NP)) cols <<= 1;
+  while (cols < uint32_t(p.nacc * p.NP)) cols <<= 1;
   p.tmem_cols = cols;
 
   p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.act = a.act;
@@ -847,7 +885,8 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
 
   // TMA-store epilogue: plain fp16 output of whole 128-channel tiles (no residual); the 4-D map
   // {C, W, H, N} clips the ragged border of the 8-pixel groups.
-  p.tma_store = env_int("TRB_PT_TMA_STORE", 1) && !a.out_f32 && a.cout_store % 128 == 0 &&
+  const bool whole = a.cout_store % 128 == 0 || a.out.coff + a.cout_store == a.out.cs;   // the map clips
+  p.tma_store = env_int("TRB_PT_TMA_STORE", 1) && !a.out_f32 && whole &&
                 a.out.cs % 8 == 0 && a.out.coff % 8 == 0 &&
                 (!a.res.ptr || (a.res.cs % 8 == 0 && a.res.coff % 8 == 0));
   plan->tmO = plan->tmW;
@@ -862,34 +901,37 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
     TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(output) failed: " + std::to_string(int(r)));
   }
 
-  plan->grid = std::min(p.total_tiles, sms);
+  const int slots = sms * (plan->dual ? 2 : 1);               // co-resident CTAs
+  plan->grid = std::min(p.total_tiles, slots);
   {
     // Stream-K where whole-tile scheduling leaves SMs idle: a last partial round (160 tiles on
-    // 148 SMs run as long as 296) or fewer tiles than SMs.
+    // 148 SMs run as long as 296) or fewer tiles than CTA slots.
     const int want = env_int("TRB_PT_SK", 1);               // 0 off, 1 auto, 2 whenever possible
     p.ipt = p.kchunks * p.iters;
-    const int rounds = ceil_div(p.total_tiles, sms);
-    const double idle = 1.0 - double(p.total_tiles) / (double(rounds) * sms);
-    const bool ok = p.ipt >= 2 && sms < int(2048 / 4) - 1;
+    const int rounds = ceil_div(p.total_tiles, slots);
+    const double idle = 1.0 - double(p.total_tiles) / (double(rounds) * slots);
+    const bool ok = p.ipt >= 2 && slots < int(2048 / 4) - 1;
     const bool worth = p.ipt >= 4 && idle >= 0.08;
     if (ok && (want == 2 || (want == 1 && worth))) {
       void* scratch = a.sk_scratch;
       if (!scratch) {
-        TR_CUDA(cudaMalloc(&plan->sk_own, conv_tc_sk_scratch_bytes()));
+        TR_CUDA(cudaMalloc(&plan->sk_own, conv_patch_scratch_bytes()));
         TR_CUDA(cudaMemset(plan->sk_own, 0, 2048));
         scratch = plan->sk_own;
       }
       p.sk = 1;
       p.sk_flags = static_cast<int*>(scratch);
       p.sk_ws = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + 2048);
-      plan->grid = int(std::min<long long>(sms, static_cast<long long>(p.total_tiles) * p.ipt));
+      plan->grid = int(std::min<long long>(slots, static_cast<long long>(p.total_tiles) * p.ipt));
     }
   }
   plan->smem = fixed + p.stages * p.stage_bytes;
-  plan->flops = 2.0 * p.N * p.H * p.W * double(a.cout_pad) * p.taps * a.cin_pad;
+  plan->flops = 2.0 * p.N * p.H * p.W * double(a.cout_pad) * p.taps * a.cin_pad;   // (cin_pad is per group)
   static bool attr_set[kMaxDevices] = {};
   if (!attr_set[dev]) {
-    TR_CUDA(cudaFuncSetAttribute(conv_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TR_CUDA(cudaFuncSetAttribute(conv_patch_kernel<kPThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TR_CUDA(cudaFuncSetAttribute(conv_patch_kernel<kPThreadsDual, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    TR_CUDA(cudaFuncSetAttribute(conv_patch_kernel<kPThreadsDual, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set[dev] = true;
   }
   return plan;
@@ -918,14 +960,14 @@ void conv_patch_plan_destroy(ConvPatchPlan* p) {
 }
 
 void conv_patch_plan_describe(const ConvPatchPlan* plan, int* axis, int* R, int* tiles, int* stages) {
-  *axis = plan->p.axis; *R = plan->p.R; *tiles = plan->p.total_tiles; *stages = plan->p.stages;
+  *axis = plan->p.axis; *R = plan->p.R; *tiles = plan->p.total_tiles; *stages = plan->p.stages + (plan->dual ? 100 : 0);
 }
 
 void conv_patch_launch(const ConvPatchPlan* plan, cudaStream_t s) {
   static const bool pdl = env_int("TRB_TC_PDL", 1) != 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(plan->grid);
-  cfg.blockDim = dim3(kPThreads);
+  cfg.blockDim = dim3(plan->dual ? kPThreadsDual : kPThreads);
   cfg.dynamicSmemBytes = plan->smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -933,7 +975,10 @@ void conv_patch_launch(const ConvPatchPlan* plan, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel, plan->tmX, plan->tmW, plan->tmO, plan->p));
+  if (plan->dual)
+    TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel<kPThreadsDual, 2>, plan->tmX, plan->tmW, plan->tmO, plan->p));
+  else
+    TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel<kPThreads, 1>, plan->tmX, plan->tmW, plan->tmO, plan->p));
 }
 
 }  // namespace trb

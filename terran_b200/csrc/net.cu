@@ -12,6 +12,8 @@
 #include <tuple>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/terran_b200.h"
 #include "detect_post.cuh"
 #include "program.h"
@@ -37,6 +39,9 @@ struct PreparedOp {
   ConvArgs conv;
   ConvTcPlan* tc = nullptr;
   ConvPatchPlan* pt = nullptr;   // TR_OP_CONV on the resident-patch tcgen05 kernel
+  // grouped conv on the other kernels: one launch per group
+  std::vector<ConvArgs> gconv;
+  std::vector<ConvTcPlan*> gtc;
   StemArgs stem;
   DwArgs dw;
   SepArgs sep;
@@ -55,6 +60,8 @@ struct Plan {
     for (auto& o : ops) {
       if (o.tc) conv_tc_plan_destroy(o.tc);
       if (o.pt) conv_patch_plan_destroy(o.pt);
+      for (auto* g : o.gtc)
+        if (g) conv_tc_plan_destroy(g);
       if (o.sep_tmp) cudaFree(o.sep_tmp);
       if (o.e0) cudaEventDestroy(o.e0);
       if (o.e1) cudaEventDestroy(o.e1);
@@ -118,6 +125,9 @@ bool patch_wanted(const ConvArgs& a) {
   static const int mode = [] { const char* e = getenv("TRB_PATCH"); return e ? atoi(e) : 1; }();
   if (!mode || !conv_patch_eligible(a)) return false;
   if (mode >= 2) return true;
+  // (64-filter layers run, but half of every 128-row MMA is padding: measured 25-60 % slower
+  // than conv_tc_kernel's pixels-on-M tiling for them)
+  if (a.cout_pad % 128) return false;
   // Measured faster than conv_tc_kernel on every eligible OpenPose layer (1x1, 3x3 and 7x7,
   // 64..512 input channels) once the map is large enough for the 8 x R tiles to fill their
   // MMA columns; small maps (ArcFace 14x14 / 7x7) waste too many of them.
@@ -130,6 +140,17 @@ bool patch_wanted(const ConvArgs& a) {
   };
   const double best = std::max(fill8(W) * fill_r(H), fill8(H) * fill_r(W));
   return best >= 0.85;
+}
+
+// Stream-K scratch of one lane (stream), shared by all its conv plans: sized for either kernel.
+void* lane_scratch(tr_net* net, bool side) {
+  void*& scratch = net->sk_scratch[side];
+  if (!scratch) {
+    const size_t bytes = std::max(conv_tc_sk_scratch_bytes(), conv_patch_scratch_bytes());
+    TR_CUDA(cudaMalloc(&scratch, bytes));
+    TR_CUDA(cudaMemset(scratch, 0, bytes));
+  }
+  return scratch;
 }
 
 View make_view(const Buf& b, int coff, int C) {
@@ -253,20 +274,46 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
         TR_CHECK(d.in_coff + d.in_c <= B[d.in].C && d.out_coff + d.out_c <= B[d.out].C,
                  "channel slice out of range");
         po.flops = 2.0 * B[d.out].N * a.H_out * a.W_out * double(d.cout_real) * d.k * d.k * d.cin_real;
-        po.mma = !net->force_direct && !d.force_direct && d.engine == TR_ENGINE_MMA && mma_enabled() &&
+        const int G = d.groups > 1 ? d.groups : 1;
+        a.groups = G;
+        if (G > 1) {
+          TR_CHECK(d.cout_pad % G == 0 && d.out_c % G == 0 && d.res < 0 && d.out2 < 0 && !B[d.out].f32,
+                   "grouped conv: equal filter / output blocks, plain fp16 epilogue");
+          TR_CHECK(d.in_coff + G * d.in_c <= B[d.in].C, "grouped conv: input slice out of range");
+        }
+        po.mma = G == 1 && !net->force_direct && !d.force_direct && d.engine == TR_ENGINE_MMA && mma_enabled() &&
                  !a.shift9 && conv_mma_eligible(a);
-        const bool use_tc = !po.mma && !net->force_direct && !d.force_direct && conv_tc_eligible(a);
+        bool use_tc = !po.mma && !net->force_direct && !d.force_direct;
+        if (use_tc && G == 1) use_tc = conv_tc_eligible(a);
         if (use_tc && patch_wanted(a)) {
+          a.sk_scratch = lane_scratch(net, d.lane == 1);
           po.pt = conv_patch_plan_create(a, conv_tc_error_flag());
           plan->tc_flops += po.flops;
           plan->tc_launches++;
-        } else if (use_tc) {
-          void*& scratch = net->sk_scratch[d.lane == 1];
-          if (!scratch) {
-            TR_CUDA(cudaMalloc(&scratch, conv_tc_sk_scratch_bytes()));
-            TR_CUDA(cudaMemset(scratch, 0, conv_tc_sk_scratch_bytes()));
+        } else if (G > 1) {
+          // the other kernels take one group at a time: block g of the filters / outputs,
+          // input channels in_coff + g * in_c
+          for (int g = 0; g < G; ++g) {
+            ConvArgs c = a;
+            c.groups = 1;
+            c.in.coff = d.in_coff + g * d.in_c;
+            c.out.coff = d.out_coff + g * (d.out_c / G); c.out.C = d.out_c / G;
+            c.cout_pad = d.cout_pad / G; c.cout_store = d.out_c / G;
+            c.w = a.w + size_t(g) * c.cout_pad * d.k * d.k * d.in_c;
+            c.scale = a.scale + g * c.cout_pad; c.shift = a.shift + g * c.cout_pad;
+            if (a.slope) c.slope = a.slope + g * c.cout_pad;
+            ConvTcPlan* tcp = nullptr;
+            if (use_tc && conv_tc_eligible(c)) {
+              c.sk_scratch = lane_scratch(net, d.lane == 1);
+              tcp = conv_tc_plan_create(c);
+              plan->tc_launches++;
+            }
+            po.gconv.push_back(c);
+            po.gtc.push_back(tcp);
           }
-          a.sk_scratch = scratch;
+          if (use_tc) plan->tc_flops += po.flops;
+        } else if (use_tc) {
+          a.sk_scratch = lane_scratch(net, d.lane == 1);
           po.tc = conv_tc_plan_create(a);
           plan->tc_flops += po.flops;
           plan->tc_launches++;
@@ -327,7 +374,8 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
       case TR_OP_VIEW:
         break;
     }
-    if (d.type != TR_OP_VIEW) plan->launches += (d.type == TR_OP_SEPCONV && !po.mma) ? 2 : 1;
+    if (d.type != TR_OP_VIEW)
+      plan->launches += (d.type == TR_OP_SEPCONV && !po.mma) ? 2 : (po.gconv.empty() ? 1 : int(po.gconv.size()));
     plan->ops.push_back(po);
   }
   Plan* raw = plan.get();
@@ -341,6 +389,13 @@ void run_plan(tr_net* net, Plan* plan, const uint8_t* image, int64_t sn, int64_t
   // Lanes: ops of lane 1 go to the net's side stream.  A FORK op marks the point of the main
   // stream the side stream has to reach first; a JOIN op (and the end of the program) waits
   // for the side stream.  Per-op profiling keeps everything on one stream.
+  // NVTX: one range per net run, one per op (visible in nsys / ncu --nvtx; a no-op otherwise)
+  struct Range {
+    explicit Range(const char* n) { nvtxRangePushA(n); }
+    ~Range() { nvtxRangePop(); }
+  };
+  static const char* kOpNames[] = {"tr:stem", "tr:conv", "tr:dwconv", "tr:maxpool", "tr:copy", "tr:view", "tr:sepconv"};
+  Range run_range("tr_net_run");
   const bool lanes = net->lanes && !profile;
   bool fork_pending = false, side_dirty = false;
   auto ensure_side = [&] {
@@ -373,6 +428,7 @@ void run_plan(tr_net* net, Plan* plan, const uint8_t* image, int64_t sn, int64_t
         side_dirty = true;
       }
     }
+    Range op_range(po.pt ? "tr:conv(patch)" : (po.tc ? "tr:conv(tcgen05)" : kOpNames[po.d.type]));
     if (profile && po.d.type != TR_OP_VIEW) {
       if (!po.e0) { TR_CUDA(cudaEventCreate(&po.e0)); TR_CUDA(cudaEventCreate(&po.e1)); }
       TR_CUDA(cudaEventRecord(po.e0, s));
@@ -386,6 +442,12 @@ void run_plan(tr_net* net, Plan* plan, const uint8_t* image, int64_t sn, int64_t
       }
       case TR_OP_CONV:
         if (po.pt) conv_patch_launch(po.pt, s);
+        else if (!po.gconv.empty()) {
+          for (size_t g = 0; g < po.gconv.size(); ++g) {
+            if (po.gtc[g]) conv_tc_launch(po.gtc[g], s);
+            else conv_direct_launch(po.gconv[g], s);
+          }
+        }
         else if (po.tc) conv_tc_launch(po.tc, s);
         else if (po.mma) conv_mma_launch(po.conv, s);
         else conv_direct_launch(po.conv, s);
@@ -536,7 +598,7 @@ int tr_net_profile(tr_net* net, float* ms, int32_t* is_tc, double* flops, int ca
       TR_CUDA(cudaEventSynchronize(po.e1));
       if (n < cap) {
         TR_CUDA(cudaEventElapsedTime(ms + n, po.e0, po.e1));
-        is_tc[n] = (po.tc || po.pt) ? 1 : 0;
+        is_tc[n] = (po.tc || po.pt || (!po.gtc.empty() && po.gtc[0])) ? 1 : 0;
         flops[n] = po.flops;
       }
       ++n;

@@ -87,6 +87,7 @@ struct ConvOpts {
   int res = -1, res_coff = 0, res_up2 = 0;
   int lane = 0, sync = 0, engine = TR_ENGINE_AUTO;
   const std::vector<Vec>* shift9 = nullptr;     // 9 vectors of cout floats
+  int groups = 0;                                // > 1: w is (cout, cin per group, k, k)
 };
 
 struct Builder {
@@ -143,6 +144,7 @@ struct Builder {
     d.res = o.res; d.res_coff = o.res_coff; d.res_up2 = o.res_up2;
     d.k = k; d.stride = o.stride; d.pad = pad; d.act = o.act; d.cout_pad = cout_pad;
     d.cin_real = cin; d.cout_real = cout; d.lane = o.lane; d.sync = o.sync; d.engine = o.engine;
+    d.groups = o.groups;
     d.w_off = add(packed.data(), packed.size() * 2);
     d.scale_off = add_vec(&scale, cout_pad);
     d.shift_off = add_vec(&shift, cout_pad);
@@ -511,43 +513,49 @@ void build_openpose(const StateDict& sd, Program& P) {
     const int src = stage == 1 ? cat[0] : cat[stage % 2];
     const int dst = stage == 1 ? cat[0] : cat[(stage + 1) % 2];
     const std::vector<StageLayer> specs[2] = {stage_layers(stage, 1), stage_layers(stage, 2)};
-    // first layer of both branches reads the same tensor: one conv with the filter banks stacked
-    const StageLayer &l1 = specs[0][0], &l2 = specs[1][0];
-    const std::string m1 = "model" + std::to_string(stage) + "_1.", m2 = "model" + std::to_string(stage) + "_2.";
-    const Tensor &w1 = sd.at(m1 + l1.name + ".weight"), &w2 = sd.at(m2 + l2.name + ".weight");
-    Vec w(size_t(w1.numel + w2.numel)), bias;
-    memcpy(w.data(), w1.f, size_t(w1.numel) * 4);
-    memcpy(w.data() + w1.numel, w2.f, size_t(w2.numel) * 4);
-    for (const Tensor* tb : {&sd.at(m1 + l1.name + ".bias"), &sd.at(m2 + l2.name + ".bias")})
-      bias.insert(bias.end(), tb->f, tb->f + tb->numel);
-    const int c1 = l1.cout, c2 = l2.cout;
-    const int first = B.buffer(c1 + c2);
-    {
+    const std::string m[2] = {"model" + std::to_string(stage) + "_1.", "model" + std::to_string(stage) + "_2."};
+    // Both branches have the same layer shapes up to their last layer.  Layer 0 reads the same
+    // tensor in both (one conv, filter banks stacked); every further layer but the last is ONE
+    // grouped conv (groups = 2) over a [branch 1 | branch 2] channel pair — half the launches,
+    // and twice the tiles per launch to spread over the SMs.  Only the last layers (38 / 19
+    // filters, written into the concat buffer) run per branch, branch 2 on the side stream.
+    auto stacked = [&](size_t li, Vec& w, Vec& bias) {
+      const StageLayer &l1 = specs[0][li], &l2 = specs[1][li];
+      const Tensor &w1 = sd.at(m[0] + l1.name + ".weight"), &w2 = sd.at(m[1] + l2.name + ".weight");
+      w.resize(size_t(w1.numel + w2.numel));
+      memcpy(w.data(), w1.f, size_t(w1.numel) * 4);
+      memcpy(w.data() + w1.numel, w2.f, size_t(w2.numel) * 4);
+      bias.clear();
+      for (const Tensor* tb : {&sd.at(m[0] + l1.name + ".bias"), &sd.at(m[1] + l2.name + ".bias")})
+        bias.insert(bias.end(), tb->f, tb->f + tb->numel);
+    };
+    Vec w, bias;
+    const size_t n_layers = specs[0].size();
+    int xb = -1, ch = 0;                      // current [branch 1 | branch 2] buffer, channels per branch
+    const int tmp[2] = {B.buffer(256), B.buffer(256)};
+    for (size_t li = 0; li + 1 < n_layers; ++li) {
+      const StageLayer& l = specs[0][li];
+      stacked(li, w, bias);
       ConvOpts o; o.act = TR_ACT_RELU;
-      o.sync = TR_SYNC_FORK | (stage > 1 ? TR_SYNC_JOIN : 0);
-      if (stage == 1) o.in_coff = 64;
-      else { o.in_map = &cat_map; o.cin_pad = 192; }
-      B.conv(w.data(), c1 + c2, l1.cin, l1.k, ones(c1 + c2), bias, src, first, o);
+      if (li == 0) {
+        if (stage > 1) o.sync = TR_SYNC_JOIN;
+        if (stage == 1) o.in_coff = 64;
+        else { o.in_map = &cat_map; o.cin_pad = 192; }
+      } else {
+        o.groups = 2;
+      }
+      if (li + 2 == n_layers) o.sync |= TR_SYNC_FORK;
+      const int y = 2 * l.cout != 256 ? B.buffer(2 * l.cout) : tmp[li & 1];
+      B.conv(w.data(), 2 * l.cout, l.cin, l.k, ones(2 * l.cout), bias, li == 0 ? src : xb, y, o);
+      xb = y; ch = l.cout;
     }
     for (int branch = 1; branch <= 2; ++branch) {
-      const auto& layers = specs[branch - 1];
-      int xb = first, x_coff = (branch - 1) * c1;
-      const int tmp[2] = {B.buffer(128), B.buffer(128)};
-      for (size_t li = 1; li < layers.size(); ++li) {
-        const StageLayer& l = layers[li];
-        const std::string pfx = "model" + std::to_string(stage) + "_" + std::to_string(branch) + "." + l.name;
-        const Tensor& wl = sd.at(pfx + ".weight");
-        const Vec bl = to_vec(sd.at(pfx + ".bias"));
-        ConvOpts o; o.in_coff = x_coff; o.act = l.relu ? TR_ACT_RELU : TR_ACT_NONE; o.lane = branch - 1;
-        if (li == layers.size() - 1) {
-          o.out_coff = branch == 1 ? 0 : 40;
-          B.conv(wl.f, l.cout, l.cin, l.k, ones(l.cout), bl, xb, dst, o);
-        } else {
-          const int y = l.cout != 128 ? B.buffer(l.cout) : tmp[li & 1];
-          B.conv(wl.f, l.cout, l.cin, l.k, ones(l.cout), bl, xb, y, o);
-          xb = y; x_coff = 0;
-        }
-      }
+      const StageLayer& l = specs[branch - 1][n_layers - 1];
+      const Tensor& wl = sd.at(m[branch - 1] + l.name + ".weight");
+      const Vec bl = to_vec(sd.at(m[branch - 1] + l.name + ".bias"));
+      ConvOpts o; o.in_coff = (branch - 1) * ch; o.act = l.relu ? TR_ACT_RELU : TR_ACT_NONE;
+      o.lane = branch - 1; o.out_coff = branch == 1 ? 0 : 40;
+      B.conv(wl.f, l.cout, l.cin, l.k, ones(l.cout), bl, xb, dst, o);
     }
   }
   P.roles[0] = cat[(6 + 1) % 2]; P.roles[1] = 0; P.roles[2] = 40;

@@ -92,16 +92,18 @@ class RetinaFace:
         stream without any host synchronisation; returns a ``PendingDetections``."""
         N, H, W, _ = frames.shape
         dev = frames.device
-        self.forward(frames)
+        with nat.nvtx_range('detect:net'):
+            self.forward(frames)
         ws = self._workspace(N, H, W)
         count = torch.empty(N, dtype=torch.int32, device=dev)
         cand = torch.empty(N, dtype=torch.int32, device=dev)
         det = torch.empty((N, max_det, 16), dtype=torch.float32, device=dev)
         heads = (C.c_int * 3)(*self.roles['heads'])
-        nat.check(nat.lib().tr_retinaface_detect(
-            self.net.handle, heads, float(threshold), float(self.nms_threshold), max_det,
-            C.c_void_p(ws.data_ptr()), C.c_void_p(count.data_ptr()), C.c_void_p(cand.data_ptr()),
-            C.c_void_p(det.data_ptr()), nat.current_stream_ptr()))
+        with nat.nvtx_range('detect:decode+nms'):
+            nat.check(nat.lib().tr_retinaface_detect(
+                self.net.handle, heads, float(threshold), float(self.nms_threshold), max_det,
+                C.c_void_p(ws.data_ptr()), C.c_void_p(count.data_ptr()), C.c_void_p(cand.data_ptr()),
+                C.c_void_p(det.data_ptr()), nat.current_stream_ptr()))
         slot = self._host_slot(N, max_det)
         slot['count'].copy_(count, non_blocking=True)
         slot['det'].copy_(det, non_blocking=True)
@@ -176,7 +178,8 @@ def unpack_detections(counts, rows, scale=None):
     scores = np.ascontiguousarray(rows[..., 0])
     coords = rows[..., 1:15]
     if scale is not None:
-        coords = np.around(coords / scale).astype(np.int32)
+        with np.errstate(invalid='ignore', over='ignore'):       # rows past `count` are uninitialised
+            coords = np.around(coords / scale).astype(np.int32)
     else:
         coords = np.ascontiguousarray(coords)
     boxes = coords[..., :4]

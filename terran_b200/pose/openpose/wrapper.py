@@ -78,6 +78,7 @@ class OpenPose:
             self.net = Net(program, self.device_index)
         self._ws = None
         self._host = {}
+        self._parse_stream = None
 
     # -- device stages --------------------------------------------------------
     def maps(self, resized):
@@ -90,16 +91,38 @@ class OpenPose:
                 self.net.export_nchw(r['maps'], r['heat_coff'], 19))
 
     def estimate_device(self, frames):
-        resized, scale = resize_short_side(frames, self.short_side)
-        paf, heat = self.maps(resized)
-        count, kps, score, status, self._ws = parse_device(paf, heat, scale, self._ws)
+        with nat.nvtx_range('pose:resize'):
+            resized, scale = resize_short_side(frames, self.short_side)
+        with nat.nvtx_range('pose:net'):
+            paf, heat = self.maps(resized)
+        with nat.nvtx_range('pose:parse'):
+            count, kps, score, status, self._ws = parse_device(paf, heat, scale, self._ws)
         return count, kps, score, status
 
     def estimate_async(self, frames):
-        """Enqueue resize + forward + parse + the D2H of the results on the current
-        stream without host synchronisation; returns a ``PendingPoses``."""
-        count, kps, score, status = self.estimate_device(frames)
+        """Enqueue resize + forward on the current stream and parse + the D2H of the results
+        on the model's own side stream, without host synchronisation; returns a ``PendingPoses``.
+        The parse kernels (peaks, limbs, greedy matching, assembly) are latency-bound and occupy
+        few SMs: on their own stream they overlap the convolutions of whatever the caller
+        enqueues next (the next batch) instead of idling the GPU behind the conv stack."""
+        with nat.nvtx_range('pose:resize'):
+            resized, scale = resize_short_side(frames, self.short_side)
+        with nat.nvtx_range('pose:net'):
+            paf, heat = self.maps(resized)
+        cur = torch.cuda.current_stream()
+        if self._parse_stream is None:
+            self._parse_stream = torch.cuda.Stream(device=self.device_index)
+        ready = torch.cuda.Event()
+        ready.record(cur)
         N = frames.shape[0]
+        with torch.cuda.stream(self._parse_stream), nat.nvtx_range('pose:parse'):
+            self._parse_stream.wait_event(ready)
+            paf.record_stream(self._parse_stream)
+            heat.record_stream(self._parse_stream)
+            count, kps, score, status, self._ws = parse_device(paf, heat, scale, self._ws)
+            return self._download(N, count, kps, score, status)
+
+    def _download(self, N, count, kps, score, status):
         ring = self._host.setdefault(N, {'i': 0, 'slots': []})
         if len(ring['slots']) < 3:
             ring['slots'].append({

@@ -64,7 +64,7 @@ class Program:
                  out2_coff=0, res=-1, res_coff=0, res_up2=0, k=1, stride=1, pad=0, act=0,
                  cout_pad=0, cin_real=0, cout_real=0, force_direct=0, lane=0, sync=0, w_off=-1, scale_off=-1, shift_off=-1, slope_off=-1,
                  scale2_off=-1, shift2_off=-1, in_scale=1.0, in_shift=0.0,
-                 dw_w_off=-1, dw_scale_off=-1, dw_shift_off=-1, dw_w16_off=-1, engine=0, reserved=0,
+                 dw_w_off=-1, dw_scale_off=-1, dw_shift_off=-1, dw_w16_off=-1, engine=0, groups=0,
                  shift9_off=-1)
         d.update(kw)
         self.ops.append(nat.OpDesc(**d))
@@ -72,7 +72,7 @@ class Program:
     def conv(self, w, scale, shift, in_, out, *, in_coff=0, in_map=None, cin_pad=None,
              out_coff=0, k=None, stride=1, pad=None, act=nat.TR_ACT_NONE, slope=None,
              res=-1, res_coff=0, res_up2=0, out2=-1, scale2=None, shift2=None,
-             force_direct=0, lane=0, sync=0, engine=nat.TR_ENGINE_AUTO, shift9=None):
+             force_direct=0, lane=0, sync=0, engine=nat.TR_ENGINE_AUTO, shift9=None, groups=0):
         """w: (cout, cin, k, k) fp32 tensor.  ``in_map[c]`` is the position of
         reference input channel c inside the (padded) input view.  ``shift9``: (9, cout)
         border-class shifts replacing ``shift`` (see ``pre_bn_fold``)."""
@@ -90,7 +90,7 @@ class Program:
                  out_coff=out_coff, out_c=_r(cout, 8), out2=out2, res=res, res_coff=res_coff,
                  res_up2=res_up2, k=k, stride=stride, pad=pad, act=act, cout_pad=cout_pad,
                  cin_real=cin, cout_real=cout, force_direct=force_direct, lane=lane, sync=sync,
-                 engine=engine, w_off=self.add(packed, np.float16),
+                 engine=engine, groups=groups, w_off=self.add(packed, np.float16),
                  scale_off=self.add_vec(scale, cout_pad), shift_off=self.add_vec(shift, cout_pad),
                  slope_off=self.add_vec(slope, cout_pad),
                  scale2_off=self.add_vec(scale2, cout_pad), shift2_off=self.add_vec(shift2, cout_pad),

@@ -14,7 +14,7 @@ def conv2d_native(nat, x, w, scale, shift, *, stride=1, pad=None, act=0, slope=N
     cout, _, k, _ = w.shape
     pad = k // 2 if pad is None else pad
     cin_pad = cin_pad or cin
-    cout_pad = (cout + 127) // 128 * 128 if int(use_tc) == 3 else (cout + 15) // 16 * 16
+    cout_pad = ((cout + 127) // 128 * 128 if cout != 64 else 64) if int(use_tc) == 3 else (cout + 15) // 16 * 16
     cout_store = (cout + 7) // 8 * 8
     assert x.shape[3] == cin_pad
     wp = torch.zeros((cout_pad, k, k, cin_pad), dtype=torch.float16)

@@ -69,10 +69,11 @@ class Interpreter:
                     y2 = y * self.vec(d.scale2_off, co).view(1, -1, 1, 1) + self.vec(d.shift2_off, co).view(1, -1, 1, 1)
                     self._store(bufs, d.out2, d.out2_coff, y2, N, H, W)
             elif t == nat.TR_OP_CONV:
-                x = bufs[d.in_][..., d.in_coff:d.in_coff + d.in_c].permute(0, 3, 1, 2)
+                G = d.groups if d.groups > 1 else 1       # block g reads channels in_coff + g * in_c
+                x = bufs[d.in_][..., d.in_coff:d.in_coff + G * d.in_c].permute(0, 3, 1, 2)
                 cp, k = d.cout_pad, d.k
                 w = self.arr(d.w_off, np.float16, cp * k * k * d.in_c).float().view(cp, k, k, d.in_c).permute(0, 3, 1, 2)
-                y = F.conv2d(x, w, stride=d.stride, padding=d.pad)
+                y = F.conv2d(x, w, stride=d.stride, padding=d.pad, groups=G)
                 y = y * self.vec(d.scale_off, cp).view(1, -1, 1, 1)
                 if getattr(d, 'shift9_off', -1) >= 0:
                     # border-class shifts: class = 3 * row class + column class (first/inner/last)

@@ -261,34 +261,33 @@ def openpose_program(sd):
         src = cat[0] if stage == 1 else cat[stage % 2]
         dst = cat[0] if stage == 1 else cat[(stage + 1) % 2]
         specs = {b: openpose_stage_layers(stage, b) for b in (1, 2)}
-        # The first layer of both branches reads the same tensor: one conv with the two
-        # filter banks stacked (N = 256 fills the UMMA tile; one launch instead of two).
-        (n1, cin, c1, k, _), (n2, _, c2, _, _) = specs[1][0], specs[2][0]
-        w = torch.cat([sd[f'model{stage}_1.{n1}.weight'], sd[f'model{stage}_2.{n2}.weight']], 0)
-        b = torch.cat([sd[f'model{stage}_1.{n1}.bias'], sd[f'model{stage}_2.{n2}.bias']], 0)
-        first = P.buffer(c1 + c2)
-        kw = dict(in_coff=64) if stage == 1 else dict(in_map=OPENPOSE_CAT_MAP, cin_pad=192)
-        # The two branches are independent until the next stage: branch 2 runs on the net's
-        # side stream so that each chain's kernels fill the scheduling tail of the other's.
-        P.conv(w, one(c1 + c2), b.float().numpy(), src, first, act=relu,
-               sync=nat.TR_SYNC_FORK | (nat.TR_SYNC_JOIN if stage > 1 else 0), **kw)
+        n_layers = len(specs[1])
+        tmp = [P.buffer(256), P.buffer(256)]
+        xb, ch = None, 0
+        # layer 0: one conv with both filter banks stacked (same input); layers 1..n-2: ONE grouped
+        # conv (groups = 2) over the [branch 1 | branch 2] channel pair; last layer: per branch
+        for li in range(n_layers - 1):
+            (n1, cin, c1, k, _), (n2, _, c2, _, _) = specs[1][li], specs[2][li]
+            w = torch.cat([sd[f'model{stage}_1.{n1}.weight'], sd[f'model{stage}_2.{n2}.weight']], 0)
+            b = torch.cat([sd[f'model{stage}_1.{n1}.bias'], sd[f'model{stage}_2.{n2}.bias']], 0)
+            kw = {}
+            sync = 0
+            if li == 0:
+                sync = nat.TR_SYNC_JOIN if stage > 1 else 0
+                kw = dict(in_coff=64) if stage == 1 else dict(in_map=OPENPOSE_CAT_MAP, cin_pad=192)
+            else:
+                kw = dict(groups=2)
+            if li + 2 == n_layers:
+                sync |= nat.TR_SYNC_FORK
+            y = P.buffer(c1 + c2) if c1 + c2 != 256 else tmp[li & 1]
+            P.conv(w, one(c1 + c2), b.float().numpy(), src if li == 0 else xb, y, act=relu, sync=sync, **kw)
+            xb, ch = y, c1
         for branch in (1, 2):
-            layers = specs[branch]
-            x, x_coff = first, (branch - 1) * c1
-            tmp = [P.buffer(128), P.buffer(128)]
-            for li, (name, cin, cout, k, has_relu) in enumerate(layers):
-                if li == 0:
-                    continue
-                pfx = f'model{stage}_{branch}.{name}'
-                w, b = sd[pfx + '.weight'], sd[pfx + '.bias'].float().numpy()
-                act = relu if has_relu else nat.TR_ACT_NONE
-                if li == len(layers) - 1:
-                    P.conv(w, one(cout), b, x, dst, in_coff=x_coff, out_coff=0 if branch == 1 else 40,
-                           act=act, lane=branch - 1)
-                else:
-                    y = P.buffer(cout) if cout != 128 else tmp[li & 1]
-                    P.conv(w, one(cout), b, x, y, in_coff=x_coff, act=act, lane=branch - 1)
-                    x, x_coff = y, 0
+            name, cin, cout, k, has_relu = specs[branch][-1]
+            pfx = f'model{stage}_{branch}.{name}'
+            w, b = sd[pfx + '.weight'], sd[pfx + '.bias'].float().numpy()
+            P.conv(w, one(cout), b, xb, dst, in_coff=(branch - 1) * ch, out_coff=0 if branch == 1 else 40,
+                   act=relu if has_relu else nat.TR_ACT_NONE, lane=branch - 1)
     return P, {'maps': cat[(6 + 1) % 2], 'paf_coff': 0, 'heat_coff': 40}
 
 

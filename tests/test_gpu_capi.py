@@ -77,7 +77,9 @@ def test_openpose_single_call(native):
     from terran_b200.pose.openpose import OpenPose
     from terran_b200.pose.openpose.wrapper import parse_device
     sd = synth.openpose_state_dict(peaks=True)
-    frames = torch.from_numpy(np.random.default_rng(5).integers(0, 256, (2, 184, 327, 3), dtype=np.uint8)).cuda()
+    from terran_b200.frames import resize_short_side
+    big = torch.from_numpy(np.random.default_rng(5).integers(0, 256, (2, 720, 1280, 3), dtype=np.uint8)).cuda()
+    frames, _ = resize_short_side(big, 184)
     model = OpenPose(device=torch.device('cuda'), state_dict=sd)
     paf, heat = model.maps(frames)
     scale = 184 / 720

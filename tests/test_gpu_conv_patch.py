@@ -50,9 +50,12 @@ def run_case(nat, N, H, W, cin, cout, k, *, act=1, res=False, out_f32=False, see
     (3, 13, 17, 64, 128, 3),        # one chunk, tiny map
     (5, 7, 7, 128, 128, 3),         # ArcFace 7x7 maps
     (2, 9, 30, 64, 128, 5),         # 5x5
+    (2, 23, 40, 64, 64, 3),         # 64 filters: half of a 128-row tile (TMA zero-fills / clips)
+    (1, 30, 50, 128, 64, 3),
 ])
-def test_patch_conv_matches_reference(native, shape):
-    run_case(native, *shape)
+@pytest.mark.parametrize('dual', [0, 2], ids=['one-cta-per-sm', 'two-ctas-per-sm'])
+def test_patch_conv_matches_reference(native, shape, dual):
+    run_case(native, *shape, env={'TRB_PT_DUAL': dual})
 
 
 @pytest.mark.parametrize('axis', [0, 1])
@@ -73,6 +76,7 @@ def test_patch_conv_epilogues(native):
     run_case(native, 2, 14, 14, 128, 256, 3, act=2, res=True)
     run_case(native, 2, 23, 40, 128, 128, 1, act=0, out_f32=True)     # fp32 output
     run_case(native, 2, 23, 40, 128, 40, 1, act=0)                    # cout 40 of a 128 tile... padded filters
+    run_case(native, 2, 28, 28, 64, 64, 3, act=2, res=True)           # 64 filters + residual
 
 
 def test_patch_conv_many_tiles_per_cta(native):
@@ -88,15 +92,18 @@ def test_patch_conv_many_tiles_per_cta(native):
     (40, 23, 40, 128, 128, 3),      # 200 tiles, short K
     (3, 9, 10, 64, 128, 1),         # one ring iteration per tile: nothing to split
 ])
-def test_patch_conv_stream_k(native, shape):
+@pytest.mark.parametrize('dual', [0, 2], ids=['one-cta-per-sm', 'two-ctas-per-sm'])
+def test_patch_conv_stream_k(native, shape, dual):
     """Stream-K (TRB_PT_SK=2: whenever possible) against the reference, launched several times in
     a row (the hand-over flags re-arm themselves) and bit-identical to a second run."""
-    a = run_case(native, *shape, env={'TRB_PT_SK': 2}, repeat=3)
-    b = run_case(native, *shape, env={'TRB_PT_SK': 2}, repeat=1)
+    a = run_case(native, *shape, env={'TRB_PT_SK': 2, 'TRB_PT_DUAL': dual}, repeat=3)
+    b = run_case(native, *shape, env={'TRB_PT_SK': 2, 'TRB_PT_DUAL': dual}, repeat=1)
     assert torch.equal(a, b)
 
 
-def test_patch_conv_stream_k_epilogues(native):
-    run_case(native, 20, 14, 14, 128, 128, 3, act=2, res=True, env={'TRB_PT_SK': 2}, repeat=2)
-    run_case(native, 3, 23, 40, 128, 128, 3, act=0, out_f32=True, env={'TRB_PT_SK': 2}, repeat=2)
+@pytest.mark.parametrize('dual', [0, 2], ids=['one-cta-per-sm', 'two-ctas-per-sm'])
+def test_patch_conv_stream_k_epilogues(native, dual):
+    run_case(native, 20, 14, 14, 128, 128, 3, act=2, res=True, env={'TRB_PT_SK': 2, 'TRB_PT_DUAL': dual}, repeat=2)
+    run_case(native, 3, 23, 40, 128, 128, 3, act=0, out_f32=True, env={'TRB_PT_SK': 2, 'TRB_PT_DUAL': dual}, repeat=2)
+    run_case(native, 40, 28, 28, 128, 128, 3, act=2, res=True, env={'TRB_PT_DUAL': dual})       # many tiles per CTA
     run_case(native, 32, 23, 40, 128, 128, 7, env={'TRB_PT_SK': 2, 'TRB_PT_SUB': 1, 'TRB_PT_STAGES': 3})
