@@ -1,0 +1,7 @@
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_nets.py tests/test_gpu_baseline_sizes.py -m gpu -q -x 2>&1 | grep -E "^E  |passed|failed" | head -12 | cut -c1-300
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r2s_bench.json 2> gpurun_out/r2s_bench.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2s_bench.json').read().strip().splitlines()[-1])
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'frac',d['roofline']['frac'],d['roofline']['in_step'])
+for k,v in d['per_config'].items(): print(k, json.dumps(v)[:1200])
+PY

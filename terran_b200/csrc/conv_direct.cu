@@ -536,15 +536,20 @@ __global__ void __launch_bounds__(128) l2_normalize_kernel(const float* in, floa
 // cv2.resize(INTER_LINEAR) on uint8, bit-exact integer restatement
 // (SURVEY.md Appendix A.5): 11-bit fixed-point taps, the intermediate row sum
 // is >>4, the vertical blend is ((b0*r0)>>16) + ((b1*r1)>>16) + 2 >> 2.
+// One thread = kResizePx consecutive output pixels of a row: all their source bytes are
+// requested before the first blend, so a warp has 4 x 12 independent loads in flight instead of
+// a dependent chain per pixel (the kernel is latency-, not bandwidth-bound).
+constexpr int kResizePx = 4;
 __global__ void __launch_bounds__(256)
-resize_u8_kernel(const uint8_t* src, int N, int H, int W, uint8_t* dst, int h, int w,
+resize_u8_kernel(const uint8_t* __restrict__ src, int N, int H, int W, uint8_t* __restrict__ dst, int h, int w,
                  double sy_d, double sx_d) {
-  const long total = static_cast<long>(N) * h * w;
+  const int wq = (w + kResizePx - 1) / kResizePx;             // pixel quads per output row
+  const long total = static_cast<long>(N) * h * wq;
   const long idx = blockIdx.x * 256L + threadIdx.x;
   if (idx >= total) return;
-  const int ox = idx % w;
-  const int oy = (idx / w) % h;
-  const int n = idx / (static_cast<long>(w) * h);
+  const int oxq = idx % wq;
+  const int oy = (idx / wq) % h;
+  const int n = idx / (static_cast<long>(wq) * h);
   // OpenCV clamps index AND fraction along x, but along y only clips the row
   // index when fetching rows (the weights keep the unclamped fraction).
   auto tap = [](int o, double scale, int n_src, bool clamp_weights, int& i0, int& i1, int& a0,
@@ -561,18 +566,36 @@ resize_u8_kernel(const uint8_t* src, int N, int H, int W, uint8_t* dst, int h, i
     a1 = static_cast<int>(rintf(f * 2048.f));
     a0 = static_cast<int>(rintf((1.f - f) * 2048.f));
   };
-  int x0, x1, ax0, ax1, y0, y1, ay0, ay1;
-  tap(ox, sx_d, W, true, x0, x1, ax0, ax1);
+  int y0, y1, ay0, ay1;
   tap(oy, sy_d, H, false, y0, y1, ay0, ay1);
   const uint8_t* r0 = src + (static_cast<long>(n) * H + y0) * W * 3;
   const uint8_t* r1 = src + (static_cast<long>(n) * H + y1) * W * 3;
-  uint8_t* o = dst + idx * 3;
+  int x0[kResizePx], x1[kResizePx], ax0[kResizePx], ax1[kResizePx];
+  uint8_t t00[kResizePx][3], t01[kResizePx][3], t10[kResizePx][3], t11[kResizePx][3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int top = r0[x0 * 3 + c] * ax0 + r0[x1 * 3 + c] * ax1;
-    const int bot = r1[x0 * 3 + c] * ax0 + r1[x1 * 3 + c] * ax1;
-    const int v = (((ay0 * (top >> 4)) >> 16) + ((ay1 * (bot >> 4)) >> 16) + 2) >> 2;
-    o[c] = static_cast<uint8_t>(min(max(v, 0), 255));
+  for (int j = 0; j < kResizePx; ++j) {
+    const int ox = min(oxq * kResizePx + j, w - 1);            // (the tail quad repeats its last pixel)
+    tap(ox, sx_d, W, true, x0[j], x1[j], ax0[j], ax1[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kResizePx; ++j) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      t00[j][c] = __ldg(r0 + x0[j] * 3 + c); t01[j][c] = __ldg(r0 + x1[j] * 3 + c);
+      t10[j][c] = __ldg(r1 + x0[j] * 3 + c); t11[j][c] = __ldg(r1 + x1[j] * 3 + c);
+    }
+  }
+  uint8_t* o = dst + ((static_cast<long>(n) * h + oy) * w + static_cast<long>(oxq) * kResizePx) * 3;
+#pragma unroll
+  for (int j = 0; j < kResizePx; ++j) {
+    if (oxq * kResizePx + j >= w) break;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int top = t00[j][c] * ax0[j] + t01[j][c] * ax1[j];
+      const int bot = t10[j][c] * ax0[j] + t11[j][c] * ax1[j];
+      const int v = (((ay0 * (top >> 4)) >> 16) + ((ay1 * (bot >> 4)) >> 16) + 2) >> 2;
+      o[j * 3 + c] = static_cast<uint8_t>(min(max(v, 0), 255));
+    }
   }
 }
 
@@ -678,7 +701,7 @@ void l2_normalize_launch(const float* in, float* out, int N, int D, cudaStream_t
 
 void resize_bilinear_u8_launch(const uint8_t* src, int N, int H, int W, uint8_t* dst, int h,
                                int w, cudaStream_t s) {
-  const long total = static_cast<long>(N) * h * w;
+  const long total = static_cast<long>(N) * h * ((w + kResizePx - 1) / kResizePx);
   resize_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
       src, N, H, W, dst, h, w, 1.0 / (double(h) / H), 1.0 / (double(w) / W));  // OpenCV: 1/inv_scale
   TR_CUDA(cudaGetLastError());

@@ -458,18 +458,31 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const float* part0 = p.sk_ws + static_cast<size_t>(blockIdx.x + 1) * 128 * p.NP;
       // v[0..7] += the parked partials of group g, in CTA order
       auto add_parts = [&](uint32_t* v, int g) {
-        for (int k = 0; k < n_parts; ++k) {
-          const float4* src = reinterpret_cast<const float4*>(part0 + static_cast<size_t>(k) * 128 * p.NP) +
-                              (g * 128 + cl) * 2;
-          const float4 f0 = __ldcg(src), f1 = __ldcg(src + 1);
-          v[0] = __float_as_uint(__uint_as_float(v[0]) + f0.x);
-          v[1] = __float_as_uint(__uint_as_float(v[1]) + f0.y);
-          v[2] = __float_as_uint(__uint_as_float(v[2]) + f0.z);
-          v[3] = __float_as_uint(__uint_as_float(v[3]) + f0.w);
-          v[4] = __float_as_uint(__uint_as_float(v[4]) + f1.x);
-          v[5] = __float_as_uint(__uint_as_float(v[5]) + f1.y);
-          v[6] = __float_as_uint(__uint_as_float(v[6]) + f1.z);
-          v[7] = __float_as_uint(__uint_as_float(v[7]) + f1.w);
+        // four partials in flight at a time (a long split-K tail would otherwise pay one L2
+        // round trip per partial), added in CTA order
+        for (int k0 = 0; k0 < n_parts; k0 += 4) {
+          float4 f[4][2];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (k0 + j < n_parts) {
+              const float4* src = reinterpret_cast<const float4*>(part0 + static_cast<size_t>(k0 + j) * 128 * p.NP) +
+                                  (g * 128 + cl) * 2;
+              f[j][0] = __ldcg(src); f[j][1] = __ldcg(src + 1);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (k0 + j < n_parts) {
+              v[0] = __float_as_uint(__uint_as_float(v[0]) + f[j][0].x);
+              v[1] = __float_as_uint(__uint_as_float(v[1]) + f[j][0].y);
+              v[2] = __float_as_uint(__uint_as_float(v[2]) + f[j][0].z);
+              v[3] = __float_as_uint(__uint_as_float(v[3]) + f[j][0].w);
+              v[4] = __float_as_uint(__uint_as_float(v[4]) + f[j][1].x);
+              v[5] = __float_as_uint(__uint_as_float(v[5]) + f[j][1].y);
+              v[6] = __float_as_uint(__uint_as_float(v[6]) + f[j][1].z);
+              v[7] = __float_as_uint(__uint_as_float(v[7]) + f[j][1].w);
+            }
+          }
         }
       };
       if (p.tma_store && walk_last(p, w)) {
@@ -791,7 +804,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   // Tile geometry: 8-pixel groups along one axis, R (even, <= 32) rows of groups along the
   // other; pick the (axis, R) that wastes the fewest MMA columns, preferring wide tiles
   // (N = 8 R >= 192 amortises the filter stream: 16 KB of L2 -> SM traffic per 4 N cycles).
-  const int force_axis = env_int("TRB_PT_AXIS", -1), force_r = env_int("TRB_PT_R", 0);
+  const int force_axis = env_int("TRB_PT_AXIS", -1), force_r = env_int("TRB_PT_R", a.patch_rows);
   double best = -1.0;
   const int halo = 2 * a.pad;
   for (int axis = 0; axis < 2; ++axis) {
@@ -820,7 +833,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   // Two CTAs per SM when one patch buffer + a filter ring of >= 2 x 16 KB fit in half of the SM's
   // shared memory (TRB_PT_DUAL: 0 never, 1 auto, 2 whenever it fits).
   {
-    const int want = env_int("TRB_PT_DUAL", 1);
+    const int want = env_int("TRB_PT_DUAL", 0);     // measured slower on every layer (profiles/r02_patch_dual.txt)
     const uint32_t half = 113u * 1024;
     const bool fits = p.patch_bytes + 2 * kFilterBlock + misc <= half;
     const bool worth = p.kchunks * p.taps >= 8;              // enough MMA work to hide the other CTA behind

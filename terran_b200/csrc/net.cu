@@ -121,8 +121,13 @@ bool mma_enabled() {
 
 // TRB_PATCH: 0 = never, 1 = auto (layers where the resident-patch kernel measured faster,
 // profiles/r02_patch_vs_plain.txt), 2 = every eligible layer.
-bool patch_wanted(const ConvArgs& a) {
+int patch_mode() {
   static const int mode = [] { const char* e = getenv("TRB_PATCH"); return e ? atoi(e) : 1; }();
+  return mode;
+}
+
+bool patch_wanted(const ConvArgs& a) {
+  const int mode = patch_mode();
   if (!mode || !conv_patch_eligible(a)) return false;
   if (mode >= 2) return true;
   // (64-filter layers run, but half of every 128-row MMA is padding: measured 25-60 % slower
@@ -285,7 +290,25 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
                  !a.shift9 && conv_mma_eligible(a);
         bool use_tc = !po.mma && !net->force_direct && !d.force_direct;
         if (use_tc && G == 1) use_tc = conv_tc_eligible(a);
-        if (use_tc && patch_wanted(a)) {
+        // A fully-connected layer (1x1 conv on 1x1 maps: ArcFace's 25088 -> 512) has one pixel
+        // per image — nothing for an 8 x R pixel tile.  The batch IS a pixel axis, though: NHWC
+        // rows of a (N,1,1,C) tensor are the pixels of a (1, N/8, 8, C) map, bit for bit, so the
+        // resident-patch kernel takes it as one image and splits the long K over all SMs
+        // (stream-K): 8 tiles x 392 channel chunks instead of 8 CTAs grinding through K alone.
+        ConvArgs fc = a;
+        const bool as_fc = use_tc && G == 1 && d.k == 1 && a.in.H == 1 && a.in.W == 1 && a.in.N % 8 == 0 &&
+                           a.in.N >= 64 && a.cin_pad >= 1024 && !a.res.ptr && patch_mode() != 0;
+        if (as_fc) {
+          fc.in.H = fc.out.H = a.in.N / 8; fc.in.W = fc.out.W = 8; fc.in.N = fc.out.N = 1;
+          fc.H_out = fc.in.H; fc.W_out = 8;
+          fc.patch_rows = 8;        // small tiles: more of them, so each is split over fewer CTAs
+        }
+        if (as_fc && conv_patch_eligible(fc)) {
+          fc.sk_scratch = lane_scratch(net, d.lane == 1);
+          po.pt = conv_patch_plan_create(fc, conv_tc_error_flag());
+          plan->tc_flops += po.flops;
+          plan->tc_launches++;
+        } else if (use_tc && patch_wanted(a)) {
           a.sk_scratch = lane_scratch(net, d.lane == 1);
           po.pt = conv_patch_plan_create(a, conv_tc_error_flag());
           plan->tc_flops += po.flops;
@@ -804,9 +827,10 @@ struct tr_model {
   float* f0 = nullptr; size_t f0_bytes = 0;     // PAF / raw embedding
   float* f1 = nullptr; size_t f1_bytes = 0;     // heat maps
   int32_t* cand = nullptr; size_t cand_bytes = 0;
+  uint8_t* u8 = nullptr; size_t u8_bytes = 0;   // padded crop batch
   ~tr_model() {
     if (net) tr_net_destroy(net);
-    for (void* p : {ws, static_cast<void*>(f0), static_cast<void*>(f1), static_cast<void*>(cand)})
+    for (void* p : {ws, static_cast<void*>(f0), static_cast<void*>(f1), static_cast<void*>(cand), static_cast<void*>(u8)})
       if (p) cudaFree(p);
   }
 };
@@ -901,18 +925,30 @@ int tr_arcface_forward(tr_model* m, const uint8_t* crops_dev, int N, int layout,
                        void* stream) {
   return guarded([&] {
     TR_CHECK(m->kind == 1, "not an ArcFace model");
+    TR_CHECK(N > 0, "empty batch");
     const int S = 112;
-    int rc = layout == 0
-                 ? tr_net_run(m->net, crops_dev + 2, N, S, S, int64_t(S) * S * 3, int64_t(S) * 3, 3, -1, stream)
-                 : tr_net_run(m->net, crops_dev, N, S, S, int64_t(3) * S * S, S, 1, int64_t(S) * S, stream);
-    if (rc) fail(g_last_error);
-    if (!normalise) {
-      if (tr_net_export_nchw_f32(m->net, m->roles[0], 0, 512, emb_dev, 0, stream)) fail(g_last_error);
-      return;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // Batches are padded to a multiple of 8 crops (zeros): the final FC then runs as a
+    // (1, N/8, 8, C) map on the resident-patch kernel with its K split over all SMs.
+    const int Np = round_up(N, 8);
+    const size_t crop_bytes = size_t(3) * S * S;
+    if (Np != N) {
+      grow(m->u8, m->u8_bytes, Np * crop_bytes);
+      TR_CUDA(cudaMemcpyAsync(m->u8, crops_dev, N * crop_bytes, cudaMemcpyDeviceToDevice, st));
+      TR_CUDA(cudaMemsetAsync(m->u8 + N * crop_bytes, 0, (Np - N) * crop_bytes, st));
+      crops_dev = m->u8;
     }
-    grow(m->f0, m->f0_bytes, size_t(N) * 512 * 4);
+    int rc = layout == 0
+                 ? tr_net_run(m->net, crops_dev + 2, Np, S, S, int64_t(S) * S * 3, int64_t(S) * 3, 3, -1, stream)
+                 : tr_net_run(m->net, crops_dev, Np, S, S, int64_t(3) * S * S, S, 1, int64_t(S) * S, stream);
+    if (rc) fail(g_last_error);
+    grow(m->f0, m->f0_bytes, size_t(Np) * 512 * 4);
     if (tr_net_export_nchw_f32(m->net, m->roles[0], 0, 512, m->f0, 0, stream)) fail(g_last_error);
-    if (tr_l2_normalize(m->f0, emb_dev, N, 512, stream)) fail(g_last_error);
+    if (normalise) {
+      if (tr_l2_normalize(m->f0, emb_dev, N, 512, stream)) fail(g_last_error);
+    } else {
+      TR_CUDA(cudaMemcpyAsync(emb_dev, m->f0, size_t(N) * 512 * 4, cudaMemcpyDeviceToDevice, st));
+    }
   });
 }
 

@@ -316,18 +316,22 @@ void build_retinaface(const StateDict& sd, bool fused, Program& P) {
   const int p8 = B.buffer(64);
   { ConvOpts o; o.res = a16; o.res_up2 = 1; cbr("refiner.conv_stride8.0", "refiner.conv_stride8.1", c8, p8, e, o); }
   const int a8 = B.buffer(64);
-  cbr("refiner.aggr_stride8.0", "refiner.aggr_stride8.1", p8, a8, e, ConvOpts{});
+  // The three pyramid levels' context modules and heads are independent chains of small,
+  // latency-bound kernels: stride 8 stays on the caller's stream, strides 16 and 32 run on the
+  // net's side stream (forked here, joined at the end of the program).
+  { ConvOpts o; o.sync = TR_SYNC_FORK; cbr("refiner.aggr_stride8.0", "refiner.aggr_stride8.1", p8, a8, e, o); }
 
   const int strides[3] = {8, 16, 32}, feats[3] = {a8, a16, p32};
   int heads[3] = {-1, -1, -1};
   for (int si = 0; si < 3; ++si) {
     const std::string st = std::to_string(strides[si]), p = "refiner.context_stride" + st;
     const int ctx = B.buffer(64), red = B.buffer(16), tmp = B.buffer(16);
-    cbr(p + ".context_3x3.0", p + ".context_3x3.1", feats[si], ctx, e, ConvOpts{});
-    cbr(p + ".dimension_reducer.0", p + ".dimension_reducer.1", feats[si], red, e, ConvOpts{});
-    { ConvOpts o; o.out_coff = 32; cbr(p + ".context_5x5.0", p + ".context_5x5.1", red, ctx, e, o); }
-    cbr(p + ".context_7x7.0", p + ".context_7x7.1", red, tmp, e, ConvOpts{});
-    { ConvOpts o; o.out_coff = 48; cbr(p + ".context_7x7.3", p + ".context_7x7.4", tmp, ctx, e, o); }
+    const int lane = si == 0 ? 0 : 1;
+    { ConvOpts o; o.lane = lane; cbr(p + ".context_3x3.0", p + ".context_3x3.1", feats[si], ctx, e, o); }
+    { ConvOpts o; o.lane = lane; cbr(p + ".dimension_reducer.0", p + ".dimension_reducer.1", feats[si], red, e, o); }
+    { ConvOpts o; o.lane = lane; o.out_coff = 32; cbr(p + ".context_5x5.0", p + ".context_5x5.1", red, ctx, e, o); }
+    { ConvOpts o; o.lane = lane; cbr(p + ".context_7x7.0", p + ".context_7x7.1", red, tmp, e, o); }
+    { ConvOpts o; o.lane = lane; o.out_coff = 48; cbr(p + ".context_7x7.3", p + ".context_7x7.4", tmp, ctx, e, o); }
     // fused head: [4 class logits | 8 bbox | 20 landmark] -> fp32
     Vec w(size_t(32) * 64), bias(32);
     const char* names[3] = {"cls", "bbox", "landmark"};
@@ -342,7 +346,7 @@ void build_retinaface(const StateDict& sd, bool fused, Program& P) {
       }
     }
     const int head = B.buffer(32, true);
-    ConvOpts o; o.engine = engine;
+    ConvOpts o; o.engine = engine; o.lane = lane;
     B.conv(w.data(), 32, 64, 1, ones(32), bias, ctx, head, o);
     heads[si] = head;
   }

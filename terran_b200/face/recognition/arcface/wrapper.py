@@ -144,6 +144,12 @@ class ArcFace:
         """crops: CUDA uint8, (N,112,112,3) RGB (``nhwc_rgb``) or the reference
         model input (N,3,112,112) BGR (``nchw_bgr``).  Returns (N,512) fp32 CUDA."""
         crops = crops.contiguous()          # element strides below assume a dense tensor
+        n_real = crops.shape[0]
+        if n_real % 8:
+            # batches are padded to a multiple of 8 crops: the final FC then runs as a
+            # (1, N/8, 8, C) map on the resident-patch kernel with its K split over all SMs
+            pad = torch.zeros((8 - n_real % 8,) + tuple(crops.shape[1:]), dtype=crops.dtype, device=crops.device)
+            crops = torch.cat([crops, pad], 0)
         N = crops.shape[0]
         S = self.image_side
         if layout == 'nhwc_rgb':
@@ -152,9 +158,11 @@ class ArcFace:
         else:
             assert tuple(crops.shape[1:]) == (3, S, S)
             self.net.run(crops, N, S, S, (3 * S * S, S, 1, S * S))
-        raw = self.net.export_nchw_f32(self.roles['embedding'], 0, 512).reshape(N, 512)
+        raw = self.net.export_nchw_f32(self.roles['embedding'], 0, 512).reshape(N, 512)[:n_real]
+        N = n_real
         if not normalise:
-            return raw
+            return raw.contiguous()
+        raw = raw.contiguous()
         out = torch.empty_like(raw)
         nat.check(nat.lib().tr_l2_normalize(C.c_void_p(raw.data_ptr()), C.c_void_p(out.data_ptr()),
                                             N, 512, nat.current_stream_ptr()))

@@ -116,7 +116,7 @@ def retinaface_program(sd, fused=True):
     p8 = P.buffer(64)
     cbr('refiner.conv_stride8.0', 'refiner.conv_stride8.1', c8, p8, e, res=a16, res_up2=1)
     a8 = P.buffer(64)
-    cbr('refiner.aggr_stride8.0', 'refiner.aggr_stride8.1', p8, a8, e)
+    cbr('refiner.aggr_stride8.0', 'refiner.aggr_stride8.1', p8, a8, e, sync=nat.TR_SYNC_FORK)
 
     heads, ctxs = {}, {}
     for stride, feat in ((8, a8), (16, a16), (32, p32)):
@@ -124,11 +124,12 @@ def retinaface_program(sd, fused=True):
         ctx = P.buffer(64)
         red = P.buffer(16)
         tmp = P.buffer(16)
-        cbr(p + '.context_3x3.0', p + '.context_3x3.1', feat, ctx, e, out_coff=0)
-        cbr(p + '.dimension_reducer.0', p + '.dimension_reducer.1', feat, red, e)
-        cbr(p + '.context_5x5.0', p + '.context_5x5.1', red, ctx, e, out_coff=32)
-        cbr(p + '.context_7x7.0', p + '.context_7x7.1', red, tmp, e)
-        cbr(p + '.context_7x7.3', p + '.context_7x7.4', tmp, ctx, e, out_coff=48)
+        lane = 0 if stride == 8 else 1        # strides 16 and 32 on the side stream
+        cbr(p + '.context_3x3.0', p + '.context_3x3.1', feat, ctx, e, out_coff=0, lane=lane)
+        cbr(p + '.dimension_reducer.0', p + '.dimension_reducer.1', feat, red, e, lane=lane)
+        cbr(p + '.context_5x5.0', p + '.context_5x5.1', red, ctx, e, out_coff=32, lane=lane)
+        cbr(p + '.context_7x7.0', p + '.context_7x7.1', red, tmp, e, lane=lane)
+        cbr(p + '.context_7x7.3', p + '.context_7x7.4', tmp, ctx, e, out_coff=48, lane=lane)
         # fused head: [4 class logits | 8 bbox | 20 landmark] -> fp32
         w = torch.cat([sd[f'outputs.cls_stride{stride}.weight'],
                        sd[f'outputs.bbox_stride{stride}.weight'],
@@ -137,7 +138,7 @@ def retinaface_program(sd, fused=True):
                           sd[f'outputs.bbox_stride{stride}.bias'],
                           sd[f'outputs.landmark_stride{stride}.bias']], 0)
         head = P.buffer(32, f32=True)
-        P.conv(w, np.ones(32, np.float32), bias.float().numpy(), ctx, head, engine=engine)
+        P.conv(w, np.ones(32, np.float32), bias.float().numpy(), ctx, head, engine=engine, lane=lane)
         heads[stride] = head
         ctxs[stride] = ctx
     roles = {'heads': [heads[32], heads[16], heads[8]], 'context': ctxs}
