@@ -33,6 +33,23 @@ def run(tag, N, H, W, cin, cout, k, env, engine=3, repeat=20):
 
 
 MODE = sys.argv[1] if len(sys.argv) > 1 else 'sweep'
+if MODE == 'fc':
+    # ArcFace's 25088 -> 512 FC as a (1, 32, 8, 25088) map: split-K over all SMs, patch-buffer depth
+    for nbuf in (2, 4, 8):
+        for R in (8, 16):
+            run(f'arcface fc 25088->512 x256 R={R} nbuf={nbuf}', 1, 32, 8, 25088, 512, 1,
+                {'TRB_PT_R': R, 'TRB_PT_NBUF': nbuf, 'TRB_PT_AXIS': 0})
+    run('trace arcface fc nbuf=8', 1, 32, 8, 25088, 512, 1, {'TRB_PT_R': 8, 'TRB_PT_AXIS': 0, 'TRB_PT_DEBUG': 32}, repeat=6)
+    sys.exit(0)
+if MODE == 'epi':
+    # is the epilogue the bound of the short-K layers?  (64: no epilogue at all, 4: no stores, 2: no MMAs)
+    for tag, shape in (('vgg 3x3 64->128 @92x163', (32, 92, 163, 64, 128, 3)),
+                       ('vgg 3x3 128->128 @92x163', (32, 92, 163, 128, 128, 3)),
+                       ('vgg 3x3 256->256 @46x81', (32, 46, 81, 256, 256, 3)),
+                       ('arcface 3x3 128 @28', (256, 28, 28, 128, 128, 3))):
+        for dbg in (0, 64, 4, 2, 66):
+            run(f'{tag} dbg={dbg}', *shape, {'TRB_PT_SK': 0, 'TRB_PT_DEBUG': dbg})
+    sys.exit(0)
 if MODE == 'dual':
     for dual in (0, 2):
         run(f'openpose 7x7 128->128 dual={dual}', 32, 23, 40, 128, 128, 7, {'TRB_PT_DUAL': dual})

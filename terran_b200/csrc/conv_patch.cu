@@ -46,8 +46,14 @@ namespace {
 constexpr int kPThreads = 352;            // 8 epilogue warps, one CTA per SM
 constexpr int kPThreadsDual = 224;        // 4 epilogue warps, two CTAs per SM
 constexpr int kPMaxStages = 12;
+constexpr int kPMaxPatchBufs = 8;         // patch buffers (2 normally; more for small 1x1 patches)
 constexpr uint32_t kFilterBlock = 128 * 64 * 2;      // one (tap, chunk) filter block: 16 KB
-constexpr uint32_t kOutStage = 2 * 4096;             // per team: 16 pixels x 128 couts fp16
+// Epilogue staging: per team a ring of kStageSlots tiles of 16 pixels x 128 couts fp16 (4 KB),
+// so that up to kStageSlots TMA stores of a team are in flight and a chunk only waits for the
+// store issued kStageSlots chunks earlier (one slot per team = one store round trip per 16
+// pixels, ~9 us per 256-pixel tile: measured as the bound of every layer with K <= 1152).
+constexpr int kStageSlots = 2;
+constexpr uint32_t kOutStage = 2 * kStageSlots * 4096;
 
 struct PatchParams {
   int N, H, W;                 // output == input dims (stride 1, "same" padding)
@@ -86,7 +92,8 @@ struct PatchParams {
   int pdl_late;
   unsigned long long* trace;   // debug & 32: globaltimer stamps of CTA 0, 16 per launch
   int debug;                   // timing experiments: 1 no filter TMA, 2 no MMA, 4 no stores,
-                               // 8 no ring-release handshake (with 1), 16 no full-barrier waits (with 1)
+                               // 8 no ring-release handshake (with 1), 16 no full-barrier waits (with 1),
+                               // 64 no epilogue (with TRB_PT_SK=0)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
@@ -182,13 +189,13 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * kPMaxStages + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * kPMaxStages + 2 + a); };
   auto pfull_bar = [&](int b) { return bars + 8u * (2 * kPMaxStages + 4 + b); };
-  auto pempty_bar = [&](int b) { return bars + 8u * (2 * kPMaxStages + 6 + b); };
-  const uint32_t tmem_slot = bars + 8u * (2 * kPMaxStages + 8);
+  auto pempty_bar = [&](int b) { return bars + 8u * (2 * kPMaxStages + 4 + kPMaxPatchBufs + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kPMaxStages + 4 + 2 * kPMaxPatchBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   volatile unsigned* trace_slot_s =
-      reinterpret_cast<volatile unsigned*>(smem_raw + (bars + 8u * (2 * kPMaxStages + 9) - smem_u32(smem_raw)));
+      reinterpret_cast<volatile unsigned*>(smem_raw + (bars + 8u * (2 * kPMaxStages + 5 + 2 * kPMaxPatchBufs) - smem_u32(smem_raw)));
   if (p.trace && threadIdx.x == 0) {
     *trace_slot_s = blockIdx.x == 0 ? static_cast<unsigned>(atomicAdd(p.trace, 1ULL)) : 0u;
     if (blockIdx.x == 0) p.trace[1 + 16 * (*trace_slot_s & 63) + 0] = global_ns();
@@ -205,8 +212,10 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), p.epi_warps);
-      mbar_init(pfull_bar(a), 1);
-      mbar_init(pempty_bar(a), 1);
+    }
+    for (int b = 0; b < p.nbuf; ++b) {
+      mbar_init(pfull_bar(b), 1);
+      mbar_init(pempty_bar(b), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -358,8 +367,9 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int A_dim = p.axis == 0 ? p.W : p.H, B_dim = p.axis == 0 ? p.H : p.W;
     const int a_step = p.axis == 0 ? 1 : p.W;             // pixel-index step along the group axis
     const int b_step = p.axis == 0 ? p.W : 1;
-    const uint32_t my_stage = stage_out + team * 4096u;   // [16 pixels][128 couts] fp16
+    const uint32_t team_stage = stage_out + team * (kStageSlots * 4096u);   // slots of [16 pixels][128 couts] fp16
     const bool store_leader = (ew & 3) == 0 && lane == 0;
+    unsigned chunk_ctr = 0;                               // staging slot = chunk_ctr % kStageSlots (across tiles)
     int tile_it = 0;
     Walk w = walk_begin(p);
     Seg sg;
@@ -410,6 +420,12 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (warp == 2) PT_STAMP(5);                           // accumulator complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * p.NP;
+      if (p.debug & 64) {                                   // timing only (with TRB_PT_SK=0): no epilogue at all
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        continue;
+      }
       if (sg.i0 > 0) {
         // Stream-K: a tile whose first iterations belong to an earlier CTA.  Park the raw
         // accumulator as [group][lane][8]: a warp writes 1 KB runs.
@@ -595,7 +611,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         };
         if (n_parts) fetch_part0(g_begin);
         const int tid = (ew & 3) * 32 + lane;
-        for (int g = g_begin; g < g_end; g += 2) {
+        for (int g = g_begin; g < g_end; g += 2, ++chunk_ctr) {
+          const uint32_t my_stage = team_stage + (chunk_ctr % kStageSlots) * 4096u;
           uint32_t v[16];
           uint4 rv[2];
           if (p.res) {                       // requested first: in flight during the TMEM read and the math
@@ -641,8 +658,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         i < 8 ? pixel_shift(i, f0, m0, l0) : pixel_shift(i - 8, f1, m1, l1));
             y[i] = fmaf(fminf(y[i], 0.f), neg, fmaxf(y[i], 0.f));
           }
-          // the previous store of this team has finished READING the staging tile
-          if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          // the store that used this slot kStageSlots chunks ago has finished READING it
+          if (store_leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStageSlots - 1) : "memory");
           asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
           const uint32_t dst = my_stage + cl * 2u;
           if (p.res) {
@@ -829,7 +846,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   p.total_tiles = p.pix_tiles * p.cout_tiles;
   p.patch_tx = p.PA * (p.R + halo) * 128;
   p.patch_bytes = round_up(p.patch_tx, 1024);
-  const uint32_t misc = kOutStage + 512 + 8 * (2 * kPMaxStages + 10) + 1024 /*alignment*/;
+  const uint32_t misc = kOutStage + 512 + 8 * (2 * kPMaxStages + 6 + 2 * kPMaxPatchBufs) + 1024 /*alignment*/;
   // Two CTAs per SM when one patch buffer + a filter ring of >= 2 x 16 KB fit in half of the SM's
   // shared memory (TRB_PT_DUAL: 0 never, 1 auto, 2 whenever it fits).
   {
@@ -840,6 +857,12 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
     plan->dual = fits && (want == 2 || (want == 1 && worth));
   }
   p.nbuf = plan->dual ? 1 : 2;
+  // A 1x1 layer consumes one (small) patch per ring iteration, so two buffers leave one TMA
+  // load in flight and the K loop runs at one L2/HBM latency per chunk (the 25088-channel
+  // ArcFace FC: 392 chunks).  Up to eight patches of <= 8 KB keep that latency covered.
+  if (!plan->dual && p.taps == 1 && p.kchunks >= 8)
+    p.nbuf = std::max(2, std::min<int>(kPMaxPatchBufs, (64u * 1024) / p.patch_bytes));
+  p.nbuf = std::max(1, std::min(p.nbuf, env_int("TRB_PT_NBUF", kPMaxPatchBufs)));
   p.nacc = plan->dual ? 1 : 2;
   p.epi_warps = plan->dual ? 4 : 8;
   p.ring_off = p.nbuf * p.patch_bytes;

@@ -103,6 +103,14 @@ struct TcParams {
   int cta2, pair_units;      // CTA-pair kernel: units = ceil(m_tiles / 2) * n_tiles
   uint32_t idesc2;
   uint32_t patch_bytes, patch_tx, ring_off;
+  // Resident-filter halo mode (one channel chunk, one filter tile, taps * b_bytes small — the
+  // 64 -> 64 3x3 layers): the whole filter bank is loaded ONCE per CTA into the ring area and
+  // never released; the only stream is one input patch per tile through `npatch` buffers
+  // (requested up to npatch - 1 tiles ahead), and a tile costs the issuing thread one patch
+  // wait + taps * KSTEPS MMAs + two commits — no ring hand-shake.  Measured before (clock64
+  // instrumentation, profiles/r02_resident_filters.txt): 5 080 cycles per 128-pixel tile, of
+  // which ~4 500 is the latency of the single patch in flight and 2 700 the MMA issue.
+  int resident, npatch;
 };
 
 // Walks the tile segments of one CTA: whole tiles with the static stride, or the CTA's
@@ -494,6 +502,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(pfull_bar(a), 1);
       mbar_init(pempty_bar(a), p.issuers);
     }
+    if (p.resident)      // patch buffers use ring barriers 1..npatch (the ring itself is one resident stage)
+      for (int b = 0; b < p.npatch; ++b) {
+        mbar_init(full_bar(1 + b), 1);
+        mbar_init(empty_bar(1 + b), 1);
+      }
     prog[0] = 0; prog[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -551,7 +564,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     long long dbg_wait = 0, dbg_pwait = 0, dbg_t0 = clock64();
     int dbg_iters = 0;
     int pq = 0, pq_issued = 0;                   // halo: chunk-steps produced / patches requested
-    while (walk_next(p, walk, tile, it0, it1)) {
+    if (p.resident) {
+      if (elect_one()) {
+        mbar_expect_tx(full_bar(0), p.taps * w_rows * p.KC * 2);
+        for (int t = 0; t < p.taps; ++t)
+          tma_load_2d(ring + t * p.b_bytes, &tmB, full_bar(0), t * p.cin_pad, 0);
+      }
+      __syncwarp();
+      for (int q = 0; walk_next(p, walk, tile, it0, it1); ++q) {
+        if (p.pdl_late && walk_done(p, walk))
+          asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        const int buf = q % p.npatch;
+        mbar_wait(empty_bar(1 + buf), ((q / p.npatch) & 1u) ^ 1u, p.err, 5);
+        if (elect_one()) {
+          int pm = tile / p.n_tiles;
+          const int pwb = pm % p.tiles_w; pm /= p.tiles_w;
+          const int phb = pm % p.tiles_h; pm /= p.tiles_h;
+          const int cw = pwb * p.bw - p.pad, ch = phb * p.bh - p.pad;
+          mbar_expect_tx(full_bar(1 + buf), p.patch_tx);
+          tma_load_5d(base + buf * p.patch_bytes, &tmA, full_bar(1 + buf), p.in_coff,
+                      p.halo == 1 ? cw : ch, p.halo == 1 ? ch : cw, pm * p.bn, 0);
+        }
+        __syncwarp();
+      }
+    }
+    while (!p.resident && walk_next(p, walk, tile, it0, it1)) {
       // A dependent CTA that is resident early only spins in griddepcontrol.wait while holding
       // an SM that a kernel of another stream could use: release it late.
       if (p.pdl_late && walk_done(p, walk))
@@ -683,7 +720,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int tile, it0, it1;
     long long dbg_wf = 0, dbg_te = 0, dbg_pw = 0, dbg_last = 0, dbg_t0 = clock64(), dbg_issue = 0, dbg_commit = 0;
     int dbg_n = 0;
-    for (; walk_next(p, walk, tile, it0, it1); ++tile_it) {
+    if (p.resident) {
+      mbar_wait(full_bar(0), 0, p.err, 3);                  // the filter bank has landed
+      for (; walk_next(p, walk, tile, it0, it1); ++tile_it) {
+        const int acc = tile_it & 1;
+        mbar_wait(tempty_bar(acc), ((tile_it >> 1) & 1u) ^ 1u, p.err, 2);
+        const int buf = tile_it % p.npatch;
+        mbar_wait(full_bar(1 + buf), (tile_it / p.npatch) & 1u, p.err, 6);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + acc * p.acc_cols;
+          const uint32_t patch_lo = umma_desc_lo(base + buf * p.patch_bytes);
+          uint32_t accumulate = 0;
+          if (!(p.debug & 2)) {
+            for (int t = 0; t < p.taps; ++t) {
+              uint32_t tap_off;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tap_off) : "r"(tab_s + 4u * t));
+              const uint32_t a_lo = patch_lo + tap_off;
+              const uint32_t b_lo = a_lo0 + t * (p.b_bytes >> 4);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                umma_f16(d_tmem, a_lo + 2 * k, halo_hi, b_lo + 2 * k, desc_hi, p.idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+          }
+          umma_commit(empty_bar(1 + buf));
+          umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+      }
+    }
+    for (; !p.resident && walk_next(p, walk, tile, it0, it1); ++tile_it) {
       const int acc = tile_it & 1;
       const uint32_t acc_phase = (tile_it >> 1) & 1u;
       if (p.debug & 32) dbg_last = clock64();
@@ -1530,18 +1598,34 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     const int per_tile = p.halo ? p.kchunks * ceil_div(p.taps, p.sub) : p.iters;
     p.issuers = ok && (want == 2 || (want == 1 && per_tile >= 4)) ? 2 : 1;
   }
-  p.iters_kc = ceil_div(p.taps, p.sub);
-  p.stage_bytes = p.sub * p.sub_bytes;
   const uint32_t param_bytes = uint32_t(p.param_rows) * p.cout_pad * 4u;
   if (p.halo) {
     p.patch_tx = ((p.swap ? p.bw : 16) + 2 * a.pad) * 16 * 128;
     p.patch_bytes = round_up(p.patch_tx, 1024);
     p.ring_off = 2 * p.patch_bytes;
+    // Resident filters (see TcParams::resident): whole filter bank + >= 3 patch buffers in 227 KB.
+    int want = 1;
+    if (const char* e = getenv("TRB_TC_RESIDENT")) want = atoi(e);
+    const uint32_t bank = uint32_t(p.taps) * p.b_bytes;
+    const uint32_t room = 227u * 1024 - 1024 /*alignment*/ - 256 - 8 * (2 * kMaxStages + 12) - 16 - param_bytes;
+    const int npatch = bank < room ? std::min<int>(kMaxStages - 1, std::min<int>(4, (room - bank) / p.patch_bytes)) : 0;
+    if (want && !p.swap && !p.cta2 && p.kchunks == 1 && p.n_tiles == 1 && plan->ctas_per_sm == 1 &&
+        p.taps <= 64 && npatch >= 3) {
+      p.resident = 1;
+      p.npatch = npatch;
+      p.issuers = 1;
+      p.sub = p.taps;                      // the "ring" is one stage that holds every tap
+      p.iters = 1;
+      p.ring_off = npatch * p.patch_bytes;
+    }
   }
+  p.iters_kc = ceil_div(p.taps, p.sub);
+  p.stage_bytes = p.sub * p.sub_bytes;
   // the patch variant of swap mode keeps two (bw + 2 pad) x 16 pixel patches resident: use all 227 KB
   const uint32_t budget = p.swap && p.halo ? 224u * 1024 : plan->ctas_per_sm == 2 ? 108u * 1024 : kSmemBudget;
   p.stages = std::min(kMaxStages, int((budget - param_bytes - p.ring_off) / p.stage_bytes));
   p.stages = std::max(2, std::min(p.stages, (p.halo ? p.iters_kc * p.kchunks : p.iters) + 1));
+  if (p.resident) p.stages = 1;
   p.sbo_bytes = 8u * p.KC * 2u;
   CUtensorMapSwizzle swz;
   if (p.KC == 64) { p.layout_type = 2; swz = CU_TENSOR_MAP_SWIZZLE_128B; }

@@ -46,10 +46,13 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 __device__ __forceinline__ int src_floor(int o) { return (o + 4) / 8 - 1; }
 
 // Bicubic x8 value of one channel map (h x w) at up-sampled pixel (y, x).
-__device__ __forceinline__ float bicubic_at(const float* __restrict__ m, int h, int w, int y, int x) {
+// (`tab` = the 8 x 4 tap table in SHARED memory: the phase differs from thread to thread, and a
+// divergent index into __constant__ memory is serialised by the constant cache)
+__device__ __forceinline__ float bicubic_at(const float* __restrict__ m, const float (*tab)[4], int h, int w,
+                                            int y, int x) {
   const int fy = src_floor(y), fx = src_floor(x);
-  const float* wy = c_bicubic[y & 7];
-  const float* wx = c_bicubic[x & 7];
+  const float* wy = tab[y & 7];
+  const float* wx = tab[x & 7];
   int ix[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) ix[j] = clampi(fx - 1 + j, 0, w - 1);
@@ -67,70 +70,91 @@ __device__ __forceinline__ float bicubic_at(const float* __restrict__ m, int h, 
 }
 
 // ---- 1. peaks: block = (band of 8 up-sampled rows, part, frame)
+// A thread owns COLUMNS of the band (x = tid, tid + 256, ...): the ten up-sampled rows
+// 8*band-1 .. 8*band+8 of a column are combinations of the same five horizontally interpolated
+// source rows, with weights and row slots that are compile-time constants per row (row k has
+// phase (k - 1) & 7 and starts at slot k >= 5), so there is no integer division, no clamp and
+// no dynamically indexed constant-memory read in the inner loops.
 __global__ void __launch_bounds__(256) pose_peaks_kernel(const PoseParams p) {
   extern __shared__ float sm[];
   const int band = blockIdx.x, part = blockIdx.y, n = blockIdx.z;
-  const int Wu = p.Wu, Hu = p.Hu;
+  const int Wu = p.Wu, Hu = p.Hu, w = p.w;
   float* rows_h = sm;                 // [5][Wu] horizontally interpolated source rows band-2..band+2
   float* up = sm + 5 * Wu;            // [10][Wu] up-sampled rows 8*band-1 .. 8*band+8
-  const float* m = p.heat + (static_cast<long>(n) * 19 + part) * p.h * p.w;
+  float* src = sm + 15 * Wu;          // [5][w] source rows band-2..band+2 (clamped)
+  __shared__ __align__(16) float wtab[8][4];
+  const float* m = p.heat + (static_cast<long>(n) * 19 + part) * p.h * w;
+  if (threadIdx.x < 32) wtab[threadIdx.x >> 2][threadIdx.x & 3] = c_bicubic[threadIdx.x >> 2][threadIdx.x & 3];
   // Early out: every up-sampled value of this band is a bicubic combination of the
   // source rows band-2..band+2, so |value| <= (max sum|w|)^2 * max|source|.  If that bound
   // is below the 0.1 peak threshold the band cannot contain a peak (exact, not a heuristic).
   {
     float mx = 0.f;
-    for (int t = threadIdx.x; t < 5 * p.w; t += 256) {
-      const int k = t / p.w, x = t % p.w;
-      mx = fmaxf(mx, fabsf(m[clampi(band - 2 + k, 0, p.h - 1) * p.w + x]));
+    for (int k = 0; k < 5; ++k) {
+      const float* row = m + clampi(band - 2 + k, 0, p.h - 1) * w;
+      for (int x = threadIdx.x; x < w; x += 256) {
+        const float v = row[x];
+        src[k * w + x] = v;
+        mx = fmaxf(mx, fabsf(v));
+      }
     }
     if (__syncthreads_count(mx * p.bicubic_gain >= 0.1f) == 0) return;
   }
-  for (int t = threadIdx.x; t < 5 * Wu; t += 256) {
-    const int k = t / Wu, x = t % Wu;
-    const float* row = m + clampi(band - 2 + k, 0, p.h - 1) * p.w;
+  for (int x = threadIdx.x; x < Wu; x += 256) {
     const int fx = src_floor(x);
-    const float* wx = c_bicubic[x & 7];
-    float r = row[clampi(fx - 1, 0, p.w - 1)] * wx[0];
-    r = r + row[clampi(fx, 0, p.w - 1)] * wx[1];
-    r = r + row[clampi(fx + 1, 0, p.w - 1)] * wx[2];
-    r = r + row[clampi(fx + 2, 0, p.w - 1)] * wx[3];
-    rows_h[t] = r;
+    const float4 wx = *reinterpret_cast<const float4*>(wtab[x & 7]);
+    const int i0 = clampi(fx - 1, 0, w - 1), i1 = clampi(fx, 0, w - 1), i2 = clampi(fx + 1, 0, w - 1),
+              i3 = clampi(fx + 2, 0, w - 1);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float* row = src + k * w;
+      float r = row[i0] * wx.x;
+      r = r + row[i1] * wx.y;
+      r = r + row[i2] * wx.z;
+      r = r + row[i3] * wx.w;
+      rows_h[k * Wu + x] = r;
+    }
   }
   __syncthreads();
   const int y_first = 8 * band - 1;
-  for (int t = threadIdx.x; t < 10 * Wu; t += 256) {
-    const int k = t / Wu, x = t % Wu;
-    const int y = y_first + k;
-    if (y < 0 || y >= Hu) continue;
-    const int fy = src_floor(y);
-    const float* wy = c_bicubic[y & 7];
-    // source row fy-1+i, clamped, lives in rows_h slot (row - (band-2)); the clamp
-    // commutes with the slot lookup because slots hold clamped rows too.
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int slot = clampi(fy - 1 + i, 0, p.h - 1) - (band - 2);
-      const int sl = clampi(slot, 0, 4);
-      const float r = rows_h[sl * Wu + x];
-      acc = (i == 0) ? r * wy[0] : acc + r * wy[i];
-    }
-    up[t] = acc;
-  }
-  __syncthreads();
   unsigned long long* keys = p.peak_keys + (static_cast<long>(n) * 18 + part) * kPeakCap;
   int* cnt = p.peak_cnt + n * 18 + part;
-  for (int t = threadIdx.x; t < 8 * Wu; t += 256) {
-    const int k = t / Wu + 1, x = t % Wu;
-    const int y = y_first + k;
-    if (y < 1 || y > Hu - 2 || x < 1 || x > Wu - 2) continue;
-    const float v = up[k * Wu + x];
-    if (v >= up[(k - 1) * Wu + x] && v >= up[k * Wu + x - 1] && v >= up[(k + 1) * Wu + x] &&
-        v >= up[k * Wu + x + 1] && v >= 0.1f) {
-      const int slot = atomicAdd(cnt, 1);
-      if (slot < kPeakCap)
-        keys[slot] = (static_cast<unsigned long long>(y * Wu + x) << 32) | __float_as_uint(v);
-      else
-        atomicOr(p.out.status + n, 1);
+  // pass 1: the ten rows of each owned column -> shared memory (neighbouring columns need them)
+  for (int x = threadIdx.x; x < Wu; x += 256) {
+    float r[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) r[k] = rows_h[k * Wu + x];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      // row y = 8 band - 1 + k: phase (k + 7) & 7, source rows start at slot (k >= 5) (the slots
+      // hold clamped rows, so the border clamp of the reference is already applied)
+      const int ph = (k + 7) & 7, s0 = k >= 5 ? 1 : 0;
+      float acc = r[s0] * c_bicubic[ph][0];
+      acc = acc + r[s0 + 1] * c_bicubic[ph][1];
+      acc = acc + r[s0 + 2] * c_bicubic[ph][2];
+      acc = acc + r[s0 + 3] * c_bicubic[ph][3];
+      up[k * Wu + x] = acc;
+    }
+  }
+  __syncthreads();
+  // pass 2: 4-neighbour maxima of rows 1..8
+  for (int x = threadIdx.x; x < Wu; x += 256) {
+    if (x < 1 || x > Wu - 2) continue;
+    float c[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) c[k] = up[k * Wu + x];
+#pragma unroll
+    for (int k = 1; k <= 8; ++k) {
+      const int y = y_first + k;
+      const float v = c[k];
+      if (y < 1 || y > Hu - 2 || !(v >= 0.1f) || !(v >= c[k - 1]) || !(v >= c[k + 1])) continue;
+      if (v >= up[k * Wu + x - 1] && v >= up[k * Wu + x + 1]) {
+        const int slot = atomicAdd(cnt, 1);
+        if (slot < kPeakCap)
+          keys[slot] = (static_cast<unsigned long long>(y * Wu + x) << 32) | __float_as_uint(v);
+        else
+          atomicOr(p.out.status + n, 1);
+      }
     }
   }
 }
@@ -179,6 +203,8 @@ __global__ void __launch_bounds__(256) pose_limbs_kernel(const PoseParams p) {
   __shared__ unsigned long long cand[kCandCap];
   __shared__ int cand_n;
   __shared__ unsigned seen[kPeakCap / 32];
+  __shared__ float wtab[8][4];
+  if (threadIdx.x < 32) wtab[threadIdx.x >> 2][threadIdx.x & 3] = c_bicubic[threadIdx.x >> 2][threadIdx.x & 3];
   const int limb = blockIdx.x, n = blockIdx.y;
   const int ks = c_limbseq[limb][0] - 1, kd = c_limbseq[limb][1] - 1;
   const int* cnts = p.peak_cnt + n * 18;
@@ -215,8 +241,8 @@ __global__ void __launch_bounds__(256) pose_limbs_kernel(const PoseParams p) {
     for (int k = 0; k < 10; ++k) {
       const int py = seg_point(fsy, fdy, step_y, k);
       const int px = seg_point(fsx, fdx, step_x, k);
-      const float a = bicubic_at(mx, p.h, p.w, py, px) * ux;
-      const float b = bicubic_at(my, p.h, p.w, py, px) * uy;
+      const float a = bicubic_at(mx, wtab, p.h, p.w, py, px) * ux;
+      const float b = bicubic_at(my, wtab, p.h, p.w, py, px) * uy;
       const float mscore = a + b;
       if (mscore > 0.05f) ++above;
       total = total + mscore;
@@ -464,7 +490,7 @@ void pose_parse_launch(const float* paf, const float* heat, int N, int h, int w,
   TR_CHECK(long(p.Hu) * p.Wu < (1L << 31), "up-sampled map too large");
   TR_CUDA(cudaMemsetAsync(p.peak_cnt, 0, size_t(N) * 18 * 4, s));
   TR_CUDA(cudaMemsetAsync(out.status, 0, size_t(N) * 4, s));
-  const size_t smem = size_t(15) * p.Wu * sizeof(float);
+  const size_t smem = (size_t(15) * p.Wu + size_t(5) * w) * sizeof(float);
   static size_t smem_set[kMaxDevices] = {};
   if (smem > 48 * 1024 && smem > smem_set[dev]) {
     TR_CUDA(cudaFuncSetAttribute(pose_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

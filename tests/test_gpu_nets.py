@@ -5,7 +5,8 @@ Stated tolerances (fp16 activations/weights, fp32 accumulation; SURVEY.md
 section 8(d)): RetinaFace class probabilities |d| <= 5e-3 away from saturation
 (the synthetic class head has a x30 gain, so logits are compared at 0.25),
 bbox/landmark deltas <= 4e-3; ArcFace normalised embedding cosine >= 0.9999 and
-max |d| <= 5e-3; OpenPose maps <= 4e-3.  Integer outputs are compared at stage
+max |d| <= 5e-3; OpenPose maps <= 2e-3 OF THE MAP RANGE on the golden fixture (measured 5e-4),
+<= 4e-3 of the range at 16 x 184x327 (measured 1.9e-3).  Integer outputs are compared at stage
 level (tests/test_gpu_post.py); end to end they are compared as sets."""
 import numpy as np
 import pytest
@@ -89,7 +90,8 @@ def test_retinaface_call_end_to_end(native, retina, golden):
     assert len(out) == 3
     for n, faces in enumerate(out):
         ref = [{'bbox': b} for b in g[f'bbox{n}']]
-        assert match_fraction(faces, ref) >= 0.8, (n, len(faces), len(ref))
+        print(f'retinaface call image {n}: {match_fraction(faces, ref):.3f} of {len(ref)} reference faces identical')
+        assert match_fraction(faces, ref) >= 0.9, (n, len(faces), len(ref))   # measured 1.0 / 0.966 / 1.0 (scores within fp16 noise of 0.5 may flip; the exact rule is in test_gpu_baseline_sizes.py)
         assert abs(len(faces) - len(ref)) <= max(3, len(ref) // 5)
         assert faces[0]['bbox'].dtype == np.float32 and faces[0]['landmarks'].shape == (5, 2)
 
@@ -104,7 +106,8 @@ def test_detection_wrapper(native, retina, golden):
     g = golden('retinaface_detection_640.npz')
     faces = det(img)
     ref = [{'bbox': b} for b in g['bbox']]
-    assert match_fraction(faces, ref) >= 0.8
+    print(f'detection 640: {match_fraction(faces, ref):.3f} of {len(ref)} reference faces identical')
+    assert match_fraction(faces, ref) >= 0.9      # measured 1.0 (23 of 23)
     assert faces[0]['bbox'].dtype == np.int32 and faces[0]['landmarks'].dtype == np.int32
     # device resize and host cv2 resize give the same answer
     det.device_resize = False
@@ -167,8 +170,14 @@ def test_openpose_maps(native, opose, golden, mode):
         paf, heat = model.maps(torch.from_numpy(np.ascontiguousarray(frames)).cuda())
     finally:
         model.net.set_force_direct(False)
-    assert np.abs(paf.cpu().numpy() - g['paf']).max() <= 4e-3
-    assert np.abs(heat.cpu().numpy() - g['heat']).max() <= 4e-3
+    # fp16 operands through 92 convs: measured 5.3e-4 (PAF) / 1.4e-4 (heat) of the map RANGE on
+    # B200 for this fixture; asserted <= 2e-3 of the range (a wrong border tap of one 7x7 moves
+    # border pixels by > 2e-2 of the range) — the maps span only 0.6 / 0.08, so an absolute
+    # bound says little.
+    dp, dh = np.abs(paf.cpu().numpy() - g['paf']).max(), np.abs(heat.cpu().numpy() - g['heat']).max()
+    print(f'openpose maps ({mode}): paf {dp:.2e} of range {np.ptp(g["paf"]):.3f}, heat {dh:.2e} of range {np.ptp(g["heat"]):.3f}')
+    assert dp <= 2e-3 * np.ptp(g['paf']), (dp, np.ptp(g['paf']))
+    assert dh <= 2e-3 * np.ptp(g['heat']), (dh, np.ptp(g['heat']))
 
 
 def test_full_size_tensor_core_path_agrees_with_direct_path(native, retina, opose):
@@ -252,8 +261,8 @@ def test_estimation_wrapper(native, opose):
     assert tuple(paf.shape) == (1, 38, 23, 40) and tuple(heat.shape) == (1, 19, 23, 40)
     xin = (resized.cpu().numpy().transpose(0, 3, 1, 2).astype(np.float32) / 255.0 - 0.5)
     paf_ref, heat_ref = nets.openpose_forward(sd, torch.from_numpy(xin))
-    assert np.abs(paf.cpu().numpy() - paf_ref.numpy()).max() <= 4e-3
-    assert np.abs(heat.cpu().numpy() - heat_ref.numpy()).max() <= 4e-3
+    assert np.abs(paf.cpu().numpy() - paf_ref.numpy()).max() <= 4e-3 * np.ptp(paf_ref.numpy())
+    assert np.abs(heat.cpu().numpy() - heat_ref.numpy()).max() <= 4e-3 * np.ptp(heat_ref.numpy())
     want = pose.parse(paf_ref.numpy(), heat_ref.numpy(), scale)
     assert [len(p) for p in out[:1]] == [len(w) for w in want]
 
