@@ -48,12 +48,11 @@ constexpr int kPThreadsDual = 224;        // 4 epilogue warps, two CTAs per SM
 constexpr int kPMaxStages = 12;
 constexpr int kPMaxPatchBufs = 8;         // patch buffers (2 normally; more for small 1x1 patches)
 constexpr uint32_t kFilterBlock = 128 * 64 * 2;      // one (tap, chunk) filter block: 16 KB
-// Epilogue staging: per team a ring of kStageSlots tiles of 16 pixels x 128 couts fp16 (4 KB),
-// so that up to kStageSlots TMA stores of a team are in flight and a chunk only waits for the
-// store issued kStageSlots chunks earlier (one slot per team = one store round trip per 16
-// pixels, ~9 us per 256-pixel tile: measured as the bound of every layer with K <= 1152).
+// Epilogue staging: per epilogue warp a ring of kStageSlots slots of 16 pixels x 32 couts fp16
+// (1 KB), so that kStageSlots TMA stores of a warp are in flight and a chunk only waits for
+// the store issued kStageSlots chunks earlier.
 constexpr int kStageSlots = 2;
-constexpr uint32_t kOutStage = 2 * kStageSlots * 4096;
+constexpr uint32_t kOutStage = 8 * kStageSlots * 1024;
 
 struct PatchParams {
   int N, H, W;                 // output == input dims (stride 1, "same" padding)
@@ -177,7 +176,8 @@ __device__ __forceinline__ bool walk_last(const PatchParams& p, const Walk& w) {
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ CUtensorMap tmO, const PatchParams p) {
+                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO32,
+                  const PatchParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // two patch buffers first
   const uint32_t ring = base + p.ring_off;
@@ -204,7 +204,10 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+    if (p.tma_store) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO32) : "memory");
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -367,8 +370,6 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int A_dim = p.axis == 0 ? p.W : p.H, B_dim = p.axis == 0 ? p.H : p.W;
     const int a_step = p.axis == 0 ? 1 : p.W;             // pixel-index step along the group axis
     const int b_step = p.axis == 0 ? p.W : 1;
-    const uint32_t team_stage = stage_out + team * (kStageSlots * 4096u);   // slots of [16 pixels][128 couts] fp16
-    const bool store_leader = (ew & 3) == 0 && lane == 0;
     unsigned chunk_ctr = 0;                               // staging slot = chunk_ctr % kStageSlots (across tiles)
     int tile_it = 0;
     Walk w = walk_begin(p);
@@ -585,47 +586,53 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 3, %0;" ::"r"(p.epi_warps * 32) : "memory");     // all epilogue warps
-        if (warp == 2 && !(p.debug & 4)) {
-          const int b = t.b0 + lane;
-          if (lane < p.R && b < B_dim) {
-            const int cw = p.axis == 0 ? t.a0 : b, ch = p.axis == 0 ? b : t.a0;
+        // every epilogue warp stores the groups ew, ew + epi_warps, ...: converged loop, one
+        // elected lane per instruction (one warp issuing all R stores from 32 divergent lanes
+        // paid the uniform-datapath waterfall R times in a row at the very end of the kernel)
+        for (int r = ew; r < p.R; r += p.epi_warps) {
+          const int b = t.b0 + r;
+          const bool ok = b < B_dim && !(p.debug & 4);        // warp-uniform
+          const int cw = p.axis == 0 ? t.a0 : b, ch = p.axis == 0 ? b : t.a0;
+          if (ok && elect_one())
             asm volatile(
                 "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                ::"l"(&tmO), "r"(base + static_cast<uint32_t>(lane) * 2048u), "r"(p.out_coff + t.ct * 128),
+                ::"l"(&tmO), "r"(base + static_cast<uint32_t>(r) * 2048u), "r"(p.out_coff + t.ct * 128),
                   "r"(cw), "r"(ch), "r"(t.n) : "memory");
-          }
+          __syncwarp();
+        }
+        if (elect_one()) {
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
+        __syncwarp();
       } else if (p.tma_store) {
-        // Two groups (16 pixels) at a time: TMEM -> registers -> [pixel][cout] tile in shared
-        // memory (a warp writes 64 contiguous bytes per pixel: conflict-free) -> one TMA store
-        // per 8-pixel group (2 KB runs in HBM; the tensor map clips the ragged border).
-        // stream-K head: the first parked partial of the NEXT 16 pixels is requested one
-        // iteration ahead, so its L2 latency hides behind the staging / store of this one
+        // WARP-LOCAL staged epilogue.  A warp owns 32 output channels (its TMEM lane quarter)
+        // of the team's pixel groups: 16 pixels at a time go TMEM -> registers -> a private
+        // [16 pixels][32 couts] fp16 slot in shared memory (a warp writes the 64 contiguous bytes
+        // of a pixel) -> two TMA stores of {32 channels x 8 pixels} (64-byte runs; the tensor map
+        // clips the ragged border).  No barrier between warps: the team-wide version (one
+        // [16][128] tile, three bar.sync per chunk) cost 8.7 us per 256-pixel tile against
+        // 2.3-4.7 us of MMA time (profiles/r02_patch_epilogue.txt; reading the slot back and
+        // storing with st.global.v4 instead of TMA measured 20-25 % slower).  The TMEM read, the
+        // residual and the first stream-K partial of the NEXT chunk are in flight while this
+        // chunk is staged; kStageSlots stores in flight per warp.
         float4 pf[4];
         auto fetch_part0 = [&](int g) {
           const float4* src = reinterpret_cast<const float4*>(part0) + (g * 128 + cl) * 2;
           pf[0] = __ldcg(src); pf[1] = __ldcg(src + 1);
           if (g + 1 < g_end) { pf[2] = __ldcg(src + 256); pf[3] = __ldcg(src + 257); }
         };
-        if (n_parts) fetch_part0(g_begin);
-        const int tid = (ew & 3) * 32 + lane;
-        for (int g = g_begin; g < g_end; g += 2, ++chunk_ctr) {
-          const uint32_t my_stage = team_stage + (chunk_ctr % kStageSlots) * 4096u;
-          uint32_t v[16];
-          uint4 rv[2];
-          if (p.res) {                       // requested first: in flight during the TMEM read and the math
+        uint4 rv[2];
+        auto fetch_res = [&](int g) {          // this warp's 16 pixels x 64 bytes of the residual tile
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int k = tid + 128 * j;
-              const __half* src = res_row_ptr(g, k >> 4);
-              rv[j] = src ? __ldg(reinterpret_cast<const uint4*>(src) + (k & 15)) : make_uint4(0, 0, 0, 0);
-            }
+          for (int j = 0; j < 2; ++j) {
+            const int k = lane + 32 * j;
+            const __half* src = res_row_ptr(g, k >> 2);
+            rv[j] = src ? __ldg(reinterpret_cast<const uint4*>(src + qd * 32) + (k & 3)) : make_uint4(0, 0, 0, 0);
           }
-          __syncwarp();
-          tmem_ld16_async(taddr + g * 8, v);
-          tmem_ld_wait();
+        };
+        const uint32_t warp_stage = stage_out + static_cast<uint32_t>(ew) * (kStageSlots * 1024u);
+        auto finish = [&](uint32_t (&v)[16], int g) {
           if (n_parts) {
             const float* f = reinterpret_cast<const float*>(pf);
 #pragma unroll
@@ -649,55 +656,96 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
           }
           float y[16];
-          float f0, m0, l0, f1, m1, l1;
-          group_shifts(g, f0, m0, l0);
-          group_shifts(g + 1, f1, m1, l1);
+          if (p.shift9) {                   // border-class shifts (kernel parameter: warp-uniform branch)
+            float f0, m0, l0, f1, m1, l1;
+            group_shifts(g, f0, m0, l0);
+            group_shifts(g + 1, f1, m1, l1);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            y[i] = fmaf(__uint_as_float(v[i]), sc,
-                        i < 8 ? pixel_shift(i, f0, m0, l0) : pixel_shift(i - 8, f1, m1, l1));
-            y[i] = fmaf(fminf(y[i], 0.f), neg, fmaxf(y[i], 0.f));
+            for (int i = 0; i < 16; ++i)
+              y[i] = fmaf(__uint_as_float(v[i]), sc,
+                          i < 8 ? pixel_shift(i, f0, m0, l0) : pixel_shift(i - 8, f1, m1, l1));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = fmaf(__uint_as_float(v[i]), sc, sh);
           }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = fmaf(fminf(y[i], 0.f), neg, fmaxf(y[i], 0.f));
+          const uint32_t slot = warp_stage + (chunk_ctr % kStageSlots) * 1024u;
+          ++chunk_ctr;
           // the store that used this slot kStageSlots chunks ago has finished READING it
-          if (store_leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStageSlots - 1) : "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
-          const uint32_t dst = my_stage + cl * 2u;
+          // (TMA / bulk-group instructions run on the uniform datapath: issued from a divergent
+          // `lane == 0` region each costs a ~200-cycle waterfall — measured 445 cycles per chunk
+          // for two stores and a commit; the warp stays converged and one elected lane issues)
+          if (elect_one()) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStageSlots - 1) : "memory");
+          __syncwarp();
           if (p.res) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              const int k = tid + 128 * j;
+              const int k = lane + 32 * j;
               asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
-                           ::"r"(my_stage + static_cast<uint32_t>(k >> 4) * 256u + (k & 15) * 16u),
+                           ::"r"(slot + static_cast<uint32_t>(k >> 2) * 64u + (k & 3) * 16u),
                              "r"(rv[j].x), "r"(rv[j].y), "r"(rv[j].z), "r"(rv[j].w) : "memory");
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
+            __syncwarp();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               unsigned short rh;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(rh) : "r"(dst + i * 256u));
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(rh) : "r"(slot + lane * 2u + i * 64u));
               y[i] += __half2float(__ushort_as_half(rh));
             }
+            __syncwarp();                                   // (the packed stores below write other lanes' cells)
+            if (g + 2 < g_end) fetch_res(g + 2);            // in flight during the next chunk's TMEM read
           }
+          // The MMAs read their operands from shared memory at ~96 of its 128 bytes per cycle
+          // (N = 256), so every staging wavefront is taken from the tensor pipe: two lanes swap
+          // halves so that each lane writes 4 bytes (two couts of one pixel) and a warp store
+          // fills a whole 128-byte wavefront (pixels i and i + 1) instead of 64 bytes.
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + i * 256u),
-                         "h"(__half_as_ushort(__float2half_rn(y[i]))) : "memory");
+          for (int i = 0; i < 16; i += 2) {
+            const __half2 h2 = __floats2half2_rn(y[i], y[i + 1]);       // lo = pixel i, hi = pixel i + 1
+            const uint32_t own = *reinterpret_cast<const uint32_t*>(&h2);
+            const uint32_t oth = __shfl_xor_sync(0xffffffffu, own, 1);
+            // even lane: pixel i, couts (lane, lane + 1);  odd lane: pixel i + 1, couts (lane - 1, lane)
+            const uint32_t val = (lane & 1) ? __byte_perm(oth, own, 0x7632) : __byte_perm(own, oth, 0x5410);
+            asm volatile("st.shared.u32 [%0], %1;"
+                         ::"r"(slot + static_cast<uint32_t>(i + (lane & 1)) * 64u + (lane & ~1) * 2u), "r"(val)
+                         : "memory");
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
-          if (store_leader && !(p.debug & 4)) {
+          __syncwarp();
 #pragma unroll
-            for (int gg = 0; gg < 2; ++gg) {
-              const int b = t.b0 + g + gg;
-              if (g + gg < g_end && b < B_dim) {
-                const int cw = p.axis == 0 ? t.a0 : b, ch = p.axis == 0 ? b : t.a0;
-                asm volatile(
-                    "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                    ::"l"(&tmO), "r"(my_stage + gg * 2048u), "r"(p.out_coff + t.ct * 128), "r"(cw),
-                      "r"(ch), "r"(t.n) : "memory");
-              }
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          for (int gg = 0; gg < 2; ++gg) {
+            const int b = t.b0 + g + gg;
+            const bool ok = g + gg < g_end && b < B_dim && !(p.debug & 4);       // warp-uniform
+            const int cw = p.axis == 0 ? t.a0 : b, ch = p.axis == 0 ? b : t.a0;
+            if (ok && elect_one())
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                  ::"l"(&tmO32), "r"(slot + gg * 512u), "r"(p.out_coff + t.ct * 128 + qd * 32), "r"(cw),
+                    "r"(ch), "r"(t.n) : "memory");
+            __syncwarp();
           }
+          if (elect_one()) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          __syncwarp();
+        };
+        if (n_parts) fetch_part0(g_begin);
+        if (p.res) fetch_res(g_begin);
+        uint32_t va[16], vb[16];
+        int g = g_begin;
+        __syncwarp();
+        tmem_ld16_async(taddr + g * 8, va);
+        while (g < g_end) {
+          __syncwarp();                       // tcgen05.ld / wait::ld are warp-collective
+          tmem_ld_wait();
+          if (g + 2 < g_end) tmem_ld16_async(taddr + (g + 2) * 8, vb);
+          finish(va, g);
+          g += 2;
+          if (g >= g_end) break;
+          __syncwarp();
+          tmem_ld_wait();
+          if (g + 2 < g_end) tmem_ld16_async(taddr + (g + 2) * 8, va);
+          finish(vb, g);
+          g += 2;
         }
       } else {
         const bool c_ok = cout < p.cout_store;
@@ -738,7 +786,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       if (warp == 2) PT_STAMP(6);                           // epilogue of a tile done
     }
-    if (p.tma_store && store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (p.tma_store && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -774,7 +823,7 @@ struct ConvPatchPlan {
   bool dual = false;
   unsigned long long* trace = nullptr;
   void* sk_own = nullptr;
-  CUtensorMap tmX, tmW, tmO;
+  CUtensorMap tmX, tmW, tmO, tmO32;     // tmO: {128 ch x 8 px} boxes (whole-tile path), tmO32: {32 ch x 8 px} (warp-local path)
   PatchParams p;
   int grid;
   uint32_t smem;
@@ -926,6 +975,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
                 a.out.cs % 8 == 0 && a.out.coff % 8 == 0 &&
                 (!a.res.ptr || (a.res.cs % 8 == 0 && a.res.coff % 8 == 0));
   plan->tmO = plan->tmW;
+  plan->tmO32 = plan->tmW;
   if (p.tma_store) {
     const cuuint64_t ocs = a.out.cs;
     cuuint64_t odim[4] = {ocs, W, H, N};
@@ -935,6 +985,11 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(output) failed: " + std::to_string(int(r)));
+    obox[0] = 32;
+    r = encode(&plan->tmO32, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.out.ptr, odim, ostr, obox, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(output, 32 channels) failed: " + std::to_string(int(r)));
   }
 
   const int slots = sms * (plan->dual ? 2 : 1);               // co-resident CTAs
@@ -1012,9 +1067,9 @@ void conv_patch_launch(const ConvPatchPlan* plan, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   if (plan->dual)
-    TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel<kPThreadsDual, 2>, plan->tmX, plan->tmW, plan->tmO, plan->p));
+    TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel<kPThreadsDual, 2>, plan->tmX, plan->tmW, plan->tmO, plan->tmO32, plan->p));
   else
-    TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel<kPThreads, 1>, plan->tmX, plan->tmW, plan->tmO, plan->p));
+    TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel<kPThreads, 1>, plan->tmX, plan->tmW, plan->tmO, plan->tmO32, plan->p));
 }
 
 }  // namespace trb

@@ -50,12 +50,15 @@ struct PreparedOp {
   View vin, vout;
 };
 
+constexpr size_t kMaxPlans = 8;      // cached (N, H, W) plans per net
+
 struct Plan {
   std::vector<Buf> bufs;
   std::vector<PreparedOp> ops;
   double tc_flops = 0;
   int tc_launches = 0, launches = 0;
   int N = 0, H = 0, W = 0;
+  unsigned long long last_use = 0;   // tr_net::use_clock of the last run (LRU eviction)
   ~Plan() {
     for (auto& o : ops) {
       if (o.tc) conv_tc_plan_destroy(o.tc);
@@ -91,6 +94,7 @@ struct tr_net {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::map<std::tuple<int, int, int, int>, std::unique_ptr<Plan>> plans;
+  unsigned long long use_clock = 0;
   Plan* last = nullptr;
   ~tr_net() {
     plans.clear();
@@ -402,7 +406,18 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
     plan->ops.push_back(po);
   }
   Plan* raw = plan.get();
-  if (net->plans.size() >= 4) net->plans.clear();   // bounded cache
+  // Bounded cache, least-recently-used eviction ONE plan at a time (lists of differently sized
+  // images produce a new shape per call: clearing everything would re-allocate every buffer
+  // of every cached shape).  The plan that ran last (net->last) is never the victim.
+  raw->last_use = ++net->use_clock;
+  while (net->plans.size() >= kMaxPlans) {
+    auto victim = net->plans.end();
+    for (auto it = net->plans.begin(); it != net->plans.end(); ++it)
+      if (it->second.get() != net->last && (victim == net->plans.end() || it->second->last_use < victim->second->last_use))
+        victim = it;
+    if (victim == net->plans.end()) break;
+    net->plans.erase(victim);
+  }
   net->plans[std::make_tuple(N, H, W, net->force_direct)] = std::move(plan);
   return raw;
 }
@@ -562,6 +577,7 @@ int tr_net_run(tr_net* net, const uint8_t* image_dev, int N, int H, int W, int64
     TR_CHECK(N > 0 && H > 0 && W > 0, "empty batch");
     auto it = net->plans.find(std::make_tuple(N, H, W, net->force_direct));
     Plan* plan = it != net->plans.end() ? it->second.get() : build_plan(net, N, H, W);
+    plan->last_use = ++net->use_clock;
     net->last = plan;
     run_plan(net, plan, image_dev, stride_n, stride_h, stride_w, stride_c,
              static_cast<cudaStream_t>(stream), net->profile != 0);

@@ -521,8 +521,8 @@ void build_openpose(const StateDict& sd, Program& P) {
     // Both branches have the same layer shapes up to their last layer.  Layer 0 reads the same
     // tensor in both (one conv, filter banks stacked); every further layer but the last is ONE
     // grouped conv (groups = 2) over a [branch 1 | branch 2] channel pair — half the launches,
-    // and twice the tiles per launch to spread over the SMs.  Only the last layers (38 / 19
-    // filters, written into the concat buffer) run per branch, branch 2 on the side stream.
+    // and twice the tiles per launch to spread over the SMs.  The last layers (38 / 19 filters,
+    // written into the concat buffer) are one conv over the pair as well (below).
     auto stacked = [&](size_t li, Vec& w, Vec& bias) {
       const StageLayer &l1 = specs[0][li], &l2 = specs[1][li];
       const Tensor &w1 = sd.at(m[0] + l1.name + ".weight"), &w2 = sd.at(m[1] + l2.name + ".weight");
@@ -542,24 +542,44 @@ void build_openpose(const StateDict& sd, Program& P) {
       stacked(li, w, bias);
       ConvOpts o; o.act = TR_ACT_RELU;
       if (li == 0) {
-        if (stage > 1) o.sync = TR_SYNC_JOIN;
         if (stage == 1) o.in_coff = 64;
         else { o.in_map = &cat_map; o.cin_pad = 192; }
       } else {
         o.groups = 2;
       }
-      if (li + 2 == n_layers) o.sync |= TR_SYNC_FORK;
       const int y = 2 * l.cout != 256 ? B.buffer(2 * l.cout) : tmp[li & 1];
       B.conv(w.data(), 2 * l.cout, l.cin, l.k, ones(2 * l.cout), bias, li == 0 ? src : xb, y, o);
       xb = y; ch = l.cout;
     }
-    for (int branch = 1; branch <= 2; ++branch) {
-      const StageLayer& l = specs[branch - 1][n_layers - 1];
-      const Tensor& wl = sd.at(m[branch - 1] + l.name + ".weight");
-      const Vec bl = to_vec(sd.at(m[branch - 1] + l.name + ".bias"));
-      ConvOpts o; o.in_coff = (branch - 1) * ch; o.act = l.relu ? TR_ACT_RELU : TR_ACT_NONE;
-      o.lane = branch - 1; o.out_coff = branch == 1 ? 0 : 40;
-      B.conv(wl.f, l.cout, l.cin, l.k, ones(l.cout), bl, xb, dst, o);
+    {
+      // Last layers (1x1, 38 PAF / 19 heat-map filters): ONE conv over the [branch 1 | branch 2]
+      // pair whose 64 output rows are the concat buffer's channels 0..63 — rows 0..37 carry the
+      // PAF filters on the first `ch` input channels, rows 40..58 the heat-map filters on the
+      // second `ch`, everything else is zero (the pad channels 38, 39, 59..63 are written as 0,
+      // which is what they hold anyway).  Adding exact zeros changes no fp32 sum, so the result
+      // is bit-identical to two per-branch launches; one launch instead of two per stage.
+      const StageLayer &l1 = specs[0][n_layers - 1], &l2 = specs[1][n_layers - 1];
+      const Tensor &w1 = sd.at(m[0] + l1.name + ".weight"), &w2 = sd.at(m[1] + l2.name + ".weight");
+      const Vec b1 = to_vec(sd.at(m[0] + l1.name + ".bias")), b2 = to_vec(sd.at(m[1] + l2.name + ".bias"));
+      const int cin2 = 2 * ch;
+      Vec wm(size_t(64) * cin2, 0.f), bm(64, 0.f), slope(64, 1.f);
+      for (int oc = 0; oc < l1.cout; ++oc) {
+        for (int c = 0; c < ch; ++c) wm[size_t(oc) * cin2 + c] = w1.f[size_t(oc) * ch + c];
+        bm[oc] = b1[oc];
+        if (l1.relu) slope[oc] = 0.f;
+      }
+      for (int oc = 0; oc < l2.cout; ++oc) {
+        for (int c = 0; c < ch; ++c) wm[size_t(40 + oc) * cin2 + ch + c] = w2.f[size_t(oc) * ch + c];
+        bm[40 + oc] = b2[oc];
+        if (l2.relu) slope[40 + oc] = 0.f;
+      }
+      // a ReLU on one branch only (the reference keeps it on Mconv7_stage6_L2) is a per-channel
+      // PReLU with slope 0 (ReLU) or 1 (identity): max(y, 0) + slope * min(y, 0), exact
+      ConvOpts o;
+      if (l1.relu || l2.relu) { o.act = TR_ACT_PRELU; o.slope = &slope; }
+      B.conv(wm.data(), 64, cin2, 1, ones(64), bm, xb, dst, o);
+      P.ops.back().cin_real = ch;                       // algorithmic work: (38 + 19) x ch MACs per pixel
+      P.ops.back().cout_real = l1.cout + l2.cout;
     }
   }
   P.roles[0] = cat[(6 + 1) % 2]; P.roles[1] = 0; P.roles[2] = 40;

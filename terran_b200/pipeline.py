@@ -71,8 +71,15 @@ class FrameFeeder:
                 return
             dev, done = item
             # consumers on any stream must see the finished copy
-            torch.cuda.current_stream(self.device_index).wait_event(done)
+            cur = torch.cuda.current_stream(self.device_index)
+            cur.wait_event(done)
             done.synchronize()
+            # The batch was allocated on the feeder's private copy stream: tell the caching
+            # allocator that the consumer's stream uses it too, so that dropping the tensor while
+            # kernels are still queued there cannot hand the block to the next upload.  (A consumer
+            # that moves the work to yet another stream must call ``record_stream`` itself, as
+            # ``PerceptionPipeline.submit`` does.)
+            dev.record_stream(cur)
             yield dev
 
     def close(self):

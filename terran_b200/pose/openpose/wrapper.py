@@ -47,11 +47,16 @@ def unpack_poses(count, kps, score, status):
     """Device or (pinned) host tensors -> the reference's list of lists of dicts."""
     count, status = count.cpu().numpy().copy(), status.cpu().numpy().copy()
     if status.any():
-        bad = int(np.flatnonzero(status)[0])
-        raise nat.NativeError(
-            f'pose parse capacity exceeded on frame {bad} (status {int(status[bad])}: '
-            f'1 = more than {nat.TR_PEAK_CAP} peaks of one part, 2 = more than '
-            f'{nat.TR_CAND_CAP} limb candidates, 4 = more than {nat.TR_HUMAN_CAP} humans)')
+        # The reference has no capacity limits and returns something for every frame: one
+        # crowded / noisy frame must not fail the batch.  The kernels clamp at their capacities
+        # (never write out of bounds), so the frame's result is TRUNCATED, and we say so.
+        import warnings
+        bad = np.flatnonzero(status)
+        warnings.warn(
+            f'pose parse capacity exceeded on frame(s) {bad.tolist()} (status '
+            f'{[int(status[b]) for b in bad]}: 1 = more than {nat.TR_PEAK_CAP} peaks of one part, '
+            f'2 = more than {nat.TR_CAND_CAP} limb candidates, 4 = more than {nat.TR_HUMAN_CAP} '
+            f'humans): results of these frames are truncated', RuntimeWarning, stacklevel=2)
     top = int(count.max()) if len(count) else 0
     kps = kps[:, :max(top, 1)].cpu().numpy().copy()
     score = score[:, :max(top, 1)].cpu().numpy().copy()

@@ -274,21 +274,32 @@ def openpose_program(sd):
             kw = {}
             sync = 0
             if li == 0:
-                sync = nat.TR_SYNC_JOIN if stage > 1 else 0
                 kw = dict(in_coff=64) if stage == 1 else dict(in_map=OPENPOSE_CAT_MAP, cin_pad=192)
             else:
                 kw = dict(groups=2)
-            if li + 2 == n_layers:
-                sync |= nat.TR_SYNC_FORK
             y = P.buffer(c1 + c2) if c1 + c2 != 256 else tmp[li & 1]
             P.conv(w, one(c1 + c2), b.float().numpy(), src if li == 0 else xb, y, act=relu, sync=sync, **kw)
             xb, ch = y, c1
-        for branch in (1, 2):
-            name, cin, cout, k, has_relu = specs[branch][-1]
-            pfx = f'model{stage}_{branch}.{name}'
-            w, b = sd[pfx + '.weight'], sd[pfx + '.bias'].float().numpy()
-            P.conv(w, one(cout), b, xb, dst, in_coff=(branch - 1) * ch, out_coff=0 if branch == 1 else 40,
-                   act=relu if has_relu else nat.TR_ACT_NONE, lane=branch - 1)
+        # last layers: one 1x1 conv over the pair, output rows = concat channels 0..63
+        # (rows 0..37 PAF filters on the first ch inputs, rows 40..58 heat filters on the second)
+        (n1, _, c1, _, relu1), (n2, _, c2, _, relu2) = specs[1][-1], specs[2][-1]
+        w1, w2 = sd[f'model{stage}_1.{n1}.weight'].float(), sd[f'model{stage}_2.{n2}.weight'].float()
+        wm = torch.zeros((64, 2 * ch, 1, 1))
+        wm[:c1, :ch] = w1
+        wm[40:40 + c2, ch:] = w2
+        bm = np.zeros(64, np.float32)
+        bm[:c1] = sd[f'model{stage}_1.{n1}.bias'].float().numpy()
+        bm[40:40 + c2] = sd[f'model{stage}_2.{n2}.bias'].float().numpy()
+        kw = {}
+        if relu1 or relu2:
+            slope = np.ones(64, np.float32)
+            if relu1:
+                slope[:c1] = 0
+            if relu2:
+                slope[40:40 + c2] = 0
+            kw = dict(act=nat.TR_ACT_PRELU, slope=slope)
+        P.conv(wm, one(64), bm, xb, dst, **kw)
+        P.ops[-1].cin_real, P.ops[-1].cout_real = ch, c1 + c2
     return P, {'maps': cat[(6 + 1) % 2], 'paf_coff': 0, 'heat_coff': 40}
 
 

@@ -161,6 +161,27 @@ def test_pose_parse_edge_cases(native):
     assert len(got[2]) == len(pose.parse_frame(paf, heat, 0.25))
 
 
+def test_pose_parse_capacity_overflow_truncates_one_frame(native):
+    """More peaks than the per-part capacity on ONE frame: a RuntimeWarning, a truncated
+    result for that frame, and the other frame of the batch exactly as if parsed alone (the
+    reference has no capacities and never fails a batch: wrapper.py:226-483)."""
+    from terran_b200 import _native as nat
+    h, w = 46, 80
+    paf, heat = pose.synthetic_scene(7, h=h, w=w, people=3)
+    crowded = np.zeros_like(heat)
+    yy, xx = np.mgrid[0:h, 0:w]
+    crowded[0] = ((yy + xx) % 2 == 0).astype(np.float32)          # ~1800 isolated maxima of part 0
+    assert crowded[0].sum() > nat.TR_PEAK_CAP
+    scale = 8 * h / 720
+    alone = native_parse([paf], [heat], scale)[0]
+    with pytest.warns(RuntimeWarning, match='capacity exceeded on frame'):
+        got = native_parse([np.zeros_like(paf), paf], [crowded, heat], scale)
+    assert len(got) == 2 and len(got[1]) == len(alone) > 0
+    for a, b in zip(got[1], alone):
+        np.testing.assert_array_equal(a['keypoints'], b['keypoints'])
+        assert a['score'] == b['score']
+
+
 def test_pose_peaks_full_size(native):
     """BASELINE size (16 frames of 23x40 maps): every reported keypoint is a
     4-neighbour local maximum >= 0.1 of the up-sampled heat map."""

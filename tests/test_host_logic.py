@@ -212,9 +212,10 @@ def test_programs_cover_every_checkpoint_tensor():
     assert len(rf['heads']) == 3
     P, _ = weights.openpose_program(synth.openpose_state_dict())
     kinds = [op.type for op in P.ops]
-    # 92 convs; in every stage all layers of the two branches but the last are ONE op each (the
-    # first reads a shared input with the filter banks stacked, the others are groups = 2 convs)
-    assert kinds.count(nat.TR_OP_CONV) + kinds.count(nat.TR_OP_STEM) == 92 - 4 - 5 * 6
+    # 92 convs; in every stage the layers of the two branches are ONE op each (the first reads a
+    # shared input with the filter banks stacked, the middle ones are groups = 2 convs, the last
+    # is one conv over the pair whose rows are the concat channels): 12 trunk + 5 + 5 * 7 launches
+    assert kinds.count(nat.TR_OP_CONV) + kinds.count(nat.TR_OP_STEM) == 92 - 5 - 6 * 5 - 5
     assert sum(op.groups == 2 for op in P.ops) == 3 + 5 * 5
     assert kinds.count(nat.TR_OP_MAXPOOL) == 3
     small = (1, 1, 1, 1)
