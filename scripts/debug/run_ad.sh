@@ -1,0 +1,4 @@
+# session AD: unified whole-tile epilogue (pipelined TMEM reads, packed stores)
+timeout 900 python -m pytest tests/test_gpu_conv_patch.py tests/test_gpu_nets.py tests/test_gpu_baseline_sizes.py tests/test_gpu_capi.py -m gpu -q -x 2>&1 | grep -E "^E  |passed|failed" | head -12 | cut -c1-300
+python scripts/bench_patch.py trace 2>&1 | grep -E "launch  [5-8]|trace"
+python scripts/profile_ops.py openpose arcface --brief 2>&1 | grep -E "^==|tcgen05" | cut -c1-150

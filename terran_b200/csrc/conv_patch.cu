@@ -502,110 +502,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
         }
       };
-      if (p.tma_store && walk_last(p, w)) {
-        // The CTA's LAST segment: nothing overlaps this epilogue, and every MMA of the CTA has
-        // retired, so both patch buffers are free — stage the whole [pixel][cout] tile there
-        // (no per-chunk store/barrier round trips), then issue all TMA stores at once.  The
-        // parked stream-K partials are requested two chunks (32 pixels) ahead.
-        float4 pfA[4], pfB[4];
-        auto fetch = [&](float4 (&pf)[4], int g) {
-          const float4* src = reinterpret_cast<const float4*>(part0) + (g * 128 + cl) * 2;
-          pf[0] = __ldcg(src); pf[1] = __ldcg(src + 1);
-          if (g + 1 < g_end) { pf[2] = __ldcg(src + 256); pf[3] = __ldcg(src + 257); }
-        };
-        auto chunk = [&](int g, const float4 (&pf)[4]) {
-          uint32_t v[16];
-          __syncwarp();
-          tmem_ld16_async(taddr + g * 8, v);
-          tmem_ld_wait();
-          if (n_parts) {
-            const float* f = reinterpret_cast<const float*>(pf);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + f[j]);
-            for (int k = 1; k < n_parts; ++k) {
-              const float* pk = part0 + static_cast<size_t>(k) * 128 * p.NP;
-              for (int gg = 0; gg < 2 && g + gg < g_end; ++gg) {
-                const float4* src = reinterpret_cast<const float4*>(pk) + ((g + gg) * 128 + cl) * 2;
-                const float4 f0 = __ldcg(src), f1 = __ldcg(src + 1);
-                uint32_t* u = v + 8 * gg;
-                u[0] = __float_as_uint(__uint_as_float(u[0]) + f0.x);
-                u[1] = __float_as_uint(__uint_as_float(u[1]) + f0.y);
-                u[2] = __float_as_uint(__uint_as_float(u[2]) + f0.z);
-                u[3] = __float_as_uint(__uint_as_float(u[3]) + f0.w);
-                u[4] = __float_as_uint(__uint_as_float(u[4]) + f1.x);
-                u[5] = __float_as_uint(__uint_as_float(u[5]) + f1.y);
-                u[6] = __float_as_uint(__uint_as_float(u[6]) + f1.z);
-                u[7] = __float_as_uint(__uint_as_float(u[7]) + f1.w);
-              }
-            }
-          }
-          const uint32_t dst = base + static_cast<uint32_t>(g) * 2048u + cl * 2u;
-          const int npx = g + 1 < g_end ? 16 : 8;           // the second group may be the other team's
-          float f0, m0, l0, f1, m1, l1;
-          group_shifts(g, f0, m0, l0);
-          group_shifts(g + 1, f1, m1, l1);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (i >= npx) break;
-            const float shi = i < 8 ? pixel_shift(i, f0, m0, l0) : pixel_shift(i - 8, f1, m1, l1);
-            float y = fmaf(__uint_as_float(v[i]), sc, shi);
-            y = fmaf(fminf(y, 0.f), neg, fmaxf(y, 0.f));
-            if (p.res) {
-              unsigned short rh;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(rh) : "r"(dst + i * 256u));
-              y += __half2float(__ushort_as_half(rh));
-            }
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + i * 256u),
-                         "h"(__half_as_ushort(__float2half_rn(y))) : "memory");
-          }
-        };
-        if (n_parts) {
-          fetch(pfA, g_begin);
-          if (g_begin + 2 < g_end) fetch(pfB, g_begin + 2);
-        }
-        if (p.res) {
-          // this team's rows of the residual tile -> staging (16 lanes per 256-byte pixel row)
-          const int tid = (ew & 3) * 32 + lane;
-          for (int k = tid; k < (g_end - g_begin) * 8 * 16; k += 128) {
-            const int r = k >> 4, c16 = k & 15;
-            const __half* src = res_row_ptr(g_begin, r);
-            const uint4 rv = src ? __ldg(reinterpret_cast<const uint4*>(src) + c16) : make_uint4(0, 0, 0, 0);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
-                         ::"r"(base + static_cast<uint32_t>(g_begin * 8 + r) * 256u + c16 * 16u),
-                           "r"(rv.x), "r"(rv.y), "r"(rv.z), "r"(rv.w) : "memory");
-          }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
-        }
-        for (int g = g_begin; g < g_end; g += 4) {
-          chunk(g, pfA);
-          if (n_parts && g + 4 < g_end) fetch(pfA, g + 4);
-          if (g + 2 < g_end) {
-            chunk(g + 2, pfB);
-            if (n_parts && g + 6 < g_end) fetch(pfB, g + 6);
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 3, %0;" ::"r"(p.epi_warps * 32) : "memory");     // all epilogue warps
-        // every epilogue warp stores the groups ew, ew + epi_warps, ...: converged loop, one
-        // elected lane per instruction (one warp issuing all R stores from 32 divergent lanes
-        // paid the uniform-datapath waterfall R times in a row at the very end of the kernel)
-        for (int r = ew; r < p.R; r += p.epi_warps) {
-          const int b = t.b0 + r;
-          const bool ok = b < B_dim && !(p.debug & 4);        // warp-uniform
-          const int cw = p.axis == 0 ? t.a0 : b, ch = p.axis == 0 ? b : t.a0;
-          if (ok && elect_one())
-            asm volatile(
-                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                ::"l"(&tmO), "r"(base + static_cast<uint32_t>(r) * 2048u), "r"(p.out_coff + t.ct * 128),
-                  "r"(cw), "r"(ch), "r"(t.n) : "memory");
-          __syncwarp();
-        }
-        if (elect_one()) {
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        }
-        __syncwarp();
-      } else if (p.tma_store) {
+      if (p.tma_store) {
         // WARP-LOCAL staged epilogue.  A warp owns 32 output channels (its TMEM lane quarter)
         // of the team's pixel groups: 16 pixels at a time go TMEM -> registers -> a private
         // [16 pixels][32 couts] fp16 slot in shared memory (a warp writes the 64 contiguous bytes
@@ -616,6 +513,11 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         // storing with st.global.v4 instead of TMA measured 20-25 % slower).  The TMEM read, the
         // residual and the first stream-K partial of the NEXT chunk are in flight while this
         // chunk is staged; kStageSlots stores in flight per warp.
+        // The CTA's LAST segment (`whole`): nothing overlaps this epilogue and every MMA of the
+        // CTA has retired, so the patch buffers are free — the same per-warp code stages the
+        // whole [pixel][128 couts] tile there (no per-chunk store, fence or slot wait), then all
+        // epilogue warps meet once and issue the tile's TMA stores.
+        const bool whole = walk_last(p, w);
         float4 pf[4];
         auto fetch_part0 = [&](int g) {
           const float4* src = reinterpret_cast<const float4*>(part0) + (g * 128 + cl) * 2;
@@ -670,27 +572,38 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) y[i] = fmaf(fminf(y[i], 0.f), neg, fmaxf(y[i], 0.f));
-          const uint32_t slot = warp_stage + (chunk_ctr % kStageSlots) * 1024u;
-          ++chunk_ctr;
-          // the store that used this slot kStageSlots chunks ago has finished READING it
-          // (TMA / bulk-group instructions run on the uniform datapath: issued from a divergent
-          // `lane == 0` region each costs a ~200-cycle waterfall — measured 445 cycles per chunk
-          // for two stores and a commit; the warp stays converged and one elected lane issues)
-          if (elect_one()) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStageSlots - 1) : "memory");
-          __syncwarp();
+          // 16 pixel rows of `pitch` bytes: a private slot, or this warp's 64-byte column of the
+          // whole-tile staging area
+          const uint32_t slot = whole ? base + static_cast<uint32_t>(g) * 2048u + qd * 64u
+                                      : warp_stage + (chunk_ctr % kStageSlots) * 1024u;
+          const uint32_t pitch = whole ? 256u : 64u;
+          // an odd number of groups per team: the second group of the last chunk is the OTHER
+          // team's first one — its rows must not be written in the shared whole-tile area
+          const int nrow = g + 1 < g_end ? 16 : 8;
+          if (!whole) {
+            ++chunk_ctr;
+            // the store that used this slot kStageSlots chunks ago has finished READING it
+            // (TMA / bulk-group instructions run on the uniform datapath: issued from a divergent
+            // `lane == 0` region each costs a ~200-cycle waterfall — measured 445 cycles per chunk
+            // for two stores and a commit; the warp stays converged and one elected lane issues)
+            if (elect_one()) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStageSlots - 1) : "memory");
+            __syncwarp();
+          }
           if (p.res) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const int k = lane + 32 * j;
-              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
-                           ::"r"(slot + static_cast<uint32_t>(k >> 2) * 64u + (k & 3) * 16u),
-                             "r"(rv[j].x), "r"(rv[j].y), "r"(rv[j].z), "r"(rv[j].w) : "memory");
+              if ((k >> 2) < nrow)
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+                             ::"r"(slot + static_cast<uint32_t>(k >> 2) * pitch + (k & 3) * 16u),
+                               "r"(rv[j].x), "r"(rv[j].y), "r"(rv[j].z), "r"(rv[j].w) : "memory");
             }
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
+              if (i >= nrow) break;
               unsigned short rh;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(rh) : "r"(slot + lane * 2u + i * 64u));
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(rh) : "r"(slot + lane * 2u + i * pitch));
               y[i] += __half2float(__ushort_as_half(rh));
             }
             __syncwarp();                                   // (the packed stores below write other lanes' cells)
@@ -707,10 +620,12 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t oth = __shfl_xor_sync(0xffffffffu, own, 1);
             // even lane: pixel i, couts (lane, lane + 1);  odd lane: pixel i + 1, couts (lane - 1, lane)
             const uint32_t val = (lane & 1) ? __byte_perm(oth, own, 0x7632) : __byte_perm(own, oth, 0x5410);
-            asm volatile("st.shared.u32 [%0], %1;"
-                         ::"r"(slot + static_cast<uint32_t>(i + (lane & 1)) * 64u + (lane & ~1) * 2u), "r"(val)
+            if (i < nrow)
+              asm volatile("st.shared.u32 [%0], %1;"
+                         ::"r"(slot + static_cast<uint32_t>(i + (lane & 1)) * pitch + (lane & ~1) * 2u), "r"(val)
                          : "memory");
           }
+          if (whole) return;
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
 #pragma unroll
@@ -746,6 +661,28 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           if (g + 2 < g_end) tmem_ld16_async(taddr + (g + 2) * 8, va);
           finish(vb, g);
           g += 2;
+        }
+        if (whole) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 3, %0;" ::"r"(p.epi_warps * 32) : "memory");     // all epilogue warps
+          // every epilogue warp stores the groups ew, ew + epi_warps, ...: converged loop, one
+          // elected lane per instruction
+          for (int r = ew; r < p.R; r += p.epi_warps) {
+            const int b = t.b0 + r;
+            const bool ok = b < B_dim && !(p.debug & 4);        // warp-uniform
+            const int cw = p.axis == 0 ? t.a0 : b, ch = p.axis == 0 ? b : t.a0;
+            if (ok && elect_one())
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                  ::"l"(&tmO), "r"(base + static_cast<uint32_t>(r) * 2048u), "r"(p.out_coff + t.ct * 128),
+                    "r"(cw), "r"(ch), "r"(t.n) : "memory");
+            __syncwarp();
+          }
+          if (elect_one()) {
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          }
+          __syncwarp();
         }
       } else {
         const bool c_ok = cout < p.cout_store;
