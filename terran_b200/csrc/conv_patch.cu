@@ -570,8 +570,15 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 16; ++i) y[i] = fmaf(__uint_as_float(v[i]), sc, sh);
           }
+          // (the epilogue is instruction-issue bound — two epilogue warps per scheduler — so the
+          // common activations take their short forms)
+          if (p.act == ACT_RELU) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = fmaf(fminf(y[i], 0.f), neg, fmaxf(y[i], 0.f));
+            for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+          } else if (p.act == ACT_PRELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = fmaf(fminf(y[i], 0.f), neg, fmaxf(y[i], 0.f));
+          }
           // 16 pixel rows of `pitch` bytes: a private slot, or this warp's 64-byte column of the
           // whole-tile staging area
           const uint32_t slot = whole ? base + static_cast<uint32_t>(g) * 2048u + qd * 64u
@@ -613,17 +620,22 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           // (N = 256), so every staging wavefront is taken from the tensor pipe: two lanes swap
           // halves so that each lane writes 4 bytes (two couts of one pixel) and a warp store
           // fills a whole 128-byte wavefront (pixels i and i + 1) instead of 64 bytes.
+          {
+            // even lane: pixel i, couts (lane, lane + 1) = (lo(own), lo(oth));
+            // odd lane: pixel i + 1, couts (lane - 1, lane) = (hi(oth), hi(own))
+            const uint32_t sel = (lane & 1) ? 0x3276u : 0x5410u;
+            const uint32_t dst0 = slot + (lane & 1) * pitch + (lane & ~1) * 2u;
+            const bool second = nrow == 16;
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const __half2 h2 = __floats2half2_rn(y[i], y[i + 1]);       // lo = pixel i, hi = pixel i + 1
-            const uint32_t own = *reinterpret_cast<const uint32_t*>(&h2);
-            const uint32_t oth = __shfl_xor_sync(0xffffffffu, own, 1);
-            // even lane: pixel i, couts (lane, lane + 1);  odd lane: pixel i + 1, couts (lane - 1, lane)
-            const uint32_t val = (lane & 1) ? __byte_perm(oth, own, 0x7632) : __byte_perm(own, oth, 0x5410);
-            if (i < nrow)
-              asm volatile("st.shared.u32 [%0], %1;"
-                         ::"r"(slot + static_cast<uint32_t>(i + (lane & 1)) * pitch + (lane & ~1) * 2u), "r"(val)
-                         : "memory");
+            for (int i = 0; i < 16; i += 2) {
+              const __half2 h2 = __floats2half2_rn(y[i], y[i + 1]);     // lo = pixel i, hi = pixel i + 1
+              const uint32_t own = *reinterpret_cast<const uint32_t*>(&h2);
+              const uint32_t oth = __shfl_xor_sync(0xffffffffu, own, 1);
+              const uint32_t val = __byte_perm(own, oth, sel);
+              if (i < 8 || second)
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst0 + static_cast<uint32_t>(i) * pitch), "r"(val)
+                             : "memory");
+            }
           }
           if (whole) return;
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
