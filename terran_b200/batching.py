@@ -60,6 +60,20 @@ class PadMerge:
             batch[i, top[i]:top[i] + hs[i], left[i]:left[i] + ws[i]] = im
         return batch, np.stack([left, top], axis=1)
 
+    def merge_device(self, images):
+        """``merge`` for a list of CUDA uint8 (h,w,3) tensors (already resized on the device):
+        the same centred zero padding, built in device memory — no host copy of the pixels."""
+        self._check()
+        hs = np.array([int(im.shape[0]) for im in images])
+        ws = np.array([int(im.shape[1]) for im in images])
+        H, W = int(hs.max()), int(ws.max())
+        top = -((hs - H) // 2)
+        left = -((ws - W) // 2)
+        batch = torch.zeros((len(images), H, W, 3), dtype=torch.uint8, device=images[0].device)
+        for i, im in enumerate(images):
+            batch[i, top[i]:top[i] + hs[i], left[i]:left[i] + ws[i]] = im
+        return batch, np.stack([left, top], axis=1)
+
     def unpad_faces(self, faces_per_image, offsets):
         if offsets is None:
             return faces_per_image

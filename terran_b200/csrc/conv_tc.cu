@@ -553,6 +553,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // (Issuing from inside an `if (lane == 0)` region makes the compiler wrap each
   // uniform-datapath instruction in a divergence "waterfall" loop — measured at
   // ~240 cycles per tcgen05.mma, 4x the MMA's own execution time.)
+  // Resident-filter mode: one MMA-issuing warp per tile parity (warp 1: even tiles into
+  // accumulator 0, warp 10: odd tiles into accumulator 1 when p.resident == 2).  The two never
+  // touch the same barrier phase: a tile's accumulator, patch buffer and commits belong to the
+  // warp that issues it, so the barrier protocol is the single-issuer one split by parity.  An
+  // N = 64 MMA is 32 cycles of tensor work but costs its issuing thread ~75: two threads keep
+  // the pipe fed.
+  auto resident_issuer = [&](int first) {
+    const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
+    const uint32_t halo_hi = umma_desc_hi(2048, p.layout_type);
+    const uint32_t a_lo0 = umma_desc_lo(ring);
+    const int step = p.resident;                            // 1 or 2 issuers
+    TileWalk walk = walk_begin(p);
+    int tile, it0, it1;
+    mbar_wait(full_bar(0), 0, p.err, 3);                    // the filter bank has landed
+    for (int tile_it = 0; walk_next(p, walk, tile, it0, it1); ++tile_it) {
+      if (step == 2 && (tile_it & 1) != first) continue;
+      const int acc = tile_it & 1;
+      mbar_wait(tempty_bar(acc), ((tile_it >> 1) & 1u) ^ 1u, p.err, 2);
+      const int buf = tile_it % p.npatch;
+      mbar_wait(full_bar(1 + buf), (tile_it / p.npatch) & 1u, p.err, 6);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * p.acc_cols;
+        const uint32_t patch_lo = umma_desc_lo(base + buf * p.patch_bytes);
+        uint32_t accumulate = 0;
+        if (!(p.debug & 2)) {
+          for (int t = 0; t < p.taps; ++t) {
+            uint32_t tap_off;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tap_off) : "r"(tab_s + 4u * t));
+            const uint32_t a_lo = patch_lo + tap_off;
+            const uint32_t b_lo = a_lo0 + t * (p.b_bytes >> 4);
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+              umma_f16(d_tmem, a_lo + 2 * k, halo_hi, b_lo + 2 * k, desc_hi, p.idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+        }
+        umma_commit(empty_bar(1 + buf));
+        umma_commit(tfull_bar(acc));
+      }
+      __syncwarp();
+    }
+  };
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0, pb = 0;
@@ -702,7 +746,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.halo) mma_issuer_alternate_halo<KSTEPS>(p, 1, base, ring, tmem_base, bars, tab_s, prog);
     else mma_issuer_alternate<KSTEPS>(p, 1, ring, tmem_base, bars, prog);
   } else if (warp == 10) {
-    // single-issuer launch: nothing to do
+    // single-issuer launch: nothing to do — except the odd tiles of resident-filter mode
+    if (p.resident == 2) resident_issuer(1);
   } else if (warp == 1 && p.issuers == 2) {
     if (p.halo) mma_issuer_alternate_halo<KSTEPS>(p, 0, base, ring, tmem_base, bars, tab_s, prog);
     else mma_issuer_alternate<KSTEPS>(p, 0, ring, tmem_base, bars, prog);
@@ -720,37 +765,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int tile, it0, it1;
     long long dbg_wf = 0, dbg_te = 0, dbg_pw = 0, dbg_last = 0, dbg_t0 = clock64(), dbg_issue = 0, dbg_commit = 0;
     int dbg_n = 0;
-    if (p.resident) {
-      mbar_wait(full_bar(0), 0, p.err, 3);                  // the filter bank has landed
-      for (; walk_next(p, walk, tile, it0, it1); ++tile_it) {
-        const int acc = tile_it & 1;
-        mbar_wait(tempty_bar(acc), ((tile_it >> 1) & 1u) ^ 1u, p.err, 2);
-        const int buf = tile_it % p.npatch;
-        mbar_wait(full_bar(1 + buf), (tile_it / p.npatch) & 1u, p.err, 6);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + acc * p.acc_cols;
-          const uint32_t patch_lo = umma_desc_lo(base + buf * p.patch_bytes);
-          uint32_t accumulate = 0;
-          if (!(p.debug & 2)) {
-            for (int t = 0; t < p.taps; ++t) {
-              uint32_t tap_off;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tap_off) : "r"(tab_s + 4u * t));
-              const uint32_t a_lo = patch_lo + tap_off;
-              const uint32_t b_lo = a_lo0 + t * (p.b_bytes >> 4);
-#pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                umma_f16(d_tmem, a_lo + 2 * k, halo_hi, b_lo + 2 * k, desc_hi, p.idesc, accumulate);
-                accumulate = 1;
-              }
-            }
-          }
-          umma_commit(empty_bar(1 + buf));
-          umma_commit(tfull_bar(acc));
-        }
-        __syncwarp();
-      }
-    }
+    if (p.resident) resident_issuer(0);
     for (; !p.resident && walk_next(p, walk, tile, it0, it1); ++tile_it) {
       const int acc = tile_it & 1;
       const uint32_t acc_phase = (tile_it >> 1) & 1u;
@@ -1604,14 +1619,14 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     p.patch_bytes = round_up(p.patch_tx, 1024);
     p.ring_off = 2 * p.patch_bytes;
     // Resident filters (see TcParams::resident): whole filter bank + >= 3 patch buffers in 227 KB.
-    int want = 1;
+    int want = 2;
     if (const char* e = getenv("TRB_TC_RESIDENT")) want = atoi(e);
     const uint32_t bank = uint32_t(p.taps) * p.b_bytes;
     const uint32_t room = 227u * 1024 - 1024 /*alignment*/ - 256 - 8 * (2 * kMaxStages + 12) - 16 - param_bytes;
     const int npatch = bank < room ? std::min<int>(kMaxStages - 1, std::min<int>(4, (room - bank) / p.patch_bytes)) : 0;
     if (want && !p.swap && !p.cta2 && p.kchunks == 1 && p.n_tiles == 1 && plan->ctas_per_sm == 1 &&
         p.taps <= 64 && npatch >= 3) {
-      p.resident = 1;
+      p.resident = want >= 2 ? 2 : 1;      // TRB_TC_RESIDENT: 0 off, 1 one issuer, 2 (default) two
       p.npatch = npatch;
       p.issuers = 1;
       p.sub = p.taps;                      // the "ring" is one stage that holds every tap

@@ -262,7 +262,9 @@ void build_retinaface(const StateDict& sd, bool fused, Program& P) {
     const int cout = int(w.dims[0]), cin = int(w.dims[1]), k = int(w.dims[2]);
     o.act = TR_ACT_RELU;
     // the warp-level kernel wins where either channel count is <= 16 (profiles/r01_retinaface_mma.txt)
-    o.engine = std::min(cout, cin) <= 16 ? engine : TR_ENGINE_AUTO;
+    // and on the 1x1 FPN laterals (a tcgen05 tile per 128 pixels with K = 64..256 is all fixed cost)
+    static const bool lateral_mma = [] { const char* e = getenv("TRB_FPN_MMA"); return e && atoi(e) != 0; }();
+    o.engine = (std::min(cout, cin) <= 16 || (k == 1 && lateral_mma)) ? engine : TR_ENGINE_AUTO;
     B.conv(w.f, cout, cin, k, s, t, in, out, o);
   };
   const int b = B.buffer(8);

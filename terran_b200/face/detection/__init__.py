@@ -68,6 +68,20 @@ class Detection:
                     handle.pending, handle.scale = pending, scales     # for device-resident consumers
                     return handle
             offsets = None
+        elif isinstance(images, (list, tuple)) and self.device_resize and len(images):
+            # A list of (possibly differently sized) images: every image is uploaded and resized
+            # on the device (bit-exact with the reference's host cv2.resize), and the centred
+            # zero-pad merge (detection/__init__.py:86-137) is built in device memory.
+            model = self._model()
+            idx = cuda_index(self.device)
+            with torch.cuda.device(idx):
+                resized, scales = [], []
+                for img in images:
+                    img = img if isinstance(img, torch.Tensor) else np.asarray(img)
+                    t, s = resize_short_side(to_device_u8(img[None], idx), self.short_side)
+                    resized.append(t[0])
+                    scales.append(s)
+                frames, offsets = self.merger.merge_device(resized)
         else:
             if isinstance(images, torch.Tensor):
                 images = images.cpu().numpy()

@@ -32,47 +32,14 @@ LANDMARK_TEMPLATE = np.array([
     [33.5493, 92.3655], [62.7299, 92.2041]], dtype=np.float32)
 
 
-def umeyama_similarity(src, dst):
-    """Least-squares similarity (rotation, uniform scale, translation) mapping
-    ``src`` points onto ``dst`` — Umeyama 1991, the estimator behind
-    ``SimilarityTransform.estimate``.  Returns the 3x3 homogeneous matrix."""
-    src = np.asarray(src, np.float64)
-    dst = np.asarray(dst, np.float64)
-    n, dim = src.shape
-    mu_s, mu_d = src.mean(0), dst.mean(0)
-    sc, dc = src - mu_s, dst - mu_d
-    cov = dc.T @ sc / n
-    d = np.ones(dim)
-    if np.linalg.det(cov) < 0:
-        d[dim - 1] = -1
-    T = np.eye(dim + 1)
-    U, S, Vt = np.linalg.svd(cov)
-    rank = np.linalg.matrix_rank(cov)
-    if rank == 0:
-        return np.full((dim + 1, dim + 1), np.nan)
-    if rank == dim - 1:
-        if np.linalg.det(U) * np.linalg.det(Vt) > 0:
-            T[:dim, :dim] = U @ Vt
-        else:
-            s = d[dim - 1]
-            d[dim - 1] = -1
-            T[:dim, :dim] = U @ np.diag(d) @ Vt
-            d[dim - 1] = s
-    else:
-        T[:dim, :dim] = U @ np.diag(d) @ Vt
-    scale = 1.0 / sc.var(0).sum() * (S @ d)
-    T[:dim, dim] = mu_d - scale * (T[:dim, :dim] @ mu_s)
-    T[:dim, :dim] *= scale
-    return T
-
-
 def similarity_coefficients(landmarks, image_size=(112, 112)):
     """Vectorised ``alignment_coefficients`` for (F,5,2) landmarks -> (F,6) float64, in closed
     form: in 2-D the least-squares similarity needs no SVD — with centred landmarks p and
     template points q, ``a = sum p.q``, ``b = sum p x q``, rotation ``atan2(b, a)``, scale
     ``hypot(a, b) / sum |p|^2`` (= Umeyama's ``S @ d / var``, reflections included).  The same
-    arithmetic runs on the device in ``tr_face_similarity``.  Agrees with
-    ``umeyama_similarity`` + ``np.linalg.inv`` to ~1e-12 (tests/test_host_logic.py)."""
+    arithmetic runs on the device in ``tr_face_similarity``.  Pinned against the oracle's SVD
+    Umeyama + ``np.linalg.inv`` (``oracle/align.py``) on 10 000 random faces
+    (tests/test_host_logic.py::test_closed_form_similarity_matches_umeyama)."""
     template = LANDMARK_TEMPLATE.copy()
     if image_size[1] == 112:
         template[:, 0] += 8.0
@@ -92,26 +59,6 @@ def similarity_coefficients(landmarks, image_size=(112, 112)):
                         -sn / s, c / s, -(-sn * t0 + c * t1) / s], axis=1)
     out[~((var > 0) & (nrm > 0))] = np.nan
     return out
-
-
-def alignment_coefficients(landmark, image_size=(112, 112)):
-    """The 6 PIL ``AFFINE`` coefficients (first two rows of the inverse
-    similarity landmarks -> template) of reference ``preprocess_face`` :39-61."""
-    template = LANDMARK_TEMPLATE.copy()
-    if image_size[1] == 112:
-        template[:, 0] += 8.0
-    T = umeyama_similarity(np.asarray(landmark).astype(np.float32), template)
-    return np.linalg.inv(T)[0:-1, :].flatten()
-
-
-def preprocess_face(image, landmark, image_size=(112, 112)):
-    """Align one face with its 5 landmarks and return the (3,112,112) uint8 BGR
-    crop (reference ``preprocess_face`` :22-72) — host path (PIL)."""
-    coeffs = alignment_coefficients(landmark, image_size)
-    warped = Image.fromarray(image).transform(
-        size=(image_size[1], image_size[0]), method=Image.AFFINE, data=coeffs,
-        resample=Image.BILINEAR, fillcolor=0)
-    return np.array(warped).transpose([2, 0, 1])[::-1, ...]
 
 
 def preprocess_face_no_landmarks(image, image_side=112):
@@ -250,10 +197,17 @@ class ArcFace:
         else:
             pre = []
             if faces_per_image is not None:
-                for image, faces in zip(images, faces_per_image):
-                    for face in faces:
-                        pre.append(preprocess_face(image, face['landmarks']))
+                # Differently sized images: each one is uploaded and its faces are warped on the
+                # GPU (the same bit-exact ``tr_face_align`` as the batched path) — no host PIL warp.
+                if not any(len(f) for f in faces_per_image):
+                    return [np.empty((0, 512)) for _ in images]
+                from terran_b200.frames import to_device_u8
+                with torch.cuda.device(self.device_index):
+                    crops = [self.align_device(to_device_u8(np.asarray(image)[None], self.device_index), [faces])
+                             for image, faces in zip(images, faces_per_image) if len(faces)]
+                    features = self.embed_device(torch.cat(crops, 0), 'nchw_bgr').cpu().numpy()
                 splits = np.cumsum(list(map(len, faces_per_image)))[:-1]
+                return np.split(features, splits, axis=0)
             else:
                 for image in images:
                     pre.append(preprocess_face_no_landmarks(image, S))

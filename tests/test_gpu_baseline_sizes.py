@@ -285,7 +285,7 @@ def test_c5_detect_recog_pose_pipeline(native, retina):
     from terran_b200.face.detection import Detection
     from terran_b200.face.recognition import Recognition
     from terran_b200.face.recognition.arcface import ArcFace
-    from terran_b200.face.recognition.arcface.wrapper import preprocess_face
+    from oracle.align import preprocess_face
     from terran_b200.pipeline import FrameFeeder, PerceptionPipeline
     from terran_b200.pose import Estimation
     from terran_b200.pose.openpose import OpenPose

@@ -115,10 +115,20 @@ def test_detection_wrapper(native, retina, golden):
     assert len(faces_host) == len(faces)
     for a, b in zip(faces, faces_host):
         np.testing.assert_array_equal(a['bbox'], b['bbox'])
-    # list input with different sizes -> pad-merge path
+    # list input with different sizes -> pad-merge path, resized and merged ON THE DEVICE;
+    # identical to the host cv2 + numpy pad-merge of the reference (detection/__init__.py:15-137)
     det.device_resize = True
     out = det([img, img[:400, :500]])
     assert len(out) == 2 and len(out[0]) > 0
+    det.device_resize = False
+    out_host = det([img, img[:400, :500]])
+    det.device_resize = True
+    assert [len(o) for o in out] == [len(o) for o in out_host]
+    for fa, fb in zip(out, out_host):
+        for a, b in zip(fa, fb):
+            np.testing.assert_array_equal(a['bbox'], b['bbox'])
+            np.testing.assert_array_equal(a['landmarks'], b['landmarks'])
+            assert a['bbox'].dtype == b['bbox'].dtype and a['landmarks'].dtype == b['landmarks'].dtype
 
 
 @pytest.mark.parametrize('mode', ['direct', 'tcgen05'])
@@ -272,7 +282,7 @@ def test_gpu_face_alignment_matches_pil(native, arc):
     bit (the reference's preprocess_face), including faces partly outside the frame;
     Recognition with faces on a frame batch == the host-aligned crops' embeddings."""
     from terran_b200.face.recognition import Recognition
-    from terran_b200.face.recognition.arcface.wrapper import preprocess_face
+    from oracle.align import preprocess_face
     model, _ = arc
     rng = np.random.default_rng(3)
     frames = rng.integers(0, 256, (2, 240, 320, 3), dtype=np.uint8)
@@ -303,3 +313,30 @@ def test_gpu_face_alignment_matches_pil(native, arc):
     np.testing.assert_allclose(out[0], host.cpu().numpy(), atol=1e-3)
     assert (out[0] * host.cpu().numpy()).sum(1).min() > 0.99999
     assert [o.shape for o in rec(frames, [[], []])] == [(0, 512), (0, 512)]
+
+
+def test_recognition_ragged_image_list(native, retina, arc):
+    """A list of differently sized images with their detected faces: resized, merged, aligned and
+    embedded on the device (no host cv2 / PIL) — the features equal the batched path of each
+    image alone on the same faces (reference: ``face_detection`` + ``extract_features`` on a list, detection/__init__.py
+    :86-182, arcface/wrapper.py:109-184)."""
+    from terran_b200.face.detection import Detection
+    from terran_b200.face.recognition import Recognition
+    dev = torch.device('cuda')
+    det = Detection(device=dev, lazy=True)
+    det.model = retina[0]
+    rec = Recognition(device=dev, lazy=True)
+    rec.model = arc[0]
+    rng = np.random.default_rng(17)
+    imgs = [rng.integers(0, 256, (540, 960, 3), dtype=np.uint8),
+            rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)]
+    faces = det(imgs)
+    assert all(len(f) > 0 for f in faces)
+    feats = rec(imgs, faces)
+    assert len(feats) == 2
+    for img, f, ft in zip(imgs, faces, feats):
+        want = rec(img[None], [f])[0]                       # batched device path, same faces
+        assert ft.shape == (len(f), 512)
+        # (the two calls embed different batch sizes: other tile shapes and split-K ranges, so
+        # the fp32 sums are ordered differently — same tolerance as every embedding comparison)
+        assert (ft * want).sum(1).min() > 0.9999 and np.abs(ft - want).max() < 5e-3

@@ -268,3 +268,44 @@ def test_bicubic_table_matches_oracle(native):
     tab = (C.c_float * 32)()
     native.lib().tr_bicubic_table(tab)
     np.testing.assert_array_equal(np.array(tab, np.float32).reshape(8, 4), pose.bicubic_table())
+
+
+def test_device_similarity_matches_host_on_10k_faces(native):
+    """``tr_face_similarity`` (closed form on the device, straight from detection rows) against the
+    host ``similarity_coefficients`` — itself pinned against the oracle's SVD Umeyama — on
+    10 000 random faces: landmarks are mapped back with value / scale, round half to even, as
+    ``Detection.resize_out`` does (detection/__init__.py:59-84)."""
+    import ctypes as C
+    from terran_b200 import _native as nat
+    from terran_b200.face.recognition.arcface.wrapper import LANDMARK_TEMPLATE, similarity_coefficients
+    rng = np.random.default_rng(5)
+    N, max_det, scale = 40, 256, 416 / 1080
+    counts = rng.integers(200, max_det + 1, N).astype(np.int32)
+    det = np.zeros((N, max_det, 16), np.float32)
+    th = rng.uniform(-np.pi, np.pi, (N, max_det))
+    sc = rng.uniform(0.3, 4.0, (N, max_det))
+    R = np.stack([np.stack([np.cos(th), -np.sin(th)], -1), np.stack([np.sin(th), np.cos(th)], -1)], -2)
+    lm = sc[..., None, None] * np.einsum('nfij,kj->nfki', R, LANDMARK_TEMPLATE.astype(np.float64)) \
+        + rng.uniform(0, 700, (N, max_det, 1, 2)) + rng.normal(0, 0.7, (N, max_det, 5, 2))
+    det[..., 5:15] = lm.reshape(N, max_det, 10)
+    F = int(counts.sum())
+    assert F >= 8000
+    dev = torch.device('cuda')
+    d_det, d_cnt = torch.from_numpy(det).to(dev), torch.from_numpy(counts).to(dev)
+    coef = torch.empty((F, 6), dtype=torch.float64, device=dev)
+    idx = torch.empty(F, dtype=torch.int32, device=dev)
+    total = torch.zeros(1, dtype=torch.int32, device=dev)
+    nat.check(nat.lib().tr_face_similarity(
+        C.c_void_p(d_det.data_ptr()), C.c_void_p(d_cnt.data_ptr()), N, max_det, C.c_float(scale), F,
+        C.c_void_p(coef.data_ptr()), C.c_void_p(idx.data_ptr()), C.c_void_p(total.data_ptr()),
+        nat.current_stream_ptr()))
+    torch.cuda.synchronize()
+    assert int(total.item()) == F
+    want_idx = np.repeat(np.arange(N), counts)
+    np.testing.assert_array_equal(idx.cpu().numpy(), want_idx)
+    rows = np.concatenate([det[n, :counts[n], 5:15] for n in range(N)])
+    pix = np.around(rows / np.float32(scale)).astype(np.int32).reshape(F, 5, 2)     # resize_out rounding
+    want = similarity_coefficients(pix)
+    got = coef.cpu().numpy()
+    rel = np.abs(got - want) / np.maximum(1e-3, np.abs(want))
+    assert rel.max() < 1e-9, rel.max()
