@@ -1619,14 +1619,14 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     p.patch_bytes = round_up(p.patch_tx, 1024);
     p.ring_off = 2 * p.patch_bytes;
     // Resident filters (see TcParams::resident): whole filter bank + >= 3 patch buffers in 227 KB.
-    int want = 2;
+    int want = 1;      // (2 = a second issuing warp on the odd tiles: 203 vs 195 us on conv1_2, not faster)
     if (const char* e = getenv("TRB_TC_RESIDENT")) want = atoi(e);
     const uint32_t bank = uint32_t(p.taps) * p.b_bytes;
     const uint32_t room = 227u * 1024 - 1024 /*alignment*/ - 256 - 8 * (2 * kMaxStages + 12) - 16 - param_bytes;
     const int npatch = bank < room ? std::min<int>(kMaxStages - 1, std::min<int>(4, (room - bank) / p.patch_bytes)) : 0;
     if (want && !p.swap && !p.cta2 && p.kchunks == 1 && p.n_tiles == 1 && plan->ctas_per_sm == 1 &&
         p.taps <= 64 && npatch >= 3) {
-      p.resident = want >= 2 ? 2 : 1;      // TRB_TC_RESIDENT: 0 off, 1 one issuer, 2 (default) two
+      p.resident = want >= 2 ? 2 : 1;      // TRB_TC_RESIDENT: 0 off, 1 one issuer (default), 2 two
       p.npatch = npatch;
       p.issuers = 1;
       p.sub = p.taps;                      // the "ring" is one stage that holds every tap
