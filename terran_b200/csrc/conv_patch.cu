@@ -374,19 +374,28 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     int tile_it = 0;
     Walk w = walk_begin(p);
     Seg sg;
+    int par_ct = -1;                                        // cout tile whose parameters are in registers
+    float sc = 0.f, sh = 0.f, slope = 1.f, s9[9];
     for (; walk_next(p, w, sg); ++tile_it) {
       const int acc = tile_it % p.nacc;
       const TileCoord t = tile_coord(p, sg.tile);
       const int cl = qd * 32 + lane;                       // cout within the tile
       const int cout = t.ct * 128 + cl;
       const bool c_in = cout < p.cout_pad;                 // (a 64-filter layer fills half a tile)
-      const float sc = c_in ? p.scale[cout] : 0.f, sh = c_in ? p.shift[cout] : 0.f;
+      // Per-channel parameters are re-read only when the cout tile changes (consecutive tiles
+      // of a CTA almost always share it): when the epilogue is the bound, the L2 round trip of
+      // these loads sits exposed at the head of every tile.
       // Border-class shifts: the three candidates of a pixel group (its position along the R
       // axis is fixed) are picked once per group, the one of a pixel by its position along the
       // 8-pixel axis.  Without shift9 all nine are the plain shift.
-      float s9[9];
+      if (t.ct != par_ct) {
+        par_ct = t.ct;
+        sc = c_in ? p.scale[cout] : 0.f;
+        sh = c_in ? p.shift[cout] : 0.f;
+        slope = (p.act == ACT_PRELU && c_in) ? p.slope[cout] : 1.f;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) s9[k] = (p.shift9 && c_in) ? p.shift9[k * p.cout_pad + cout] : sh;
+        for (int k = 0; k < 9; ++k) s9[k] = (p.shift9 && c_in) ? p.shift9[k * p.cout_pad + cout] : sh;
+      }
       auto group_shifts = [&](int g, float& first, float& inner, float& last) {
         const int b = t.b0 + g;
         const int bc = b == 0 ? 0 : (b >= B_dim - 1 ? 2 : 1);
@@ -416,7 +425,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         return p.res + static_cast<size_t>(pix) * p.res_cs + p.res_coff + t.ct * 128;
       };
       // one activation formula: y = max(y, 0) + neg * min(y, 0)   (ReLU 0, PReLU slope, none 1)
-      const float neg = p.act == ACT_RELU ? 0.f : (p.act == ACT_PRELU && c_in ? p.slope[cout] : 1.f);
+      const float neg = p.act == ACT_RELU ? 0.f : slope;
       mbar_wait(tfull_bar(acc), (tile_it / p.nacc) & 1u, p.err, 4);
       if (warp == 2) PT_STAMP(5);                           // accumulator complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
