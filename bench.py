@@ -489,6 +489,26 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e = world * BATCH * args.steps / float(dt.item())
+    # The host->device ceiling of this box under the SAME concurrency: every rank copies its
+    # pinned 199 MB batch K times at once (nothing else running), max over ranks.  e2e's
+    # h2d_gbs_per_gpu against this number says how close the streaming pipeline is to the
+    # host-memory / PCIe limit (which drops as more ranks share the host: SCALE runs).
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = torch.empty_like(frames)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        stage.copy_(host, non_blocking=True)               # warm-up
+        c0.record()
+        for _ in range(max(args.steps // 2, 5)):
+            stage.copy_(host, non_blocking=True)
+        c1.record()
+    copy_stream.synchronize()
+    h2d_ms = torch.tensor([c0.elapsed_time(c1) / max(args.steps // 2, 5)], device=dev)
+    if world > 1:
+        dist.all_reduce(h2d_ms, op=dist.ReduceOp.MAX)
+    h2d_ceiling = BATCH * H * W * 3 / (float(h2d_ms.item()) * 1e-3) / 1e9
+    del stage
     # bytes the wrappers copy back every step (fixed-size pinned slots, see
     # retinaface/wrapper.py::detect_async and openpose/wrapper.py::estimate_async)
     from terran_b200 import _native as nat
@@ -552,6 +572,8 @@ def run_ours(args):
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': BATCH * H * W * 3,
                 'd2h_bytes_per_step': int(d2h),
                 'h2d_gbs_per_gpu': BATCH * H * W * 3 * args.steps / float(dt.item()) / 1e9,
+                'h2d_ceiling_gbs_per_gpu': h2d_ceiling,
+                'frames_per_s_at_h2d_ceiling': world * h2d_ceiling * 1e9 / (H * W * 3),
                 'window': 'cold start: all K uploads, passes and downloads inside the timed region'},
         'gpu_launches': int(launches_per_step * args.steps),
         'roofline': {

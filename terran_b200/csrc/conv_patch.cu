@@ -173,11 +173,23 @@ __device__ __forceinline__ bool walk_last(const PatchParams& p, const Walk& w) {
   return p.sk ? w.pos >= w.end : w.tile >= p.total_tiles;
 }
 
-template <int THREADS, int MINB>
+// MODE: what the EPILOGUE of this instantiation can do (bits: 1 stream-K partials, 2 border-class
+// shifts, 4 residual, 8 everything else: the unstaged store path, fp32 output, the timing /
+// trace debug modes).  The epilogue is ~900 SASS instructions per 16-pixel chunk with every
+// path compiled in; a layer launches the smallest instantiation that covers it, so the hot
+// loop of the common layers (plain fp16 output through the staged TMA store) stays short.
+constexpr int kModeSK = 1, kModeS9 = 2, kModeRes = 4, kModeAll = 15;
+template <int THREADS, int MINB, int MODE>
 __global__ void __launch_bounds__(THREADS, MINB)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO32,
-                  const PatchParams p) {
+                  const PatchParams pk) {
+  // the features this instantiation leaves out become compile-time constants
+  PatchParams p = pk;
+  if (!(MODE & kModeSK)) p.sk = 0;
+  if (!(MODE & kModeS9)) p.shift9 = nullptr;
+  if (!(MODE & kModeRes)) p.res = nullptr;
+  if (!(MODE & 8)) { p.tma_store = 1; p.debug = 0; p.trace = nullptr; p.out_f32 = nullptr; }
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // two patch buffers first
   const uint32_t ring = base + p.ring_off;
@@ -775,10 +787,30 @@ int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+using PatchKernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, PatchParams);
+#define TRB_PATCH_MODES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(7) X(15)
+PatchKernel patch_kernel_for(int mode, bool dual) {
+  if (dual) return conv_patch_kernel<kPThreadsDual, 2, kModeAll>;
+  switch (mode) {
+#define X(m) case m: return conv_patch_kernel<kPThreads, 1, m>;
+    TRB_PATCH_MODES(X)
+#undef X
+  }
+  return conv_patch_kernel<kPThreads, 1, kModeAll>;
+}
+template <typename F>
+void for_each_patch_kernel(F f) {
+#define X(m) f(reinterpret_cast<const void*>(conv_patch_kernel<kPThreads, 1, m>), false);
+  TRB_PATCH_MODES(X)
+#undef X
+  f(reinterpret_cast<const void*>(conv_patch_kernel<kPThreadsDual, 2, kModeAll>), true);
+}
+
 }  // namespace
 
 struct ConvPatchPlan {
   bool dual = false;
+  int mode = 15;                    // epilogue instantiation (see MODE of conv_patch_kernel)
   unsigned long long* trace = nullptr;
   void* sk_own = nullptr;
   CUtensorMap tmX, tmW, tmO, tmO32;     // tmO: {128 ch x 8 px} boxes (whole-tile path), tmO32: {32 ch x 8 px} (warp-local path)
@@ -976,11 +1008,18 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   }
   plan->smem = fixed + p.stages * p.stage_bytes;
   plan->flops = 2.0 * p.N * p.H * p.W * double(a.cout_pad) * p.taps * a.cin_pad;   // (cin_pad is per group)
+  // the smallest instantiation that covers the layer (see MODE above)
+  {
+    const int need = (p.sk ? kModeSK : 0) | (p.shift9 ? kModeS9 : 0) | (p.res ? kModeRes : 0);
+    const bool generic = plan->dual || !p.tma_store || p.debug || p.trace || env_int("TRB_PT_GENERIC", 0);
+    plan->mode = generic ? kModeAll : (need == 6 ? 7 : need);
+  }
   static bool attr_set[kMaxDevices] = {};
   if (!attr_set[dev]) {
-    TR_CUDA(cudaFuncSetAttribute(conv_patch_kernel<kPThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    TR_CUDA(cudaFuncSetAttribute(conv_patch_kernel<kPThreadsDual, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    TR_CUDA(cudaFuncSetAttribute(conv_patch_kernel<kPThreadsDual, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    for_each_patch_kernel([](const void* fn, bool dual) {
+      TR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dual ? 113 * 1024 : 227 * 1024));
+      if (dual) TR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    });
     attr_set[dev] = true;
   }
   return plan;
@@ -1024,10 +1063,8 @@ void conv_patch_launch(const ConvPatchPlan* plan, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  if (plan->dual)
-    TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel<kPThreadsDual, 2>, plan->tmX, plan->tmW, plan->tmO, plan->tmO32, plan->p));
-  else
-    TR_CUDA(cudaLaunchKernelEx(&cfg, conv_patch_kernel<kPThreads, 1>, plan->tmX, plan->tmW, plan->tmO, plan->tmO32, plan->p));
+  TR_CUDA(cudaLaunchKernelEx(&cfg, patch_kernel_for(plan->mode, plan->dual), plan->tmX, plan->tmW, plan->tmO,
+                             plan->tmO32, plan->p));
 }
 
 }  // namespace trb
