@@ -463,10 +463,13 @@ __device__ __forceinline__ void mma_issuer_alternate_halo(const TcParams& p, int
 // instruction plus ~500 cycles of barrier/commit latency per ring stage (measured with the
 // clock64 instrumentation, profiles/r01_swap_modes.txt), which is MORE than the tensor time of
 // an N <= 128 instruction (64 cycles): two CTAs give the SM's tensor pipe two issuing threads.
-template <int KSTEPS, int MINB>
-__global__ void __launch_bounds__(kThreads1, MINB)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TcParams p) {
+// MODE: 0 = every path compiled in (181 KB of SASS); 1 = resident-filter halo layers only;
+// 2 = plain per-tap layers (no halo / swap / second output / debug instrumentation).  The lean
+// instantiations keep the role loops and the epilogue of the layers that use them inside the
+// instruction cache — the same effect as in conv_patch.cu (`no_instructions` was one of the
+// top three stall reasons of the fat kernel, profiles/r02_resident_filters.txt).
+template <int KSTEPS>
+__device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Manual 1024-byte alignment (SWIZZLE_128B atoms repeat every 1024 bytes).
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1046,6 +1049,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+template <int KSTEPS, int MINB, int MODE = 0>
+__global__ void __launch_bounds__(kThreads1, MINB)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams pk) {
+  if (MODE == 0) {
+    conv_tc_body<KSTEPS>(tmA, tmB, pk);
+    return;
+  }
+  // the features a lean instantiation leaves out become compile-time constants
+  TcParams p = pk;
+  p.swap = 0; p.debug = 0; p.out2 = nullptr; p.rotate = 0; p.cta2 = 0;
+  if (MODE == 1) {            // resident filters: one issuer, whole tiles
+    p.resident = 1; p.issuers = 1; p.sk = 0; p.out_f32 = nullptr;
+    if (p.halo != 2) p.halo = 1;
+  }
+  if (MODE == 2) {            // plain per-tap loads
+    p.halo = 0; p.resident = 0;
+  }
+  conv_tc_body<KSTEPS>(tmA, tmB, p);
+}
+
 // ---------------------------------------------------------------------------
 // CTA-pair variant (tcgen05 cta_group::2).  Two CTAs of a cluster compute two
 // adjacent pixel tiles against the SAME filter tile: each CTA loads its own A
@@ -1376,12 +1400,14 @@ int num_sms() {
 
 using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const TcParams);
 
-KernelFn kernel_for(int kc, int ctas_per_sm) {
+KernelFn kernel_for(int kc, int ctas_per_sm, int mode = 0) {
   KernelFn fn = ctas_per_sm == 2
                     ? (kc == 64 ? conv_tc_kernel<4, 2> : (kc == 32 ? conv_tc_kernel<2, 2> : conv_tc_kernel<1, 2>))
-                    : (kc == 64 ? conv_tc_kernel<4, 1> : (kc == 32 ? conv_tc_kernel<2, 1> : conv_tc_kernel<1, 1>));
-  static bool attr_set[kMaxDevices][6] = {};
-  const int slot = (kc == 64 ? 0 : (kc == 32 ? 1 : 2)) + (ctas_per_sm == 2 ? 3 : 0);
+                    : (kc == 64 ? (mode == 1 ? conv_tc_kernel<4, 1, 1> : mode == 2 ? conv_tc_kernel<4, 1, 2> : conv_tc_kernel<4, 1>)
+                                : (kc == 32 ? conv_tc_kernel<2, 1> : conv_tc_kernel<1, 1>));
+  if (ctas_per_sm == 2 || kc != 64) mode = 0;
+  static bool attr_set[kMaxDevices][8] = {};
+  const int slot = mode ? 5 + mode : (kc == 64 ? 0 : (kc == 32 ? 1 : 2)) + (ctas_per_sm == 2 ? 3 : 0);
   const int dev = current_device();
   if (!attr_set[dev][slot]) {
     TR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1402,6 +1428,7 @@ struct ConvTcPlan {
   void* sk_own = nullptr;
   int grid;
   int ctas_per_sm = 1;
+  int mode = 0;                 // kernel instantiation (see MODE of conv_tc_kernel)
   uint32_t smem;
   double flops;
 };
@@ -1733,7 +1760,15 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     }
   }
   plan->flops = 2.0 * p.N * p.H_out * p.W_out * double(a.cout_pad) * a.kh * a.kw * a.cin_pad;
-  kernel_for(p.KC, plan->ctas_per_sm);
+  // lean instantiations (see MODE of conv_tc_kernel)
+  {
+    static const bool lean = [] { const char* e = getenv("TRB_TC_LEAN"); return !e || atoi(e) != 0; }();
+    const bool base_ok = lean && p.KC == 64 && plan->ctas_per_sm == 1 && !p.swap && !p.debug && !p.out2 && !p.rotate && !p.cta2;
+    plan->mode = 0;
+    if (base_ok && p.resident == 1 && !p.out_f32) plan->mode = 1;
+    else if (base_ok && !p.halo && !p.resident) plan->mode = 2;
+  }
+  kernel_for(p.KC, plan->ctas_per_sm, plan->mode);
   return plan;
 }
 
@@ -1787,7 +1822,7 @@ void conv_tc_launch(const ConvTcPlan* plan, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  TR_CUDA(cudaLaunchKernelEx(&cfg, kernel_for(plan->p.KC, plan->ctas_per_sm), plan->tmA, plan->tmB, plan->p));
+  TR_CUDA(cudaLaunchKernelEx(&cfg, kernel_for(plan->p.KC, plan->ctas_per_sm, plan->mode), plan->tmA, plan->tmB, plan->p));
 }
 
 }  // namespace trb
