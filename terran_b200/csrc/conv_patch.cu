@@ -139,29 +139,35 @@ __device__ __forceinline__ TileCoord tile_coord(const PatchParams& p, int tile) 
   return t;
 }
 
-// One CTA's sequence of tile segments [i0, i1) (in ring iterations of the tile).
+// One CTA's sequence of tile segments [i0, i1) (in ring iterations of the tile).  32-bit
+// arithmetic: the plan only enables stream-K when total_tiles * ipt * grid < 2^32 (a 64-bit
+// division is ~100 inlined instructions, and every role walks).
 struct Walk {
-  long long pos, end;
+  unsigned pos, end;
   int tile;
 };
 struct Seg {
   int tile, i0, i1;
 };
+__device__ __forceinline__ unsigned walk_bound(const PatchParams& p, unsigned cta) {
+  return static_cast<unsigned>(p.total_tiles) * static_cast<unsigned>(p.ipt) * cta / gridDim.x;
+}
 __device__ __forceinline__ Walk walk_begin(const PatchParams& p) {
   Walk w;
-  const long long total = static_cast<long long>(p.total_tiles) * p.ipt;
-  w.pos = p.sk ? total * blockIdx.x / gridDim.x : 0;
-  w.end = p.sk ? total * (blockIdx.x + 1) / gridDim.x : 0;
+  w.pos = p.sk ? walk_bound(p, blockIdx.x) : 0u;
+  w.end = p.sk ? walk_bound(p, blockIdx.x + 1) : 0u;
   w.tile = blockIdx.x;
   return w;
 }
 __device__ __forceinline__ bool walk_next(const PatchParams& p, Walk& w, Seg& s) {
   if (p.sk) {
     if (w.pos >= w.end) return false;
-    s.tile = static_cast<int>(w.pos / p.ipt);
-    s.i0 = static_cast<int>(w.pos - static_cast<long long>(s.tile) * p.ipt);
-    s.i1 = static_cast<int>(min(static_cast<long long>(p.ipt), s.i0 + (w.end - w.pos)));
-    w.pos += s.i1 - s.i0;
+    const unsigned ipt = static_cast<unsigned>(p.ipt);
+    const unsigned tile = w.pos / ipt;
+    s.tile = static_cast<int>(tile);
+    s.i0 = static_cast<int>(w.pos - tile * ipt);
+    s.i1 = static_cast<int>(min(ipt, static_cast<unsigned>(s.i0) + (w.end - w.pos)));
+    w.pos += static_cast<unsigned>(s.i1 - s.i0);
     return true;
   }
   if (w.tile >= p.total_tiles) return false;
@@ -475,9 +481,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       int n_parts = 0;
       if (sg.i1 < p.ipt) {
         // The rest of this tile was the FIRST thing the next CTA(s) computed.
-        const long long total = static_cast<long long>(p.total_tiles) * p.ipt;
-        const long long tile_end = static_cast<long long>(sg.tile + 1) * p.ipt;
-        for (int b = blockIdx.x + 1; b < grid && total * b / grid < tile_end; ++b) ++n_parts;
+        const unsigned tile_end = static_cast<unsigned>(sg.tile + 1) * static_cast<unsigned>(p.ipt);
+        for (int b = blockIdx.x + 1; b < grid && walk_bound(p, b) < tile_end; ++b) ++n_parts;
         if (lane == 0) {
           for (int k = 1; k <= n_parts; ++k) {
             const long long t0 = clock64();
@@ -991,7 +996,8 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
     p.ipt = p.kchunks * p.iters;
     const int rounds = ceil_div(p.total_tiles, slots);
     const double idle = 1.0 - double(p.total_tiles) / (double(rounds) * slots);
-    const bool ok = p.ipt >= 2 && slots < int(2048 / 4) - 1;
+    const bool ok = p.ipt >= 2 && slots < int(2048 / 4) - 1 &&
+                    double(p.total_tiles) * p.ipt * (slots + 1) < 4.0e9;      // 32-bit walk arithmetic
     const bool worth = p.ipt >= 4 && idle >= 0.08;
     if (ok && (want == 2 || (want == 1 && worth))) {
       void* scratch = a.sk_scratch;
