@@ -34,6 +34,7 @@
 #include <cudaTypedefs.h>
 
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -560,8 +561,10 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
         };
         const uint32_t warp_stage = stage_out + static_cast<uint32_t>(ew) * (kStageSlots * 1024u);
-        auto finish = [&](uint32_t (&v)[16], int g) {
-          if (n_parts) {
+        // (`parts_c`: compile-time "this tile has parked stream-K partials" — the loop below is
+        // instantiated twice so that the common no-partials chunk code is short and contiguous)
+        auto finish = [&](uint32_t (&v)[16], int g, auto parts_c) {
+          if (decltype(parts_c)::value) {
             const float* f = reinterpret_cast<const float*>(pf);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + f[j]);
@@ -681,25 +684,29 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           if (elect_one()) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           __syncwarp();
         };
-        if (n_parts) fetch_part0(g_begin);
         if (p.res) fetch_res(g_begin);
-        uint32_t va[16], vb[16];
-        int g = g_begin;
-        __syncwarp();
-        tmem_ld16_async(taddr + g * 8, va);
-        while (g < g_end) {
-          __syncwarp();                       // tcgen05.ld / wait::ld are warp-collective
-          tmem_ld_wait();
-          if (g + 2 < g_end) tmem_ld16_async(taddr + (g + 2) * 8, vb);
-          finish(va, g);
-          g += 2;
-          if (g >= g_end) break;
+        auto run = [&](auto parts_c) {
+          if (decltype(parts_c)::value) fetch_part0(g_begin);
+          uint32_t va[16], vb[16];
+          int g = g_begin;
           __syncwarp();
-          tmem_ld_wait();
-          if (g + 2 < g_end) tmem_ld16_async(taddr + (g + 2) * 8, va);
-          finish(vb, g);
-          g += 2;
-        }
+          tmem_ld16_async(taddr + g * 8, va);
+          while (g < g_end) {
+            __syncwarp();                       // tcgen05.ld / wait::ld are warp-collective
+            tmem_ld_wait();
+            if (g + 2 < g_end) tmem_ld16_async(taddr + (g + 2) * 8, vb);
+            finish(va, g, parts_c);
+            g += 2;
+            if (g >= g_end) break;
+            __syncwarp();
+            tmem_ld_wait();
+            if (g + 2 < g_end) tmem_ld16_async(taddr + (g + 2) * 8, va);
+            finish(vb, g, parts_c);
+            g += 2;
+          }
+        };
+        if (n_parts) run(std::true_type{});
+        else run(std::false_type{});
         if (whole) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("bar.sync 3, %0;" ::"r"(p.epi_warps * 32) : "memory");     // all epilogue warps
