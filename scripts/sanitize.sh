@@ -22,8 +22,12 @@ PATCH="tests/test_gpu_conv_patch.py"
 OPS="tests/test_gpu_ops.py"
 run patch-default   memcheck  -- $PATCH -k "matches_reference or epilogues or stream_k"
 run patch-sk-always memcheck  TRB_PT_SK=2 -- $PATCH -k "matches_reference or tile_geometries"
+run patch-generic   memcheck  TRB_PT_GENERIC=1 -- $PATCH -k "matches_reference or epilogues"
 run patch-race      racecheck -- $PATCH -k "matches_reference or stream_k_epilogues"
 run tc-default      memcheck  -- $OPS -k "conv or sepconv"
+run tc-fat-kernel   memcheck  TRB_TC_LEAN=0 -- $OPS -k "conv_matches_reference"
+run tc-resident-2   memcheck  TRB_TC_RESIDENT=2 -- $OPS -k "conv_matches_reference"
+run tc-resident-off memcheck  TRB_TC_RESIDENT=0 -- $OPS -k "conv_matches_reference"
 run tc-issuers-off  memcheck  TRB_TC_ISSUERS=0 -- $OPS -k "conv_matches_reference or conv_stream_k"
 run tc-sk-always    memcheck  TRB_TC_SK=2 -- $OPS -k "conv_matches_reference or conv_stream_k"
 run tc-halo-off     memcheck  TRB_TC_HALO=0 -- $OPS -k "conv_matches_reference or conv_stream_k"
