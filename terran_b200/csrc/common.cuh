@@ -78,6 +78,7 @@ struct ConvArgs {
   // cout_pad filter rows are `groups` equal blocks, block g reads channels in.coff + g * cin_pad
   int groups = 1;
   int patch_rows = 0;  // conv_patch: force R rows of 8-pixel groups per tile (0 = choose)
+  int pool2 = 0;       // conv_patch: fuse the 2x2 / stride-2 max-pool that follows; `out` is the POOLED view
   int cout_pad = 0;   // multiple of 16
   int cout_store = 0; // channels actually written (multiple of 8, <= cout_pad)
   int cin_pad = 0;    // multiple of 16

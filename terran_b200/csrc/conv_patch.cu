@@ -66,6 +66,8 @@ struct PatchParams {
   int sub, iters, stages;      // taps per ring stage, stages per chunk, ring depth
   uint32_t stage_bytes, patch_bytes, patch_tx, ring_off;
   int tma_store;               // 1: epilogue transposes through smem and stores with TMA (UTMASTG)
+  int pool;                    // 1: 2x2 / stride-2 max-pool fused into the (staged) epilogue: the output
+                               // maps describe the POOLED tensor (floor(H/2) x floor(W/2))
   // Stream-K: the CTAs split the launch's (tile, ring iteration) sequence into equal contiguous
   // ranges instead of whole tiles, so no SM idles in a last partial round and a launch with
   // fewer tiles than SMs still uses all of them (split-K).  A range that starts inside a tile
@@ -185,7 +187,7 @@ __device__ __forceinline__ bool walk_last(const PatchParams& p, const Walk& w) {
 // trace debug modes).  The epilogue is ~900 SASS instructions per 16-pixel chunk with every
 // path compiled in; a layer launches the smallest instantiation that covers it, so the hot
 // loop of the common layers (plain fp16 output through the staged TMA store) stays short.
-constexpr int kModeSK = 1, kModeS9 = 2, kModeRes = 4, kModeAll = 15;
+constexpr int kModeSK = 1, kModeS9 = 2, kModeRes = 4, kModeAll = 15, kModePool = 16;
 template <int THREADS, int MINB, int MODE>
 __global__ void __launch_bounds__(THREADS, MINB)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
@@ -197,6 +199,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (!(MODE & kModeS9)) p.shift9 = nullptr;
   if (!(MODE & kModeRes)) p.res = nullptr;
   if (!(MODE & 8)) { p.tma_store = 1; p.debug = 0; p.trace = nullptr; p.out_f32 = nullptr; }
+  p.pool = (MODE & kModePool) ? 1 : 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // two patch buffers first
   const uint32_t ring = base + p.ring_off;
@@ -608,6 +611,48 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 16; ++i) y[i] = fmaf(fminf(y[i], 0.f), neg, fmaxf(y[i], 0.f));
           }
+          if (p.pool) {
+            // Fused 2x2 / stride-2 max-pool (VGG: conv -> ReLU -> pool): the chunk holds two
+            // adjacent lines of eight pixels of this lane's channel, so the four windows are
+            // in-lane maxima; four pooled pixels are staged and stored instead of sixteen.
+            float q[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              q[j] = fmaxf(fmaxf(y[2 * j], y[2 * j + 1]), fmaxf(y[8 + 2 * j], y[9 + 2 * j]));
+            const uint32_t pslot = whole ? base + static_cast<uint32_t>(g >> 1) * 1024u + qd * 64u
+                                         : warp_stage + (chunk_ctr % kStageSlots) * 1024u;
+            const uint32_t ppitch = whole ? 256u : 64u;
+            if (!whole) {
+              ++chunk_ctr;
+              if (elect_one()) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStageSlots - 1) : "memory");
+              __syncwarp();
+            }
+            const uint32_t sel = (lane & 1) ? 0x3276u : 0x5410u;
+            const uint32_t dst0 = pslot + (lane & 1) * ppitch + (lane & ~1) * 2u;
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) {
+              const __half2 h2 = __floats2half2_rn(q[i], q[i + 1]);
+              const uint32_t own = *reinterpret_cast<const uint32_t*>(&h2);
+              const uint32_t oth = __shfl_xor_sync(0xffffffffu, own, 1);
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst0 + static_cast<uint32_t>(i) * ppitch),
+                           "r"(__byte_perm(own, oth, sel)) : "memory");
+            }
+            if (whole) return;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            const int bp = (t.b0 + g) >> 1, ap = t.a0 >> 1;          // pooled coordinates
+            const bool ok = t.b0 + g + 1 < B_dim;                     // warp-uniform (floor pooling)
+            const int cw = p.axis == 0 ? ap : bp, ch = p.axis == 0 ? bp : ap;
+            if (ok && elect_one())
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                  ::"l"(&tmO32), "r"(pslot), "r"(p.out_coff + t.ct * 128 + qd * 32), "r"(cw), "r"(ch), "r"(t.n)
+                  : "memory");
+            __syncwarp();
+            if (elect_one()) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            __syncwarp();
+            return;
+          }
           // 16 pixel rows of `pitch` bytes: a private slot, or this warp's 64-byte column of the
           // whole-tile staging area
           const uint32_t slot = whole ? base + static_cast<uint32_t>(g) * 2048u + qd * 64u
@@ -712,15 +757,17 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           asm volatile("bar.sync 3, %0;" ::"r"(p.epi_warps * 32) : "memory");     // all epilogue warps
           // every epilogue warp stores the groups ew, ew + epi_warps, ...: converged loop, one
           // elected lane per instruction
-          for (int r = ew; r < p.R; r += p.epi_warps) {
-            const int b = t.b0 + r;
-            const bool ok = b < B_dim && !(p.debug & 4);        // warp-uniform
-            const int cw = p.axis == 0 ? t.a0 : b, ch = p.axis == 0 ? b : t.a0;
+          const int n_rows = p.pool ? p.R >> 1 : p.R;             // staged lines: 4 pooled / 8 pixels each
+          for (int r = ew; r < n_rows; r += p.epi_warps) {
+            const int b = p.pool ? (t.b0 >> 1) + r : t.b0 + r;
+            const bool ok = (p.pool ? t.b0 + 2 * r + 1 < B_dim : b < B_dim) && !(p.debug & 4);   // warp-uniform
+            const int a = p.pool ? t.a0 >> 1 : t.a0;
+            const int cw = p.axis == 0 ? a : b, ch = p.axis == 0 ? b : a;
             if (ok && elect_one())
               asm volatile(
                   "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                  ::"l"(&tmO), "r"(base + static_cast<uint32_t>(r) * 2048u), "r"(p.out_coff + t.ct * 128),
-                    "r"(cw), "r"(ch), "r"(t.n) : "memory");
+                  ::"l"(&tmO), "r"(base + static_cast<uint32_t>(r) * (p.pool ? 1024u : 2048u)),
+                    "r"(p.out_coff + t.ct * 128), "r"(cw), "r"(ch), "r"(t.n) : "memory");
             __syncwarp();
           }
           if (elect_one()) {
@@ -800,7 +847,7 @@ int env_int(const char* name, int dflt) {
 }
 
 using PatchKernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, PatchParams);
-#define TRB_PATCH_MODES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(7) X(15)
+#define TRB_PATCH_MODES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(7) X(15) X(16) X(17)
 PatchKernel patch_kernel_for(int mode, bool dual) {
   if (dual) return conv_patch_kernel<kPThreadsDual, 2, kModeAll>;
   switch (mode) {
@@ -880,6 +927,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
     const int A = axis == 0 ? p.W : p.H, B = axis == 0 ? p.H : p.W;
     for (int R = 2; R <= 32; R += 2) {
       if (force_r && R != force_r) continue;
+      if (a.pool2 && R % 4) continue;          // a team's groups pair up into pooling windows
       const uint32_t patch = round_up(p.PA * (R + halo) * 128, 1024);
       if (2 * patch + 3 * kFilterBlock + kOutStage + 4096 > 227u * 1024) continue;
       const double util = double(A) / (8.0 * ceil_div(A, 8)) * double(B) / (double(R) * ceil_div(B, R));
@@ -973,6 +1021,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   // TMA-store epilogue: plain fp16 output of whole 128-channel tiles (no residual); the 4-D map
   // {C, W, H, N} clips the ragged border of the 8-pixel groups.
   const bool whole = a.cout_store % 128 == 0 || a.out.coff + a.cout_store == a.out.cs;   // the map clips
+  p.pool = a.pool2 ? 1 : 0;
   p.tma_store = env_int("TRB_PT_TMA_STORE", 1) && !a.out_f32 && whole &&
                 a.out.cs % 8 == 0 && a.out.coff % 8 == 0 &&
                 (!a.res.ptr || (a.res.cs % 8 == 0 && a.res.coff % 8 == 0));
@@ -980,9 +1029,12 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   plan->tmO32 = plan->tmW;
   if (p.tma_store) {
     const cuuint64_t ocs = a.out.cs;
-    cuuint64_t odim[4] = {ocs, W, H, N};
-    cuuint64_t ostr[3] = {ocs * 2, W * ocs * 2, H * W * ocs * 2};
-    cuuint32_t obox[4] = {128, cuuint32_t(p.axis == 0 ? 8 : 1), cuuint32_t(p.axis == 0 ? 1 : 8), 1};
+    // (fused pooling: the maps describe the pooled tensor, four pooled pixels per staged line)
+    const cuuint64_t oW = p.pool ? cuuint64_t(a.out.W) : W, oH = p.pool ? cuuint64_t(a.out.H) : H;
+    const cuuint32_t line = p.pool ? 4 : 8;
+    cuuint64_t odim[4] = {ocs, oW, oH, N};
+    cuuint64_t ostr[3] = {ocs * 2, oW * ocs * 2, oH * oW * ocs * 2};
+    cuuint32_t obox[4] = {128, cuuint32_t(p.axis == 0 ? line : 1), cuuint32_t(p.axis == 0 ? 1 : line), 1};
     r = encode(&plan->tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.out.ptr, odim, ostr, obox, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1026,6 +1078,12 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
     const int need = (p.sk ? kModeSK : 0) | (p.shift9 ? kModeS9 : 0) | (p.res ? kModeRes : 0);
     const bool generic = plan->dual || !p.tma_store || p.debug || p.trace || env_int("TRB_PT_GENERIC", 0);
     plan->mode = generic ? kModeAll : (need == 6 ? 7 : need);
+    if (p.pool) {
+      TR_CHECK(!generic && !(need & (kModeS9 | kModeRes)) && a.act == ACT_RELU,
+               "fused max-pool needs the staged plain ReLU epilogue");
+      TR_CHECK(a.out.H == a.H_out / 2 && a.out.W == a.W_out / 2, "fused max-pool: pooled output dims");
+      plan->mode = kModePool | (need & kModeSK);
+    }
   }
   static bool attr_set[kMaxDevices] = {};
   if (!attr_set[dev]) {

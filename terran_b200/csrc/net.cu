@@ -48,6 +48,7 @@ struct PreparedOp {
   bool mma = false;          // TR_OP_CONV on the warp-level mma.sync kernel
   void* sep_tmp = nullptr;   // force_direct: depthwise output between the two unfused kernels
   View vin, vout;
+  bool skip = false;        // fused into the previous op (2x2 max-pool in the conv epilogue): no launch
 };
 
 constexpr size_t kMaxPlans = 8;      // cached (N, H, W) plans per net
@@ -234,9 +235,31 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
   for (const tr_op_desc& d : net->ops)
     if (d.type == TR_OP_VIEW) B[d.out].ptr = B[d.in].ptr;
   // ---- pass 3: prepare launches
-  for (const tr_op_desc& d : net->ops) {
+  // A 2x2 max-pool whose input is written by the op right before it and read by nothing else
+  // (VGG: conv -> ReLU -> pool) is fused into that conv's epilogue when the resident-patch
+  // kernel runs it (TRB_POOL_FUSE=0 keeps the separate kernel).
+  static const bool pool_fuse = [] {
+    const char* e = getenv("TRB_POOL_FUSE");
+    return (!e || atoi(e) != 0) && !getenv("TRB_PT_DEBUG") && !getenv("TRB_PT_GENERIC") && !getenv("TRB_PT_TMA_STORE");
+  }();
+  auto sole_consumer_is_next_pool = [&](size_t i) {
+    if (i + 1 >= net->ops.size()) return false;
+    const tr_op_desc &c = net->ops[i], &m = net->ops[i + 1];
+    if (m.type != TR_OP_MAXPOOL || m.in != c.out || m.in_coff != c.out_coff || m.in_c != c.out_c) return false;
+    for (size_t j = 0; j < net->ops.size(); ++j) {
+      if (j == i || j == i + 1) continue;
+      const tr_op_desc& o = net->ops[j];
+      if (o.in == c.out || o.res == c.out || o.out == c.out || o.out2 == c.out) return false;
+    }
+    return true;
+  };
+  bool skip_next = false;
+  for (size_t op_i = 0; op_i < net->ops.size(); ++op_i) {
+    const tr_op_desc& d = net->ops[op_i];
     PreparedOp po{};
     po.d = d;
+    po.skip = skip_next;
+    skip_next = false;
     switch (d.type) {
       case TR_OP_STEM: {
         StemArgs& a = po.stem;
@@ -313,6 +336,13 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
           plan->tc_flops += po.flops;
           plan->tc_launches++;
         } else if (use_tc && patch_wanted(a)) {
+          if (pool_fuse && G == 1 && d.act == TR_ACT_RELU && d.res < 0 && d.out2 < 0 && !a.shift9 && !a.out_f32 &&
+              d.out_c % 128 == 0 && sole_consumer_is_next_pool(op_i)) {
+            const tr_op_desc& m = net->ops[op_i + 1];
+            a.pool2 = 1;
+            a.out = make_view(B[m.out], m.out_coff, m.out_c);      // the POOLED tensor
+            skip_next = true;
+          }
           a.sk_scratch = lane_scratch(net, d.lane == 1);
           po.pt = conv_patch_plan_create(a, conv_tc_error_flag());
           plan->tc_flops += po.flops;
@@ -401,7 +431,7 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
       case TR_OP_VIEW:
         break;
     }
-    if (d.type != TR_OP_VIEW)
+    if (d.type != TR_OP_VIEW && !po.skip)
       plan->launches += (d.type == TR_OP_SEPCONV && !po.mma) ? 2 : (po.gconv.empty() ? 1 : int(po.gconv.size()));
     plan->ops.push_back(po);
   }
@@ -495,7 +525,7 @@ void run_plan(tr_net* net, Plan* plan, const uint8_t* image, int64_t sn, int64_t
         else { dwconv_launch(po.dw, s); conv_direct_launch(po.conv, s); }
         break;
       case TR_OP_DWCONV: dwconv_launch(po.dw, s); break;
-      case TR_OP_MAXPOOL: maxpool2_launch(po.vin, po.vout, s); break;
+      case TR_OP_MAXPOOL: if (!po.skip) maxpool2_launch(po.vin, po.vout, s); break;
       case TR_OP_COPY: copy_slice_launch(po.vin, po.vout, s); break;
       default: break;
     }
