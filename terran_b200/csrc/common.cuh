@@ -79,6 +79,8 @@ struct ConvArgs {
   int groups = 1;
   int patch_rows = 0;  // conv_patch: force R rows of 8-pixel groups per tile (0 = choose)
   int pool2 = 0;       // conv_patch: fuse the 2x2 / stride-2 max-pool that follows; `out` is the POOLED view
+  View pool_out;       // conv_tc: OPTIONAL pooled output view — the plan fuses the pool if its tile layout allows
+                       // (conv_tc_plan_pooled tells), and then writes this tensor INSTEAD of `out`
   int cout_pad = 0;   // multiple of 16
   int cout_store = 0; // channels actually written (multiple of 8, <= cout_pad)
   int cin_pad = 0;    // multiple of 16
@@ -106,6 +108,7 @@ bool conv_patch_eligible(const ConvArgs& a);
 size_t conv_patch_scratch_bytes();
 struct ConvPatchPlan;
 ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag);
+bool conv_tc_plan_pooled(const ConvTcPlan* p);   // did the plan take ConvArgs::pool_out?
 void conv_patch_plan_destroy(ConvPatchPlan* p);
 void conv_patch_launch(const ConvPatchPlan* p, cudaStream_t s);
 void conv_patch_plan_describe(const ConvPatchPlan* p, int* axis, int* R, int* tiles, int* stages);

@@ -111,6 +111,11 @@ struct TcParams {
   // instrumentation, profiles/r02_resident_filters.txt): 5 080 cycles per 128-pixel tile, of
   // which ~4 500 is the latency of the single patch in flight and 2 700 the MMA issue.
   int resident, npatch;
+  // Fused 2x2 / stride-2 max-pool (halo tiles only: 8 x 16 / 16 x 8 pixels, the four pixels of a
+  // window are lanes l, l ^ 1, l ^ 8, l ^ 9 of one epilogue warp): the pooled tensor is written
+  // INSTEAD of the full-resolution one.
+  int pool;
+  __half* pool_out; int pool_cs, pool_coff, pool_H, pool_W;
 };
 
 // Walks the tile segments of one CTA: whole tiles with the static stride, or the CTA's
@@ -151,12 +156,15 @@ struct EpiCtx {
   int cpad;
   bool valid;
   long pix, rpix;
+  bool pool_store;       // this lane writes the pooled pixel of its 2x2 window
+  long ppix;
 };
 
 // Scale/shift/activation/residual/store of 16 consecutive output channels.
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiCtx& e,
                                                const uint32_t (&v)[16], int cbase) {
-  if (!e.valid || cbase >= p.cout_store || (p.debug & 8)) return;
+  // (fused pooling shuffles across the warp: lanes of invalid pixels take part, with -inf)
+  if ((!e.valid && !p.pool) || cbase >= p.cout_store || (p.debug & 8)) return;
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const int c = cbase + g * 8;
@@ -178,6 +186,28 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiCtx& 
       const float sl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = y[j] >= 0.f ? y[j] : y[j] * sl[j];
+    }
+    if (p.pool) {
+      // max over the window's four lanes on packed halves (rounding is monotonic: the same
+      // value as pooling the rounded full-resolution tensor), then one lane of the four stores
+      uint32_t h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2 t2 = __floats2half2_rn(e.valid ? y[2 * j] : -65504.f, e.valid ? y[2 * j + 1] : -65504.f);
+        h[j] = *reinterpret_cast<const uint32_t*>(&t2);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t o = __shfl_xor_sync(0xffffffffu, h[j], 1);
+        __half2 m = __hmax2(*reinterpret_cast<__half2*>(&h[j]), *reinterpret_cast<__half2*>(&o));
+        h[j] = *reinterpret_cast<uint32_t*>(&m);
+        o = __shfl_xor_sync(0xffffffffu, h[j], 8);
+        m = __hmax2(*reinterpret_cast<__half2*>(&h[j]), *reinterpret_cast<__half2*>(&o));
+        h[j] = *reinterpret_cast<uint32_t*>(&m);
+      }
+      if (e.pool_store && !(p.debug & 4))
+        *reinterpret_cast<uint4*>(p.pool_out + e.ppix * p.pool_cs + p.pool_coff + c) = make_uint4(h[0], h[1], h[2], h[3]);
+      continue;
     }
     if (p.res) {
       const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res + e.rpix * p.res_cs +
@@ -906,6 +936,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
       const int ow = wb * p.bw + w_l, oh = hb * p.bh + h_l, on = nb * p.bn + n_l;
       e.valid = row < p.rows && ow < p.W_out && oh < p.H_out && on < p.N;
       e.pix = (static_cast<long>(on) * p.H_out + oh) * p.W_out + ow;
+      e.pool_store = p.pool && e.valid && !(lane & 9) && oh + 1 < p.H_out && ow + 1 < p.W_out;
+      e.ppix = p.pool ? (static_cast<long>(on) * p.pool_H + (oh >> 1)) * p.pool_W + (ow >> 1) : 0;
       // swap mode: the tile is a band of full-width rows of image nb (consecutive pixels), or
       // bw columns x 8 rows of the halo patch
       SwapTile st;
@@ -1065,7 +1097,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.halo != 2) p.halo = 1;
   }
   if (MODE == 2) {            // plain per-tap loads
-    p.halo = 0; p.resident = 0;
+    p.halo = 0; p.resident = 0; p.pool = 0;
   }
   conv_tc_body<KSTEPS>(tmA, tmB, p);
 }
@@ -1311,6 +1343,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int ow = wb * p.bw + w_l, oh = hb * p.bh + h_l, on = nb * p.bn + n_l;
       e.valid = row < p.rows && ow < p.W_out && oh < p.H_out && on < p.N;
       e.pix = (static_cast<long>(on) * p.H_out + oh) * p.W_out + ow;
+      e.pool_store = false; e.ppix = 0;
       // swap mode: the tile is a band of full-width rows of image nb (consecutive pixels), or
       // bw columns x 8 rows of the halo patch
       SwapTile st;
@@ -1688,6 +1721,12 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   p.res = a.res.ptr; p.res_cs = a.res.cs; p.res_coff = a.res.coff; p.res_up2 = a.res_up2;
   p.res_H = a.res.H; p.res_W = a.res.W;
   p.out_f32 = a.out_f32;
+  p.pool = a.pool_out.ptr && p.halo && !p.swap && !p.cta2 && a.act == ACT_RELU && !a.res.ptr && !a.out2.ptr &&
+           !a.out_f32 && !a.shift9 && a.pool_out.H == a.H_out / 2 && a.pool_out.W == a.W_out / 2;
+  if (p.pool) {
+    p.pool_out = a.pool_out.ptr; p.pool_cs = a.pool_out.cs; p.pool_coff = a.pool_out.coff;
+    p.pool_H = a.pool_out.H; p.pool_W = a.pool_out.W;
+  }
   p.err = tc_error_flag();
   if (const char* dbg = getenv("TRB_TC_DEBUG")) p.debug = atoi(dbg);
   p.pdl_late = 1;
@@ -1778,6 +1817,8 @@ void conv_tc_plan_destroy(ConvTcPlan* p) {
 }
 
 double conv_tc_plan_flops(const ConvTcPlan* p) { return p->flops; }
+
+bool conv_tc_plan_pooled(const ConvTcPlan* p) { return p->p.pool != 0; }
 
 int* conv_tc_error_flag() { return tc_error_flag(); }
 

@@ -371,7 +371,13 @@ Plan* build_plan(tr_net* net, int N, int H, int W) {
           if (use_tc) plan->tc_flops += po.flops;
         } else if (use_tc) {
           a.sk_scratch = lane_scratch(net, d.lane == 1);
+          if (pool_fuse && d.act == TR_ACT_RELU && d.res < 0 && d.out2 < 0 && !a.shift9 && !a.out_f32 &&
+              sole_consumer_is_next_pool(op_i)) {
+            const tr_op_desc& m = net->ops[op_i + 1];
+            a.pool_out = make_view(B[m.out], m.out_coff, m.out_c);
+          }
           po.tc = conv_tc_plan_create(a);
+          if (a.pool_out.ptr && conv_tc_plan_pooled(po.tc)) skip_next = true;
           plan->tc_flops += po.flops;
           plan->tc_launches++;
         }
