@@ -340,3 +340,40 @@ def test_recognition_ragged_image_list(native, retina, arc):
         # (the two calls embed different batch sizes: other tile shapes and split-K ranges, so
         # the fp32 sums are ordered differently — same tolerance as every embedding comparison)
         assert (ft * want).sum(1).min() > 0.9999 and np.abs(ft - want).max() < 5e-3
+
+
+def test_fused_max_pool_matches_separate_kernel(native, opose, tmp_path):
+    """The 2x2 max-pools fused into the conv epilogues (conv_patch: in-lane maxima, conv_tc: two
+    shuffle rounds) against the separate ``maxpool2_kernel`` (``TRB_POOL_FUSE=0``, read once per
+    process: run in a child) on odd and even map sizes, floor pooling at the ragged border
+    (openpose/model.py:41-58).  Pooling rounded values is exact, but a fused layer picks another
+    tile height (groups must pair up), hence other stream-K split points and another fp32
+    summation order in that conv: the maps agree to fp16 round-off (measured 7e-4 absolute), far
+    below what a wrong window or a dropped border column would give."""
+    import subprocess, sys, os
+    model, _ = opose
+    rng = np.random.default_rng(23)
+    shapes = [(2, 184, 327), (3, 90, 130), (1, 75, 101)]
+    frames = [rng.integers(0, 256, s + (3,), dtype=np.uint8) for s in shapes]
+    np.savez(tmp_path / 'in.npz', *frames)
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "from terran_b200 import synth\n"
+        "from terran_b200.pose.openpose import OpenPose\n"
+        "m = OpenPose(device=torch.device('cuda'), state_dict=synth.openpose_state_dict())\n"
+        f"z = np.load({str(tmp_path / 'in.npz')!r})\n"
+        "out = {}\n"
+        "for k in z.files:\n"
+        "    paf, heat = m.maps(torch.from_numpy(z[k]).cuda())\n"
+        "    out[k + '_paf'], out[k + '_heat'] = paf.cpu().numpy(), heat.cpu().numpy()\n"
+        f"np.savez({str(tmp_path / 'out.npz')!r}, **out)\n")
+    env = dict(os.environ, TRB_POOL_FUSE='0')
+    subprocess.run([sys.executable, '-c', code], check=True, env=env, timeout=600)
+    want = np.load(tmp_path / 'out.npz')
+    assert model.net.stats()['launches'] > 0
+    for i, f in enumerate(frames):
+        paf, heat = model.maps(torch.from_numpy(f).cuda())
+        for got, ref in ((paf.cpu().numpy(), want[f'arr_{i}_paf']), (heat.cpu().numpy(), want[f'arr_{i}_heat'])):
+            assert got.shape == ref.shape
+            assert np.abs(got - ref).max() <= 2e-3 * np.ptp(ref), (i, np.abs(got - ref).max(), np.ptp(ref))
