@@ -240,7 +240,8 @@ def test_resize_matches_cv2(native):
     from terran_b200.frames import resize_short_side
     rng = np.random.default_rng(0)
     for (H, W), short in (((1080, 1920), 416), ((720, 1280), 184), ((640, 640), 416),
-                          ((1080, 1920), 184), ((333, 517), 416), ((97, 61), 184)):
+                          ((1080, 1920), 184), ((333, 517), 416), ((97, 61), 184),
+                          ((2160, 3840), 184), ((300, 401), 184), ((277, 1003), 97)):
         frames = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
         got, scale = resize_short_side(torch.from_numpy(frames).cuda(), short)
         size = (int(W * scale), int(H * scale))
