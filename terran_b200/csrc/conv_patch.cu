@@ -910,7 +910,10 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   p.cin_pad = a.cin_pad; p.kchunks = a.cin_pad / 64; p.in_coff = a.in.coff;
   p.cout_tiles = ceil_div(a.cout_pad, 128);
   p.tiles_per_group = std::max(1, p.cout_tiles / std::max(1, a.groups));
-  p.PA = a.pad == 0 ? 8 : 16;
+  // patch lines hold exactly the 8 + 2 pad pixels a tap's 8-pixel group can touch (the group
+  // stride of the B descriptor need not be a multiple of the 1024-byte swizzle repeat: the
+  // swizzle XORs absolute address bits; TRB_PT_PA16=1 restores 16-pixel lines)
+  p.PA = a.pad == 0 ? 8 : (env_int("TRB_PT_PA16", 0) ? 16 : 8 + 2 * a.pad);
 
   int sms = 0;
   const int dev = current_device();

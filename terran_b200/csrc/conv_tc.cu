@@ -114,6 +114,7 @@ struct TcParams {
   // Fused 2x2 / stride-2 max-pool (halo tiles only: 8 x 16 / 16 x 8 pixels, the four pixels of a
   // window are lanes l, l ^ 1, l ^ 8, l ^ 9 of one epilogue warp): the pooled tensor is written
   // INSTEAD of the full-resolution one.
+  int pw;      // halo patch: pixels per patch line along the 8-pixel axis (8 + 2 pad, or 16)
   int pool;
   __half* pool_out; int pool_cs, pool_coff, pool_H, pool_W;
 };
@@ -394,7 +395,7 @@ __device__ __forceinline__ void mma_issuer_alternate_halo(const TcParams& p, int
   auto pempty_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 8 + b); };
   const int lane_id = threadIdx.x & 31;
   const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
-  const uint32_t halo_hi = umma_desc_hi(2048, p.layout_type);
+  const uint32_t halo_hi = umma_desc_hi(static_cast<uint32_t>(p.pw) * 128u, p.layout_type);
   const uint32_t a_lo0 = umma_desc_lo(ring);
   const uint32_t stage_step = p.stage_bytes >> 4;
   int stage = w % p.stages;
@@ -552,7 +553,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
     // rows_off * 128 B >> 4: what tap (r, s) adds to the patch's descriptor start address
     for (int t = lane; t < p.taps && t < 64; t += 32) {
       const int r = t / p.kw, sx = t - r * p.kw;
-      const uint32_t v = (p.halo == 1 ? r * 16 + sx : sx * 16 + r) * 8u;
+      const uint32_t v = (p.halo == 1 ? r * p.pw + sx : sx * p.pw + r) * 8u;
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_s + 4u * t), "r"(v) : "memory");
     }
   }
@@ -594,7 +595,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
   // the pipe fed.
   auto resident_issuer = [&](int first) {
     const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
-    const uint32_t halo_hi = umma_desc_hi(2048, p.layout_type);
+    const uint32_t halo_hi = umma_desc_hi(static_cast<uint32_t>(p.pw) * 128u, p.layout_type);
     const uint32_t a_lo0 = umma_desc_lo(ring);
     const int step = p.resident;                            // 1 or 2 issuers
     TileWalk walk = walk_begin(p);
@@ -790,7 +791,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
     uint32_t phase = 0, pphase = 0;
     int tile_it = 0;
     const uint32_t desc_hi = umma_desc_hi(p.sbo_bytes, p.layout_type);
-    const uint32_t halo_hi = umma_desc_hi(2048, p.layout_type);   // 16 patch rows per 8-row group step
+    const uint32_t halo_hi = umma_desc_hi(static_cast<uint32_t>(p.pw) * 128u, p.layout_type);   // 16 patch rows per 8-row group step
     const uint32_t a_lo0 = umma_desc_lo(ring);
     const uint32_t stage_step = p.stage_bytes >> 4, sub_step = p.sub_bytes >> 4,
                    b_off = p.a_bytes >> 4;
@@ -1433,6 +1434,11 @@ int num_sms() {
 
 using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const TcParams);
 
+int env_npatch() {
+  static const int n = [] { const char* e = getenv("TRB_TC_NPATCH"); return e ? atoi(e) : 4; }();   // (6 measured no better than 4)
+  return n;
+}
+
 KernelFn kernel_for(int kc, int ctas_per_sm, int mode = 0) {
   KernelFn fn = ctas_per_sm == 2
                     ? (kc == 64 ? conv_tc_kernel<4, 2> : (kc == 32 ? conv_tc_kernel<2, 2> : conv_tc_kernel<1, 2>))
@@ -1579,6 +1585,17 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
       }
     }
   }
+  // Patch lines hold exactly the 8 + 2 pad pixels a tap's 8-pixel group can touch (TRB_TC_PW=16:
+  // lines padded to 16 pixels = a whole number of 1024-byte swizzle repeats per line, the
+  // round-1 layout).  The UMMA group stride then is (8 + 2 pad) * 128 B — not a multiple of the
+  // swizzle repeat, which is fine because the 128B swizzle XORs ABSOLUTE address bits on both
+  // the TMA write and the MMA read (lesson in `Halo mode`): 36 % fewer patch bytes for 3x3.
+  p.pw = 16;
+  {
+    int want = 0;
+    if (const char* e = getenv("TRB_TC_PW")) want = atoi(e);
+    if (p.halo && !p.swap && want != 16) p.pw = 8 + 2 * a.pad;
+  }
   p.rows = p.bw * p.bh * p.bn;
   p.tiles_w = ceil_div(p.W_out, p.bw);
   p.tiles_h = ceil_div(p.H_out, p.bh);
@@ -1646,7 +1663,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   if (const char* s = getenv("TRB_TC_SUB")) p.sub = clamp_sub(atoi(s));
   {
     // two stages (+ the halo patches, parameters, barriers) must fit in the SM's 227 KB
-    const uint32_t patches = p.halo ? 2 * round_up(((p.swap ? p.bw : 16) + 2 * a.pad) * 16 * 128, 1024) : 0;
+    const uint32_t patches = p.halo ? 2 * round_up(((p.swap ? p.bw : 16) + 2 * a.pad) * p.pw * 128, 1024) : 0;
     const uint32_t limit = plan->ctas_per_sm == 2 ? 108u * 1024 : 224u * 1024;
     while (p.sub > 1 && patches + 2u * p.sub * p.sub_bytes + uint32_t(p.param_rows) * p.cout_pad * 4u + 2048u > limit) --p.sub;
   }
@@ -1675,7 +1692,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   }
   const uint32_t param_bytes = uint32_t(p.param_rows) * p.cout_pad * 4u;
   if (p.halo) {
-    p.patch_tx = ((p.swap ? p.bw : 16) + 2 * a.pad) * 16 * 128;
+    p.patch_tx = ((p.swap ? p.bw : 16) + 2 * a.pad) * p.pw * 128;
     p.patch_bytes = round_up(p.patch_tx, 1024);
     p.ring_off = 2 * p.patch_bytes;
     // Resident filters (see TcParams::resident): whole filter bank + >= 3 patch buffers in 227 KB.
@@ -1683,7 +1700,7 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
     if (const char* e = getenv("TRB_TC_RESIDENT")) want = atoi(e);
     const uint32_t bank = uint32_t(p.taps) * p.b_bytes;
     const uint32_t room = 227u * 1024 - 1024 /*alignment*/ - 256 - 8 * (2 * kMaxStages + 12) - 16 - param_bytes;
-    const int npatch = bank < room ? std::min<int>(kMaxStages - 1, std::min<int>(4, (room - bank) / p.patch_bytes)) : 0;
+    const int npatch = bank < room ? std::min<int>(kMaxStages - 1, std::min<int>(env_npatch(), (room - bank) / p.patch_bytes)) : 0;
     if (want && !p.swap && !p.cta2 && p.kchunks == 1 && p.n_tiles == 1 && plan->ctas_per_sm == 1 &&
         p.taps <= 64 && npatch >= 3) {
       p.resident = want >= 2 ? 2 : 1;      // TRB_TC_RESIDENT: 0 off, 1 one issuer (default), 2 two
@@ -1746,12 +1763,12 @@ ConvTcPlan* conv_tc_plan_create(const ConvArgs& a) {
   if (p.halo == 2) {        // dims (C, H, W, N): patch rows run along H
     gdim[0] = cs; gdim[1] = H; gdim[2] = W; gdim[3] = N; gdim[4] = 1;
     gstr[0] = W * cs * 2; gstr[1] = cs * 2; gstr[2] = H * W * cs * 2; gstr[3] = N * H * W * cs * 2;
-    box[0] = p.KC; box[1] = 16; box[2] = (p.swap ? p.bw : 16) + 2 * a.pad; box[3] = 1; box[4] = 1;
+    box[0] = p.KC; box[1] = p.pw; box[2] = (p.swap ? p.bw : 16) + 2 * a.pad; box[3] = 1; box[4] = 1;
   } else if (a.stride == 1) {
     gdim[0] = cs; gdim[1] = W; gdim[2] = H; gdim[3] = N; gdim[4] = 1;
     gstr[0] = cs * 2; gstr[1] = W * cs * 2; gstr[2] = H * W * cs * 2; gstr[3] = N * H * W * cs * 2;
     box[0] = p.KC; box[1] = p.bw; box[2] = p.bh; box[3] = p.bn; box[4] = 1;
-    if (p.halo == 1) { box[1] = 16; box[2] = 16 + 2 * a.pad; box[3] = 1; }
+    if (p.halo == 1) { box[1] = p.pw; box[2] = 16 + 2 * a.pad; box[3] = 1; }
   } else {
     gdim[0] = 2 * cs; gdim[1] = W / 2; gdim[2] = 2; gdim[3] = H / 2; gdim[4] = N;
     gstr[0] = 2 * cs * 2; gstr[1] = W * cs * 2; gstr[2] = 2 * W * cs * 2; gstr[3] = H * W * cs * 2;
