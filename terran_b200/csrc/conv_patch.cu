@@ -66,6 +66,12 @@ struct PatchParams {
   int sub, iters, stages;      // taps per ring stage, stages per chunk, ring depth
   uint32_t stage_bytes, patch_bytes, patch_tx, ring_off;
   int tma_store;               // 1: epilogue transposes through smem and stores with TMA (UTMASTG)
+  // Stacked images (small maps: ArcFace 14x14, 7x7): a tile takes `stack` consecutive images
+  // along the R axis.  The patch holds their (B + 2 pad)-line blocks one after the other, so
+  // the B operand keeps ONE group stride; R = stack * bstride - 2 pad lines are computed, the
+  // 2 pad lines between two images are garbage nobody stores.  N = 8 R instead of 8 B columns
+  // per instruction: 240 instead of 112 for 14x14 maps (whose MMAs were issue-bound).
+  int stack, bstride;          // stack = 1: off; bstride = B + 2 pad
   int pool;                    // 1: 2x2 / stride-2 max-pool fused into the (staged) epilogue: the output
                                // maps describe the POOLED tensor (floor(H/2) x floor(W/2))
   // Stream-K: the CTAs split the launch's (tile, ring iteration) sequence into equal contiguous
@@ -136,7 +142,7 @@ __device__ __forceinline__ TileCoord tile_coord(const PatchParams& p, int tile) 
   int pt = tile - t.ct * p.pix_tiles;
   const int ta = pt % p.tiles_a; pt /= p.tiles_a;
   const int tb = pt % p.tiles_b;
-  t.n = pt / p.tiles_b;
+  t.n = pt / p.tiles_b * p.stack;
   t.a0 = ta * 8;
   t.b0 = tb * p.R;
   return t;
@@ -315,9 +321,15 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_wait(pempty_bar(buf), ((q / p.nbuf) & 1u) ^ 1u, p.err, 5);
         if (elect_one()) {
           mbar_expect_tx(pfull_bar(buf), p.patch_tx);
-          tma_load_4d(base + buf * p.patch_bytes, &tmX, pfull_bar(buf),
-                      p.in_coff + (t.ct / p.tiles_per_group) * p.cin_pad + kc * 64,
-                      t.a0 - p.pad, t.b0 - p.pad, t.n);
+          const int c0 = p.in_coff + (t.ct / p.tiles_per_group) * p.cin_pad + kc * 64;
+          if (p.stack == 1) {
+            tma_load_4d(base + buf * p.patch_bytes, &tmX, pfull_bar(buf), c0, t.a0 - p.pad, t.b0 - p.pad, t.n);
+          } else {
+            // one box per image (an image index beyond the batch is zero-filled and still counted)
+            for (int si = 0; si < p.stack; ++si)
+              tma_load_4d(base + buf * p.patch_bytes + static_cast<uint32_t>(si * p.bstride * p.PA) * 128u, &tmX,
+                          pfull_bar(buf), c0, t.a0 - p.pad, -p.pad, t.n + si);
+          }
         }
         __syncwarp();
       }
@@ -390,6 +402,10 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int per_team = p.R / (p.epi_warps >> 2);
     const int g_begin = team * per_team, g_end = g_begin + per_team;
     const int A_dim = p.axis == 0 ? p.W : p.H, B_dim = p.axis == 0 ? p.H : p.W;
+    // line g of a tile -> (image offset, position along the R axis); a stacked tile has
+    // garbage lines (b >= B_dim) between its images
+    auto line_img = [&](int g) { return p.stack == 1 ? 0 : g / p.bstride; };
+    auto line_b = [&](int b0, int g) { return p.stack == 1 ? b0 + g : g - (g / p.bstride) * p.bstride; };
     const int a_step = p.axis == 0 ? 1 : p.W;             // pixel-index step along the group axis
     const int b_step = p.axis == 0 ? p.W : 1;
     unsigned chunk_ctr = 0;                               // staging slot = chunk_ctr % kStageSlots (across tiles)
@@ -419,7 +435,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int k = 0; k < 9; ++k) s9[k] = (p.shift9 && c_in) ? p.shift9[k * p.cout_pad + cout] : sh;
       }
       auto group_shifts = [&](int g, float& first, float& inner, float& last) {
-        const int b = t.b0 + g;
+        const int b = line_b(t.b0, g);
         const int bc = b == 0 ? 0 : (b >= B_dim - 1 ? 2 : 1);
         if (p.axis == 0) {               // b = output row, the 8-pixel axis runs along columns
           first = bc == 0 ? s9[0] : (bc == 1 ? s9[3] : s9[6]);
@@ -441,9 +457,9 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       // block that starts at group g0 is pixel (g0 + r / 8, r % 8).
       auto res_row_ptr = [&](int g0, int r) -> const __half* {
         const int gg = g0 + (r >> 3), i = r & 7;
-        const int b = t.b0 + gg, a = t.a0 + i;
-        if (gg >= g_end || b >= B_dim || a >= A_dim) return nullptr;
-        const unsigned pix = static_cast<unsigned>(t.n) * p.H * p.W + a * a_step + b * b_step;
+        const int b = line_b(t.b0, gg), a = t.a0 + i, img = t.n + line_img(gg);
+        if (gg >= g_end || b >= B_dim || a >= A_dim || img >= p.N) return nullptr;
+        const unsigned pix = static_cast<unsigned>(img) * p.H * p.W + a * a_step + b * b_step;
         return p.res + static_cast<size_t>(pix) * p.res_cs + p.res_coff + t.ct * 128;
       };
       // one activation formula: y = max(y, 0) + neg * min(y, 0)   (ReLU 0, PReLU slope, none 1)
@@ -716,14 +732,14 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           __syncwarp();
 #pragma unroll
           for (int gg = 0; gg < 2; ++gg) {
-            const int b = t.b0 + g + gg;
-            const bool ok = g + gg < g_end && b < B_dim && !(p.debug & 4);       // warp-uniform
+            const int b = line_b(t.b0, g + gg), img = t.n + line_img(g + gg);
+            const bool ok = g + gg < g_end && b < B_dim && img < p.N && !(p.debug & 4);       // warp-uniform
             const int cw = p.axis == 0 ? t.a0 : b, ch = p.axis == 0 ? b : t.a0;
             if (ok && elect_one())
               asm volatile(
                   "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                   ::"l"(&tmO32), "r"(slot + gg * 512u), "r"(p.out_coff + t.ct * 128 + qd * 32), "r"(cw),
-                    "r"(ch), "r"(t.n) : "memory");
+                    "r"(ch), "r"(img) : "memory");
             __syncwarp();
           }
           if (elect_one()) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -759,15 +775,15 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           // elected lane per instruction
           const int n_rows = p.pool ? p.R >> 1 : p.R;             // staged lines: 4 pooled / 8 pixels each
           for (int r = ew; r < n_rows; r += p.epi_warps) {
-            const int b = p.pool ? (t.b0 >> 1) + r : t.b0 + r;
-            const bool ok = (p.pool ? t.b0 + 2 * r + 1 < B_dim : b < B_dim) && !(p.debug & 4);   // warp-uniform
+            const int b = p.pool ? (t.b0 >> 1) + r : line_b(t.b0, r), img = t.n + (p.pool ? 0 : line_img(r));
+            const bool ok = (p.pool ? t.b0 + 2 * r + 1 < B_dim : b < B_dim && img < p.N) && !(p.debug & 4);   // warp-uniform
             const int a = p.pool ? t.a0 >> 1 : t.a0;
             const int cw = p.axis == 0 ? a : b, ch = p.axis == 0 ? b : a;
             if (ok && elect_one())
               asm volatile(
                   "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                   ::"l"(&tmO), "r"(base + static_cast<uint32_t>(r) * (p.pool ? 1024u : 2048u)),
-                    "r"(p.out_coff + t.ct * 128), "r"(cw), "r"(ch), "r"(t.n) : "memory");
+                    "r"(p.out_coff + t.ct * 128), "r"(cw), "r"(ch), "r"(img) : "memory");
             __syncwarp();
           }
           if (elect_one()) {
@@ -940,14 +956,40 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
     }
   }
   TR_CHECK(best > 0, "no patch tile fits in shared memory");
+  // Stacked images (see PatchParams::stack): small maps whose whole R axis fits several times
+  // into 32 lines.  Staged fp16 epilogue only (the unstaged path and the pooled one keep one
+  // image per tile).
+  p.stack = 1; p.bstride = 0;
+  const bool staged_out = env_int("TRB_PT_TMA_STORE", 1) && !a.out_f32 && !env_int("TRB_PT_DEBUG", 0) &&
+                          !env_int("TRB_PT_GENERIC", 0) && a.out.cs % 8 == 0 && a.out.coff % 8 == 0 &&
+                          (a.cout_store % 128 == 0 || a.out.coff + a.cout_store == a.out.cs) &&
+                          (!a.res.ptr || (a.res.cs % 8 == 0 && a.res.coff % 8 == 0));
+  if (env_int("TRB_PT_STACK", 1) && !env_int("TRB_PT_DUAL", 0) && a.pad > 0 && !a.pool2 && !force_r && staged_out &&
+      p.N >= 2) {
+    for (int axis = 0; axis < 2; ++axis) {
+      if (force_axis >= 0 && axis != force_axis) continue;
+      const int A = axis == 0 ? p.W : p.H, B = axis == 0 ? p.H : p.W;
+      const int bs = B + halo;
+      const int S = std::min(p.N, (32 + halo) / bs);
+      if (S < 2) continue;
+      int R = S * bs - halo;
+      R += R & 1;                                   // (one more garbage line keeps R even)
+      const uint32_t patch = round_up(p.PA * (R + halo) * 128, 1024);
+      if (R > 32 || 2 * patch + 3 * kFilterBlock + kOutStage + 4096 > 227u * 1024) continue;
+      const double util = double(A) / (8.0 * ceil_div(A, 8)) * double(S * B) / double(R);
+      const double wide = std::min(1.0, (8.0 * R + 64.0) / 256.0);
+      const double score = util * wide + 1e-4 * R;
+      if (score > best + 0.02) { best = score; p.axis = axis; p.R = R; p.stack = S; p.bstride = bs; }
+    }
+  }
   p.NP = 8 * p.R;
   const int A = p.axis == 0 ? p.W : p.H, B = p.axis == 0 ? p.H : p.W;
   p.tiles_a = ceil_div(A, 8);
-  p.tiles_b = ceil_div(B, p.R);
-  p.pix_tiles = p.tiles_a * p.tiles_b * p.N;
+  p.tiles_b = p.stack > 1 ? 1 : ceil_div(B, p.R);
+  p.pix_tiles = p.tiles_a * p.tiles_b * ceil_div(p.N, p.stack);
   p.total_tiles = p.pix_tiles * p.cout_tiles;
-  p.patch_tx = p.PA * (p.R + halo) * 128;
-  p.patch_bytes = round_up(p.patch_tx, 1024);
+  p.patch_tx = p.stack > 1 ? p.stack * p.PA * p.bstride * 128 : p.PA * (p.R + halo) * 128;
+  p.patch_bytes = round_up(p.PA * (p.R + halo) * 128, 1024);
   const uint32_t misc = kOutStage + 512 + 8 * (2 * kPMaxStages + 6 + 2 * kPMaxPatchBufs) + 1024 /*alignment*/;
   // Two CTAs per SM when one patch buffer + a filter ring of >= 2 x 16 KB fit in half of the SM's
   // shared memory (TRB_PT_DUAL: 0 never, 1 auto, 2 whenever it fits).
@@ -1003,7 +1045,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   auto encode = patch_encode_fn();
   const cuuint64_t cs = a.in.cs, W = a.in.W, H = a.in.H, N = a.in.N;
   cuuint64_t gdim[4], gstr[3];
-  cuuint32_t box[4] = {64, cuuint32_t(p.PA), cuuint32_t(p.R + halo), 1}, estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {64, cuuint32_t(p.PA), cuuint32_t(p.stack > 1 ? p.bstride : p.R + halo), 1}, estr[4] = {1, 1, 1, 1};
   gdim[0] = cs; gdim[3] = N;
   gstr[2] = H * W * cs * 2;
   if (p.axis == 0) { gdim[1] = W; gdim[2] = H; gstr[0] = cs * 2; gstr[1] = W * cs * 2; }
@@ -1081,6 +1123,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
     const int need = (p.sk ? kModeSK : 0) | (p.shift9 ? kModeS9 : 0) | (p.res ? kModeRes : 0);
     const bool generic = plan->dual || !p.tma_store || p.debug || p.trace || env_int("TRB_PT_GENERIC", 0);
     plan->mode = generic ? kModeAll : (need == 6 ? 7 : need);
+    TR_CHECK(p.stack == 1 || !generic, "stacked tiles need the staged epilogue");
     if (p.pool) {
       TR_CHECK(!generic && !(need & (kModeS9 | kModeRes)) && a.act == ACT_RELU,
                "fused max-pool needs the staged plain ReLU epilogue");

@@ -107,3 +107,15 @@ def test_patch_conv_stream_k_epilogues(native, dual):
     run_case(native, 3, 23, 40, 128, 128, 3, act=0, out_f32=True, env={'TRB_PT_SK': 2, 'TRB_PT_DUAL': dual}, repeat=2)
     run_case(native, 40, 28, 28, 128, 128, 3, act=2, res=True, env={'TRB_PT_DUAL': dual})       # many tiles per CTA
     run_case(native, 32, 23, 40, 128, 128, 7, env={'TRB_PT_SK': 2, 'TRB_PT_SUB': 1, 'TRB_PT_STAGES': 3})
+
+
+@pytest.mark.parametrize('stack', [0, 1], ids=['one-image-per-tile', 'stacked-images'])
+def test_patch_conv_stacked_images(native, stack):
+    """Small maps: several images per tile with garbage lines between them (ArcFace 14x14 and
+    7x7 stages, arcface/model.py:11-35) — odd batch sizes leave the last tile short of images;
+    residual and PReLU go through the line -> (image, row) mapping of the epilogue."""
+    env = {'TRB_PT_STACK': stack}
+    run_case(native, 5, 14, 14, 256, 256, 3, act=0, res=True, env=env)
+    run_case(native, 7, 7, 7, 128, 256, 3, act=2, env=env, seed=2)
+    run_case(native, 3, 14, 9, 64, 128, 5, env=env, seed=3)           # 5x5: bstride 14 + 4
+    run_case(native, 2, 6, 28, 128, 128, 3, act=2, res=True, env=env, seed=4)
