@@ -1012,7 +1012,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
   p.ring_off = p.nbuf * p.patch_bytes;
   const uint32_t budget = plan->dual ? 113u * 1024 : 227u * 1024;
   const uint32_t fixed = p.ring_off + misc;
-  p.sub = std::max(1, std::min(env_int("TRB_PT_SUB", 2), p.taps));
+  p.sub = std::max(1, std::min(env_int("TRB_PT_SUB", 3), p.taps));
   while (p.sub > 1 && fixed + 2u * p.sub * kFilterBlock > budget) --p.sub;
   p.iters = ceil_div(p.taps, p.sub);
   p.stage_bytes = p.sub * kFilterBlock;
