@@ -46,6 +46,7 @@ namespace {
 
 constexpr int kPThreads = 352;            // 8 epilogue warps, one CTA per SM
 constexpr int kPThreadsDual = 224;        // 4 epilogue warps, two CTAs per SM
+constexpr int kPThreadsWide = 480;        // 12 epilogue warps (three teams): short-K layers whose epilogue is the bound
 constexpr int kPMaxStages = 12;
 constexpr int kPMaxPatchBufs = 8;         // patch buffers (2 normally; more for small 1x1 patches)
 constexpr uint32_t kFilterBlock = 128 * 64 * 2;      // one (tap, chunk) filter block: 16 KB
@@ -53,7 +54,7 @@ constexpr uint32_t kFilterBlock = 128 * 64 * 2;      // one (tap, chunk) filter 
 // (1 KB), so that kStageSlots TMA stores of a warp are in flight and a chunk only waits for
 // the store issued kStageSlots chunks earlier.
 constexpr int kStageSlots = 2;
-constexpr uint32_t kOutStage = 8 * kStageSlots * 1024;
+constexpr uint32_t kOutStage = 12 * kStageSlots * 1024;      // (up to 12 epilogue warps)
 
 struct PatchParams {
   int N, H, W;                 // output == input dims (stride 1, "same" padding)
@@ -864,8 +865,9 @@ int env_int(const char* name, int dflt) {
 
 using PatchKernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, PatchParams);
 #define TRB_PATCH_MODES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(7) X(15) X(16) X(17)
-PatchKernel patch_kernel_for(int mode, bool dual) {
+PatchKernel patch_kernel_for(int mode, bool dual, bool wide = false) {
   if (dual) return conv_patch_kernel<kPThreadsDual, 2, kModeAll>;
+  if (wide) return mode == kModePool ? conv_patch_kernel<kPThreadsWide, 1, kModePool> : conv_patch_kernel<kPThreadsWide, 1, 0>;
   switch (mode) {
 #define X(m) case m: return conv_patch_kernel<kPThreads, 1, m>;
     TRB_PATCH_MODES(X)
@@ -879,12 +881,15 @@ void for_each_patch_kernel(F f) {
   TRB_PATCH_MODES(X)
 #undef X
   f(reinterpret_cast<const void*>(conv_patch_kernel<kPThreadsDual, 2, kModeAll>), true);
+  f(reinterpret_cast<const void*>(conv_patch_kernel<kPThreadsWide, 1, 0>), false);
+  f(reinterpret_cast<const void*>(conv_patch_kernel<kPThreadsWide, 1, kModePool>), false);
 }
 
 }  // namespace
 
 struct ConvPatchPlan {
   bool dual = false;
+  bool wide = false;                // 12 epilogue warps (kPThreadsWide)
   int mode = 15;                    // epilogue instantiation (see MODE of conv_patch_kernel)
   unsigned long long* trace = nullptr;
   void* sk_own = nullptr;
@@ -1124,6 +1129,13 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
     const bool generic = plan->dual || !p.tma_store || p.debug || p.trace || env_int("TRB_PT_GENERIC", 0);
     plan->mode = generic ? kModeAll : (need == 6 ? 7 : need);
     TR_CHECK(p.stack == 1 || !generic, "stacked tiles need the staged epilogue");
+    // Twelve epilogue warps (three teams) for plain short-K layers: their epilogue (~3 us per
+    // 192..256-pixel tile with eight warps) is longer than their MMAs.
+    const int wide_k = env_int("TRB_PT_WIDE_K", 18);
+    if (!generic && env_int("TRB_PT_WIDE", 1) && need == 0 && p.R % 6 == 0 && p.kchunks * p.taps <= wide_k) {
+      plan->wide = true;
+      p.epi_warps = 12;
+    }
     if (p.pool) {
       TR_CHECK(!generic && !(need & (kModeS9 | kModeRes)) && a.act == ACT_RELU,
                "fused max-pool needs the staged plain ReLU epilogue");
@@ -1172,7 +1184,7 @@ void conv_patch_launch(const ConvPatchPlan* plan, cudaStream_t s) {
   static const bool pdl = env_int("TRB_TC_PDL", 1) != 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(plan->grid);
-  cfg.blockDim = dim3(plan->dual ? kPThreadsDual : kPThreads);
+  cfg.blockDim = dim3(plan->dual ? kPThreadsDual : plan->wide ? kPThreadsWide : kPThreads);
   cfg.dynamicSmemBytes = plan->smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -1180,7 +1192,7 @@ void conv_patch_launch(const ConvPatchPlan* plan, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  TR_CUDA(cudaLaunchKernelEx(&cfg, patch_kernel_for(plan->mode, plan->dual), plan->tmX, plan->tmW, plan->tmO,
+  TR_CUDA(cudaLaunchKernelEx(&cfg, patch_kernel_for(plan->mode, plan->dual, plan->wide), plan->tmX, plan->tmW, plan->tmO,
                              plan->tmO32, plan->p));
 }
 
