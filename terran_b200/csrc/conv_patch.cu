@@ -400,8 +400,11 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int ew = warp - 2;
     const int qd = warp & 3;                 // TMEM lane quarter this warp may access
     const int team = ew >> 2;                // teams of four warps split the pixel groups
-    const int per_team = p.R / (p.epi_warps >> 2);
-    const int g_begin = team * per_team, g_end = g_begin + per_team;
+    // the R / 2 chunks (pairs of lines) are dealt to the teams as evenly as possible
+    const int n_teams = p.epi_warps >> 2, chunks = p.R >> 1;
+    const int c_base = chunks / n_teams, c_rem = chunks - c_base * n_teams;
+    const int g_begin = 2 * (team * c_base + min(team, c_rem));
+    const int g_end = g_begin + 2 * (c_base + (team < c_rem ? 1 : 0));
     const int A_dim = p.axis == 0 ? p.W : p.H, B_dim = p.axis == 0 ? p.H : p.W;
     // line g of a tile -> (image offset, position along the R axis); a stacked tile has
     // garbage lines (b >= B_dim) between its images
@@ -1132,7 +1135,7 @@ ConvPatchPlan* conv_patch_plan_create(const ConvArgs& a, int* err_flag) {
     // Twelve epilogue warps (three teams) for plain short-K layers: their epilogue (~3 us per
     // 192..256-pixel tile with eight warps) is longer than their MMAs.
     const int wide_k = env_int("TRB_PT_WIDE_K", 18);
-    if (!generic && env_int("TRB_PT_WIDE", 1) && need == 0 && p.R % 6 == 0 && p.kchunks * p.taps <= wide_k) {
+    if (!generic && env_int("TRB_PT_WIDE", 1) && need == 0 && p.R >= 6 && p.kchunks * p.taps <= wide_k) {
       plan->wide = true;
       p.epi_warps = 12;
     }
