@@ -15,3 +15,29 @@ def cuda_index(device):
             'terran_b200 runs on a B200 GPU only: got device '
             f'{device} (there is no CPU fallback)')
     return device.index if device.index is not None else torch.cuda.current_device()
+
+
+#: How host threads wait for results: False = the CUDA default (the waiting thread spins on the
+#: event, lowest latency), True = blocking waits (the thread sleeps until the driver's interrupt).
+#: ``None`` (default) decides per process in ``completion_event``: blocking when the ranks of
+#: this box reach a quarter of the CPUs they may run on — spinning waits of many ranks then
+#: take the cores the feeder threads and the result unpacking need.
+blocking_events = None
+
+
+def completion_event():
+    """Event a host thread will ``synchronize()`` on for the results of a batch."""
+    import os
+    mode = blocking_events
+    if mode is None:
+        env = os.environ.get('TRB_BLOCKING_SYNC')
+        if env is not None:
+            mode = env not in ('0', '')
+        else:
+            ranks = int(os.environ.get('LOCAL_WORLD_SIZE', '1'))
+            try:
+                cpus = len(os.sched_getaffinity(0))
+            except (AttributeError, OSError):
+                cpus = os.cpu_count() or 1
+            mode = ranks * 4 >= cpus
+    return torch.cuda.Event(blocking=bool(mode))

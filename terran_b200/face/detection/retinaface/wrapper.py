@@ -14,7 +14,7 @@ import torch
 
 from terran_b200 import _native as nat
 from terran_b200.checkpoint import get_checkpoint_path
-from terran_b200.defaults import cuda_index, default_device
+from terran_b200.defaults import completion_event, cuda_index, default_device
 from terran_b200.frames import to_device_u8
 from terran_b200.weights import Net, retinaface_program
 
@@ -107,7 +107,7 @@ class RetinaFace:
         slot = self._host_slot(N, max_det)
         slot['count'].copy_(count, non_blocking=True)
         slot['det'].copy_(det, non_blocking=True)
-        done = torch.cuda.Event()
+        done = completion_event()
         done.record()
         self.last_candidates = cand
         return PendingDetections(self, frames, threshold, max_det, slot, done, count, det)

@@ -15,7 +15,7 @@ import threading
 import numpy as np
 import torch
 
-from terran_b200.defaults import cuda_index, default_device
+from terran_b200.defaults import completion_event, cuda_index, default_device
 
 
 class FrameFeeder:
@@ -55,7 +55,7 @@ class FrameFeeder:
                     slot += 1
                 with torch.cuda.stream(stream):
                     dev = t.to(f'cuda:{self.device_index}', non_blocking=True)
-                    done = torch.cuda.Event()
+                    done = completion_event()
                     done.record(stream)
                 self.queue.put((dev, done))
         finally:
@@ -139,7 +139,7 @@ class PerceptionPipeline:
             features, counts = rec.model.embed_detections(dev_frames, pending, det_handle.scale)
             host = torch.empty(features.shape, dtype=torch.float32).pin_memory()
             host.copy_(features, non_blocking=True)
-            done = torch.cuda.Event()
+            done = completion_event()
             done.record()
 
         def finish():

@@ -15,7 +15,7 @@ import torch
 
 from terran_b200 import _native as nat
 from terran_b200.checkpoint import get_checkpoint_path
-from terran_b200.defaults import cuda_index, default_device
+from terran_b200.defaults import completion_event, cuda_index, default_device
 from terran_b200.frames import resize_short_side, to_device_u8
 from terran_b200.weights import Net, openpose_program
 
@@ -144,7 +144,7 @@ class OpenPose:
         slot['status'].copy_(status, non_blocking=True)
         slot['kps'].copy_(kps, non_blocking=True)
         slot['score'].copy_(score, non_blocking=True)
-        done = torch.cuda.Event()
+        done = completion_event()
         done.record()
         return PendingPoses(slot, done)
 
