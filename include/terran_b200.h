@@ -205,6 +205,24 @@ int tr_l2_normalize(const float* in_dev, float* out_dev, int N, int D, void* str
 int tr_face_align(const uint8_t* frames_dev, int H, int W, const double* coef_dev,
                   const int32_t* image_index_dev, int F, uint8_t* out_dev, int side, void* stream);
 
+/* Faces given WITHOUT landmarks: replaces preprocess_face_no_landmarks of arcface/wrapper.py:75-99
+ * (PIL Image.resize to longer side `side` — Pillow's antialiased BICUBIC for RGB — centred on a
+ * zero canvas, channels BGR), bit-exact with Pillow's 8-bit resampler.  n RGB HWC uint8 images of
+ * any size lie back to back in pixels_dev; offsets_host[i] is the byte offset of image i and
+ * sizes_host[2i], sizes_host[2i+1] its height and width (both arrays on the HOST: the fixed-point
+ * filter tables are built on the host from the sizes).  out_dev: (n,3,side,side) uint8.
+ * workspace_dev: tr_face_letterbox_workspace_bytes(sizes_host, n, side) bytes (0 = bad sizes;
+ * tr_last_error says why).  An image so thin that its resized shorter side is 0 pixels is an
+ * error, as in Pillow ("height and width must be > 0"). */
+size_t tr_face_letterbox_workspace_bytes(const int32_t* sizes_host, int n, int side);
+int tr_face_letterbox(const uint8_t* pixels_dev, const int64_t* offsets_host, const int32_t* sizes_host,
+                      int n, int side, void* workspace_dev, uint8_t* out_dev, void* stream);
+/* Host-only helper (no GPU needed): Pillow's bicubic filter table of one axis, as the kernels
+ * use it.  bounds_host: out_size x (first input sample, count); coeffs_host: out_size x ksize
+ * int32 weights with 22 fractional bits.  Returns ksize (also when both pointers are NULL, to
+ * size the buffers), -1 on error. */
+int tr_resample_table(int in_size, int out_size, int32_t* bounds_host, int32_t* coeffs_host);
+
 /* The 2x3 inverse similarity (PIL AFFINE data) of every detected face, computed on the device
  * from the detection rows of tr_retinaface_detect (so detect -> align -> embed needs no host
  * round trip for landmarks): landmarks are mapped back to frame pixels as Detection.resize_out

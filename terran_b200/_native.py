@@ -22,6 +22,7 @@ SYMBOLS = (
     'tr_conv2d', 'tr_sepconv2d',
     'tr_detect_workspace_bytes', 'tr_retinaface_decode_nms', 'tr_retinaface_detect',
     'tr_l2_normalize', 'tr_face_align', 'tr_face_similarity',
+    'tr_face_letterbox_workspace_bytes', 'tr_face_letterbox', 'tr_resample_table',
     'tr_pose_workspace_bytes', 'tr_openpose_parse', 'tr_bicubic_table',
     'tr_resize_bilinear_u8',
 )
@@ -123,6 +124,10 @@ def lib():
         L.tr_pose_workspace_bytes.argtypes = [i32]
         L.tr_pose_workspace_bytes.restype = C.c_size_t
         L.tr_openpose_parse.argtypes = [vp, vp, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp]
+        L.tr_face_letterbox_workspace_bytes.argtypes = [vp, i32, i32]
+        L.tr_face_letterbox_workspace_bytes.restype = C.c_size_t
+        L.tr_face_letterbox.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+        L.tr_resample_table.argtypes = [i32, i32, vp, vp]
         L.tr_bicubic_table.argtypes = [C.POINTER(f32)]
         L.tr_bicubic_table.restype = None
         L.tr_resize_bilinear_u8.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp]

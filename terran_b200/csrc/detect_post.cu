@@ -8,6 +8,10 @@
 // IoU is compared against the threshold as a double like torchvision's CPU nms.
 #include "detect_post.cuh"
 
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 namespace trb {
 
 namespace {
@@ -411,6 +415,223 @@ void face_align_launch(const uint8_t* frames, int H, int W, const double* coef,
   if (F == 0) return;
   TR_CHECK(S <= 128, "crop side");
   face_align_kernel<<<dim3(S, F), 128, 0, s>>>(frames, H, W, coef, image_index, out, S);
+  TR_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// Faces given WITHOUT landmarks (arcface/wrapper.py:75-99): the image is resized so that its
+// longer side is 112 with PIL's default Image.resize — for RGB images Pillow's antialiased
+// BICUBIC resampler — and centred on a zero 112x112 canvas, channels BGR.  Pillow's 8-bit
+// resampler (Resample.c) is integer arithmetic on precomputed fixed-point tables, so the device
+// version is bit-exact with it:
+//   * per axis and output sample: the window [first, first + count) of input samples under the
+//     filter (support 2 * max(1, in/out)), bicubic weights (a = -0.5) evaluated in double,
+//     normalised by their sum, rounded half away from zero to 22 fractional bits;
+//   * horizontal pass over all rows, result rounded to uint8 ((acc + 2^21) >> 22, clamped),
+//     then the vertical pass over that intermediate image, rounded the same way.
+// The tables depend only on (input size, output size): the host builds them in double exactly
+// as Pillow does and ships them with the per-image descriptors in one small upload.
+// ---------------------------------------------------------------------------
+namespace {
+
+constexpr int kResampleBits = 32 - 8 - 2;
+
+inline double pil_bicubic(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+struct LetterDesc {
+  long long pix_off, tmp_off;          // bytes into the pixel blob / into the intermediate area
+  int h, w, oh, ow, x_min, y_min;
+  int kh_off, bh_off, ksize_h;         // int32 offsets into the table area
+  int kv_off, bv_off, ksize_v;
+};
+
+__device__ __forceinline__ uint8_t resample_round(int acc) {
+  return static_cast<uint8_t>(min(max(acc >> kResampleBits, 0), 255));
+}
+
+__global__ void __launch_bounds__(256)
+letterbox_rows_kernel(const uint8_t* __restrict__ pixels, const LetterDesc* __restrict__ descs,
+                      const int* __restrict__ tables, uint8_t* __restrict__ tmp) {
+  const LetterDesc d = descs[blockIdx.y];
+  const long idx = static_cast<long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= static_cast<long>(d.h) * d.ow) return;
+  const int row = static_cast<int>(idx / d.ow), x = static_cast<int>(idx % d.ow);
+  const int first = tables[d.bh_off + 2 * x], count = tables[d.bh_off + 2 * x + 1];
+  const int* k = tables + d.kh_off + x * d.ksize_h;
+  const uint8_t* src = pixels + d.pix_off + (static_cast<long>(row) * d.w + first) * 3;
+  int a0 = 1 << (kResampleBits - 1), a1 = a0, a2 = a0;
+  for (int i = 0; i < count; ++i) {
+    const int c = k[i];
+    a0 += src[3 * i] * c;
+    a1 += src[3 * i + 1] * c;
+    a2 += src[3 * i + 2] * c;
+  }
+  uint8_t* o = tmp + d.tmp_off + idx * 3;
+  o[0] = resample_round(a0);
+  o[1] = resample_round(a1);
+  o[2] = resample_round(a2);
+}
+
+__global__ void __launch_bounds__(128)
+letterbox_cols_kernel(const LetterDesc* __restrict__ descs, const int* __restrict__ tables,
+                      const uint8_t* __restrict__ tmp, uint8_t* __restrict__ out, int S) {
+  const LetterDesc d = descs[blockIdx.y];
+  const int y = blockIdx.x, x = threadIdx.x;
+  if (x >= S) return;
+  const int ox = x - d.x_min, oy = y - d.y_min;
+  uint8_t px[3] = {0, 0, 0};
+  if (ox >= 0 && ox < d.ow && oy >= 0 && oy < d.oh) {
+    const int first = tables[d.bv_off + 2 * oy], count = tables[d.bv_off + 2 * oy + 1];
+    const int* k = tables + d.kv_off + oy * d.ksize_v;
+    const uint8_t* src = tmp + d.tmp_off + (static_cast<long>(first) * d.ow + ox) * 3;
+    int a0 = 1 << (kResampleBits - 1), a1 = a0, a2 = a0;
+    for (int i = 0; i < count; ++i) {
+      const int c = k[i];
+      const uint8_t* p = src + static_cast<long>(i) * d.ow * 3;
+      a0 += p[0] * c;
+      a1 += p[1] * c;
+      a2 += p[2] * c;
+    }
+    px[0] = resample_round(a0);
+    px[1] = resample_round(a1);
+    px[2] = resample_round(a2);
+  }
+  uint8_t* o = out + static_cast<long>(blockIdx.y) * 3 * S * S + static_cast<long>(y) * S + x;
+  o[0] = px[2];
+  o[static_cast<long>(S) * S] = px[1];
+  o[2L * S * S] = px[0];
+}
+
+int resample_ksize(int in_size, int out_size) {
+  double filterscale = static_cast<double>(in_size) / out_size;
+  if (filterscale < 1.0) filterscale = 1.0;
+  return static_cast<int>(std::ceil(2.0 * filterscale)) * 2 + 1;
+}
+
+struct LetterGeometry { int oh, ow, x_min, y_min; };
+
+LetterGeometry letter_geometry(int h, int w, int S) {
+  // (reference :77-83) scale on the longer side, int() truncation, centred
+  const double scale = static_cast<double>(S) / (w > h ? w : h);
+  LetterGeometry g;
+  g.ow = static_cast<int>(w * scale);
+  g.oh = static_cast<int>(h * scale);
+  g.x_min = static_cast<int>((S - g.ow) / 2.0);
+  g.y_min = static_cast<int>((S - g.oh) / 2.0);
+  return g;
+}
+
+size_t align16(size_t v) { return (v + 15) & ~static_cast<size_t>(15); }
+
+}  // namespace
+
+int resample_table_host(int in_size, int out_size, int* bounds, int* coeffs) {
+  TR_CHECK(in_size > 0 && out_size > 0, "resample sizes");
+  const double scale = static_cast<double>(in_size) / out_size;
+  double filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 2.0 * filterscale;
+  const int ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+  if (!bounds || !coeffs) return ksize;
+  std::vector<double> w(ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    const double ss = 1.0 / filterscale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      w[x] = pil_bicubic((x + xmin - center + 0.5) * ss);
+      ww += w[x];
+    }
+    int* k = coeffs + static_cast<long>(xx) * ksize;
+    for (int x = 0; x < ksize; ++x) {
+      if (x >= xmax) { k[x] = 0; continue; }
+      const double v = ww != 0.0 ? w[x] / ww : w[x];
+      k[x] = v < 0 ? static_cast<int>(-0.5 + v * (1 << kResampleBits))
+                   : static_cast<int>(0.5 + v * (1 << kResampleBits));
+    }
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+  return ksize;
+}
+
+namespace {
+
+// Sizes of the three workspace areas for a list of images (sizes: n x (height, width)).
+struct LetterLayout { size_t desc_bytes, table_ints, tmp_bytes; };
+
+LetterLayout letter_layout(const int* sizes, int n, int S) {
+  LetterLayout L{align16(sizeof(LetterDesc) * static_cast<size_t>(n)), 0, 0};
+  for (int i = 0; i < n; ++i) {
+    const int h = sizes[2 * i], w = sizes[2 * i + 1];
+    TR_CHECK(h > 0 && w > 0, "image " + std::to_string(i) + " is empty");
+    const LetterGeometry g = letter_geometry(h, w, S);
+    TR_CHECK(g.ow > 0 && g.oh > 0, "height and width must be > 0 (image " + std::to_string(i) + " is too thin)");
+    L.table_ints += static_cast<size_t>(g.ow) * (resample_ksize(w, g.ow) + 2)
+                  + static_cast<size_t>(g.oh) * (resample_ksize(h, g.oh) + 2);
+    L.tmp_bytes += align16(static_cast<size_t>(h) * g.ow * 3);
+  }
+  return L;
+}
+
+}  // namespace
+
+size_t face_letterbox_workspace_bytes(const int* sizes, int n, int S) {
+  const LetterLayout L = letter_layout(sizes, n, S);
+  return L.desc_bytes + align16(L.table_ints * 4) + L.tmp_bytes;
+}
+
+void face_letterbox_launch(const uint8_t* pixels, const long long* offsets, const int* sizes, int n,
+                           int S, void* workspace, uint8_t* out, cudaStream_t s) {
+  if (n == 0) return;
+  TR_CHECK(S <= 128, "crop side");
+  const LetterLayout L = letter_layout(sizes, n, S);
+  const size_t head_bytes = L.desc_bytes + align16(L.table_ints * 4);
+  std::vector<char> head(head_bytes, 0);
+  LetterDesc* descs = reinterpret_cast<LetterDesc*>(head.data());
+  int* tables = reinterpret_cast<int*>(head.data() + L.desc_bytes);
+  size_t t = 0, tmp_off = 0;
+  long max_elems = 0;
+  for (int i = 0; i < n; ++i) {
+    const int h = sizes[2 * i], w = sizes[2 * i + 1];
+    const LetterGeometry g = letter_geometry(h, w, S);
+    LetterDesc& d = descs[i];
+    d.pix_off = offsets[i];
+    d.tmp_off = static_cast<long long>(tmp_off);
+    d.h = h; d.w = w; d.oh = g.oh; d.ow = g.ow; d.x_min = g.x_min; d.y_min = g.y_min;
+    d.ksize_h = resample_ksize(w, g.ow);
+    d.bh_off = static_cast<int>(t); t += 2 * static_cast<size_t>(g.ow);
+    d.kh_off = static_cast<int>(t); t += static_cast<size_t>(g.ow) * d.ksize_h;
+    resample_table_host(w, g.ow, tables + d.bh_off, tables + d.kh_off);
+    d.ksize_v = resample_ksize(h, g.oh);
+    d.bv_off = static_cast<int>(t); t += 2 * static_cast<size_t>(g.oh);
+    d.kv_off = static_cast<int>(t); t += static_cast<size_t>(g.oh) * d.ksize_v;
+    resample_table_host(h, g.oh, tables + d.bv_off, tables + d.kv_off);
+    tmp_off += align16(static_cast<size_t>(h) * g.ow * 3);
+    max_elems = std::max(max_elems, static_cast<long>(h) * g.ow);
+  }
+  TR_CHECK(t == L.table_ints, "table layout");
+  char* ws = static_cast<char*>(workspace);
+  // pageable source: the runtime stages it before returning, so `head` may go out of scope
+  TR_CUDA(cudaMemcpyAsync(ws, head.data(), head_bytes, cudaMemcpyHostToDevice, s));
+  const LetterDesc* ddesc = reinterpret_cast<const LetterDesc*>(ws);
+  const int* dtab = reinterpret_cast<const int*>(ws + L.desc_bytes);
+  uint8_t* dtmp = reinterpret_cast<uint8_t*>(ws + head_bytes);
+  letterbox_rows_kernel<<<dim3(static_cast<unsigned>((max_elems + 255) / 256), n), 256, 0, s>>>(
+      pixels, ddesc, dtab, dtmp);
+  TR_CUDA(cudaGetLastError());
+  letterbox_cols_kernel<<<dim3(S, n), 128, 0, s>>>(ddesc, dtab, dtmp, out, S);
   TR_CUDA(cudaGetLastError());
 }
 

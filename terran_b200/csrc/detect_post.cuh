@@ -46,4 +46,12 @@ void face_similarity_launch(const float* det, const int* count, int N, int max_d
 void face_align_launch(const uint8_t* frames, int H, int W, const double* coef,
                        const int* image_index, int F, uint8_t* out, int S, cudaStream_t s);
 
+// ---- faces without landmarks (PIL-exact antialiased bicubic resize to max side S, centred on a
+//      zero canvas, (n,3,S,S) BGR).  sizes: n x (height, width) and offsets: n byte offsets of the
+//      RGB HWC images inside `pixels`, both on the HOST; pixels / workspace / out on the device.
+int resample_table_host(int in_size, int out_size, int* bounds, int* coeffs);
+size_t face_letterbox_workspace_bytes(const int* sizes, int n, int S);
+void face_letterbox_launch(const uint8_t* pixels, const long long* offsets, const int* sizes, int n,
+                           int S, void* workspace, uint8_t* out, cudaStream_t s);
+
 }  // namespace trb

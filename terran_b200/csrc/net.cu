@@ -853,6 +853,26 @@ int tr_face_similarity(const float* det_dev, const int32_t* count_dev, int N, in
   });
 }
 
+int tr_resample_table(int in_size, int out_size, int32_t* bounds_host, int32_t* coeffs_host) {
+  int ksize = -1;
+  const int rc = guarded([&] { ksize = resample_table_host(in_size, out_size, bounds_host, coeffs_host); });
+  return rc ? -1 : ksize;
+}
+
+size_t tr_face_letterbox_workspace_bytes(const int32_t* sizes_host, int n, int side) {
+  size_t bytes = 0;
+  guarded([&] { bytes = face_letterbox_workspace_bytes(sizes_host, n, side); });
+  return bytes;
+}
+
+int tr_face_letterbox(const uint8_t* pixels_dev, const int64_t* offsets_host, const int32_t* sizes_host,
+                      int n, int side, void* workspace_dev, uint8_t* out_dev, void* stream) {
+  return guarded([&] {
+    face_letterbox_launch(pixels_dev, reinterpret_cast<const long long*>(offsets_host), sizes_host, n,
+                          side, workspace_dev, out_dev, static_cast<cudaStream_t>(stream));
+  });
+}
+
 size_t tr_pose_workspace_bytes(int N) { return pose_workspace_bytes(N); }
 
 int tr_openpose_parse(const float* paf_dev, const float* heat_dev, int N, int h, int w, double scale,

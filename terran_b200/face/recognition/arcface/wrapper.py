@@ -6,17 +6,18 @@ returning L2-normalised 512-d float32 embeddings, split per image when faces
 are given.  The ResNet forward, the final FC + BatchNorm1d and the L2
 normalisation (done on the host with sklearn upstream) run in the native library.
 
-Face alignment: the 2x3 similarity per face is estimated on the host (closed-form
-Umeyama, what ``skimage.transform.SimilarityTransform.estimate`` implements — 5
-points per face); the affine bilinear warp to the 112x112 crop runs on the GPU
-(``tr_face_align``, bit-exact with the PIL warp upstream uses) when the frames
-come as one batch, and through PIL exactly as upstream otherwise.
+Face alignment: the 2x3 similarity per face is estimated in closed form (what
+``skimage.transform.SimilarityTransform.estimate`` computes for five 2-D points) — on the device
+from the detection rows in the pipeline (``tr_face_similarity``), on the host from the face dicts
+in ``call`` — and the affine bilinear warp to the 112x112 crop runs on the GPU (``tr_face_align``,
+bit-exact with the PIL warp upstream uses), for batches and for lists of differently sized images.
+Faces given without landmarks are resized and centre-padded on the GPU too
+(``tr_face_letterbox``, bit-exact with PIL's ``Image.resize``): there is no host image path.
 """
 import ctypes as C
 
 import numpy as np
 import torch
-from PIL import Image
 
 from terran_b200 import _native as nat
 from terran_b200.checkpoint import get_checkpoint_path
@@ -58,19 +59,6 @@ def similarity_coefficients(landmarks, image_size=(112, 112)):
         out = np.stack([c / s, sn / s, -(c * t0 + sn * t1) / s,
                         -sn / s, c / s, -(-sn * t0 + c * t1) / s], axis=1)
     out[~((var > 0) & (nrm > 0))] = np.nan
-    return out
-
-
-def preprocess_face_no_landmarks(image, image_side=112):
-    """Resize to max side 112 and centre-pad (reference :75-99)."""
-    face = Image.fromarray(image)
-    scale = image_side / max(face.size[0], face.size[1])
-    face = face.resize((int(face.size[0] * scale), int(face.size[1] * scale)))
-    x_min = int((image_side - face.size[0]) / 2)
-    y_min = int((image_side - face.size[1]) / 2)
-    out = np.zeros((3, image_side, image_side), dtype=np.uint8)
-    out[:, y_min:y_min + face.size[1], x_min:x_min + face.size[0]] = (
-        np.asarray(face).transpose([2, 0, 1])[::-1, ...])
     return out
 
 
@@ -137,6 +125,38 @@ class ArcFace:
                 nat.current_stream_ptr()))
         return out
 
+    def letterbox_device(self, images):
+        """Faces without landmarks (reference ``preprocess_face_no_landmarks`` :75-99): a list of
+        (h,w,3) uint8 RGB arrays of any size -> (n,3,112,112) uint8 BGR CUDA crops, each image
+        resized to longer side 112 (PIL's default antialiased bicubic, bit-exact) and centred on
+        a zero canvas — one upload of all pixels, two kernels (``tr_face_letterbox``)."""
+        S = self.image_side
+        images = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        for im in images:
+            if im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError(f'expected (h, w, 3) uint8 RGB images, got shape {im.shape}')
+            if min(int(im.shape[1] * (S / max(im.shape[:2]))), int(im.shape[0] * (S / max(im.shape[:2])))) < 1:
+                raise ValueError('height and width must be > 0')        # (PIL's own error)
+        n = len(images)
+        sizes = np.array([im.shape[:2] for im in images], np.int32).reshape(n, 2)
+        nbytes = np.array([im.size for im in images], np.int64)
+        offsets = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.int64)
+        blob = torch.empty(int(nbytes.sum()), dtype=torch.uint8).pin_memory()
+        flat = blob.numpy()
+        for im, off in zip(images, offsets):
+            flat[off:off + im.size] = im.reshape(-1)
+        dev = torch.device('cuda', self.device_index)
+        pixels = blob.to(dev, non_blocking=True)
+        need = nat.lib().tr_face_letterbox_workspace_bytes(sizes.ctypes.data, n, S)
+        if need == 0:
+            raise nat.NativeError(nat.lib().tr_last_error().decode())
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        out = torch.empty((n, 3, S, S), dtype=torch.uint8, device=dev)
+        nat.check(nat.lib().tr_face_letterbox(
+            C.c_void_p(pixels.data_ptr()), offsets.ctypes.data, sizes.ctypes.data, n, S,
+            C.c_void_p(ws.data_ptr()), C.c_void_p(out.data_ptr()), nat.current_stream_ptr()))
+        return out
+
     def embed_detections(self, frames, pending, scale):
         """Device-resident detect -> align -> embed: ``pending`` is the ``PendingDetections`` of
         ``RetinaFace.detect_async`` on (the resized copy of) ``frames`` (CUDA uint8 (N,H,W,3)),
@@ -188,41 +208,27 @@ class ArcFace:
                 features = self.embed_device(crops, 'nchw_bgr').cpu().numpy()
             splits = np.cumsum(list(map(len, faces_per_image)))[:-1]
             return np.split(features, splits, axis=0)
-        fast = faces_per_image is None and all(
-            getattr(im, 'shape', None) == (S, S, 3) for im in images)
-        if fast and len(images):
-            batch = np.ascontiguousarray(np.stack(images, 0))
-            layout = 'nhwc_rgb'
-            splits = []
-        else:
-            pre = []
-            if faces_per_image is not None:
-                # Differently sized images: each one is uploaded and its faces are warped on the
-                # GPU (the same bit-exact ``tr_face_align`` as the batched path) — no host PIL warp.
-                if not any(len(f) for f in faces_per_image):
-                    return [np.empty((0, 512)) for _ in images]
-                from terran_b200.frames import to_device_u8
-                with torch.cuda.device(self.device_index):
-                    crops = [self.align_device(to_device_u8(np.asarray(image)[None], self.device_index), [faces])
-                             for image, faces in zip(images, faces_per_image) if len(faces)]
-                    features = self.embed_device(torch.cat(crops, 0), 'nchw_bgr').cpu().numpy()
-                splits = np.cumsum(list(map(len, faces_per_image)))[:-1]
-                return np.split(features, splits, axis=0)
-            else:
-                for image in images:
-                    pre.append(preprocess_face_no_landmarks(image, S))
-                splits = []
-            if not pre:
-                # upstream returns float64 here (np.empty default dtype)
+        if faces_per_image is not None:
+            # Differently sized images: each one is uploaded and its faces are warped on the
+            # GPU (the same bit-exact ``tr_face_align`` as the batched path) — no host PIL warp.
+            if not any(len(f) for f in faces_per_image):
                 return [np.empty((0, 512)) for _ in images]
-            batch = np.ascontiguousarray(np.stack(pre, axis=0))
-            layout = 'nchw_bgr'
-
+            from terran_b200.frames import to_device_u8
+            with torch.cuda.device(self.device_index):
+                crops = [self.align_device(to_device_u8(np.asarray(image)[None], self.device_index), [faces])
+                         for image, faces in zip(images, faces_per_image) if len(faces)]
+                features = self.embed_device(torch.cat(crops, 0), 'nchw_bgr').cpu().numpy()
+            splits = np.cumsum(list(map(len, faces_per_image)))[:-1]
+            return np.split(features, splits, axis=0)
+        # No landmarks: the images ARE the faces, returned as one (n,512) array (:150-183).
+        if not len(images):
+            return [np.empty((0, 512)) for _ in images]      # (upstream: float64 empties, here [])
         with torch.cuda.device(self.device_index):
-            dev = torch.from_numpy(batch).pin_memory().to(f'cuda:{self.device_index}',
-                                                          non_blocking=True)
-            features = self.embed_device(dev, layout).cpu().numpy()
-        per_image = np.split(features, splits, axis=0)
-        if faces_per_image is None:
-            per_image = per_image[0]
-        return per_image
+            if all(getattr(im, 'shape', None) == (S, S, 3) for im in images):
+                # already 112x112: PIL's resize would be the identity; straight to the stem
+                batch = np.ascontiguousarray(np.stack(images, 0))
+                dev = torch.from_numpy(batch).pin_memory().to(f'cuda:{self.device_index}',
+                                                              non_blocking=True)
+                return self.embed_device(dev, 'nhwc_rgb').cpu().numpy()
+            # any other size: resized + centre-padded on the GPU (``tr_face_letterbox``)
+            return self.embed_device(self.letterbox_device(images), 'nchw_bgr').cpu().numpy()

@@ -315,6 +315,38 @@ def test_gpu_face_alignment_matches_pil(native, arc):
     assert [o.shape for o in rec(frames, [[], []])] == [(0, 512), (0, 512)]
 
 
+def test_gpu_face_letterbox_matches_pil(native, arc):
+    """tr_face_letterbox == the reference's preprocess_face_no_landmarks (PIL Image.resize to longer
+    side 112 + centre pad + BGR, arcface/wrapper.py:75-99) bit for bit on images of many sizes
+    (down- and up-scaled, wide, tall, one pixel thin after resizing, already 112), and
+    Recognition on such a list == the embeddings of the PIL-prepared crops."""
+    from oracle.letterbox import preprocess_face_no_landmarks
+    from terran_b200.face.recognition import Recognition
+    model, _ = arc
+    rng = np.random.default_rng(11)
+    shapes = [(112, 112), (224, 224), (57, 41), (300, 181), (181, 300), (1080, 1920), (9, 640),
+              (640, 9), (3, 5), (111, 113), (113, 111), (1, 1), (517, 512), (2000, 37)]
+    images = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    # smooth content too: rounding of long filter windows on gradients, saturation at 0 / 255
+    yy, xx = np.mgrid[0:333, 0:471]
+    images.append(np.stack([(xx * 255 // 470), (yy * 255 // 332), ((xx + yy) % 2) * 255], -1).astype(np.uint8))
+    crops = model.letterbox_device(images).cpu().numpy()
+    assert crops.shape == (len(images), 3, 112, 112)
+    for im, got in zip(images, crops):
+        np.testing.assert_array_equal(got, preprocess_face_no_landmarks(im), err_msg=str(im.shape))
+    rec = Recognition(device=torch.device('cuda'), lazy=True)
+    rec.model = model
+    out = rec(images[:5])
+    assert out.shape == (5, 512) and out.dtype == np.float32
+    want = model.embed_device(torch.from_numpy(np.stack(
+        [preprocess_face_no_landmarks(im) for im in images[:5]])).cuda(), 'nchw_bgr').cpu().numpy()
+    np.testing.assert_allclose(out, want, atol=1e-6)
+    np.testing.assert_allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-5)
+    with pytest.raises(ValueError, match='height and width'):
+        model.letterbox_device([np.zeros((1, 500, 3), np.uint8)])     # 0 px tall after resizing (PIL raises too)
+    assert rec([]) == []
+
+
 def test_recognition_ragged_image_list(native, retina, arc):
     """A list of differently sized images with their detected faces: resized, merged, aligned and
     embedded on the device (no host cv2 / PIL) — the features equal the batched path of each

@@ -346,3 +346,29 @@ def test_bench_reference_arm_contract():
     assert d['cpu_baseline']['value'] == d['value'] and 'sample' in d['cpu_baseline']
     assert d['e2e'] == {'value': d['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0}
+
+
+def test_resample_tables_of_the_library_match_the_oracle():
+    """tr_resample_table (host-only entry of the C ABI: the fixed-point filter tables the
+    letterbox kernels read) == oracle/letterbox.py::resample_table, which is pinned against PIL."""
+    from oracle.letterbox import resample_table
+    from terran_b200 import _native as nat
+    L = nat.lib()
+    rng = np.random.default_rng(2)
+    cases = [(int(a), int(b)) for a, b in zip(rng.integers(1, 3000, 120), rng.integers(1, 160, 120))]
+    cases += [(112, 112), (1, 1), (1, 112), (1920, 112), (1080, 63), (5, 112)]
+    for in_size, out_size in cases:
+        ksize = L.tr_resample_table(in_size, out_size, None, None)
+        bounds = np.zeros((out_size, 2), np.int32)
+        coeffs = np.full((out_size, ksize), -7, np.int32)
+        assert L.tr_resample_table(in_size, out_size, bounds.ctypes.data, coeffs.ctypes.data) == ksize
+        want_b, want_k = resample_table(in_size, out_size)
+        assert want_k.shape[1] == ksize
+        np.testing.assert_array_equal(bounds, want_b)
+        np.testing.assert_array_equal(coeffs, want_k)
+    assert L.tr_resample_table(0, 5, None, None) == -1
+    sizes = np.array([[1, 500]], np.int32)            # resized height 0: Pillow's own error
+    assert L.tr_face_letterbox_workspace_bytes(sizes.ctypes.data, 1, 112) == 0
+    assert b'must be > 0' in L.tr_last_error()
+    sizes = np.array([[300, 181], [112, 112]], np.int32)
+    assert L.tr_face_letterbox_workspace_bytes(sizes.ctypes.data, 2, 112) > 300 * 67 * 3

@@ -246,3 +246,23 @@ def test_baseline_c2_oracle_detection_1080p_matches_reference(golden, retina_sd)
         np.testing.assert_array_equal(np.stack([f['bbox'] for f in faces]), g[f'bbox{n}'])
         np.testing.assert_array_equal(np.stack([f['landmarks'] for f in faces]), g[f'landmarks{n}'])
         np.testing.assert_array_equal(np.array([f['score'] for f in faces]), g[f'score{n}'])
+
+
+def test_pil_resize_restatement_matches_pil():
+    """oracle/letterbox.py restates Pillow's 8-bit antialiased bicubic resampler: pinned bit-exact
+    against PIL itself (the routine the reference calls in preprocess_face_no_landmarks,
+    arcface/wrapper.py:75-99) over down- and up-scaling, extreme aspect ratios and tiny images."""
+    from PIL import Image
+    from oracle import letterbox as lb
+    rng = np.random.default_rng(5)
+    shapes = [(int(h), int(w)) for h, w in rng.integers(3, 400, (25, 2))]
+    shapes += [(112, 112), (1, 1), (2, 300), (300, 2), (720, 1280), (1001, 37)]
+    for h, w in shapes:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        s = 112 / max(w, h)
+        ow, oh = int(w * s), int(h * s)
+        if ow < 1 or oh < 1:
+            continue
+        want = np.asarray(Image.fromarray(img).resize((ow, oh)))
+        np.testing.assert_array_equal(lb.pil_resize_bicubic(img, ow, oh), want, err_msg=f'{h}x{w}')
+        np.testing.assert_array_equal(lb.letterbox(img), lb.preprocess_face_no_landmarks(img))
