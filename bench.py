@@ -479,7 +479,7 @@ def run_ours(args):
     # under-estimate of the steady state, never an over-estimate).
     from terran_b200.pipeline import FrameFeeder, PerceptionPipeline
     pipe = PerceptionPipeline(detection, estimation, device=dev)
-    for faces, poses in pipe.run(FrameFeeder((host for _ in range(3)), device=dev)):
+    for faces, poses in pipe.run(FrameFeeder((host for _ in range(8)), device=dev)):
         pass                                        # warm-up: pinned result slots, allocator
     # The window is short (K steps are tens of milliseconds) and timed on the host clock, max
     # over ranks: one scheduling hiccup on any rank of the box moves it by tens of per cent

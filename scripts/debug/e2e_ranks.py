@@ -84,9 +84,11 @@ def main():
         torch.cuda.synchronize()
 
     report = {'rank': rank, 'binding': binding}
-    for mode in ('spin', 'blocking', 'spin'):
+    modes = os.environ.get('MODES', 'spin,blocking,spin').split(',')
+    for mode in modes:
         defaults.blocking_events = mode == 'blocking'
-        for _ in pipe.run(FrameFeeder((host for _ in range(3)), device=dev)):
+        os.environ['TRB_FEEDER_PRIVATE_STREAM'] = '1' if mode == 'private' else '0'
+        for _ in pipe.run(FrameFeeder((host for _ in range(8)), device=dev)):
             pass
         rows = []
         for _ in range(windows):
@@ -106,7 +108,7 @@ def main():
     else:
         gathered = [report]
     if rank == 0:
-        for mode in ('spin', 'blocking'):
+        for mode in dict.fromkeys(modes):
             for rep, _ in enumerate(gathered[0][mode]):
                 print(f'== {mode} (pass {rep}): per rank, window ms (process CPU ms)')
                 worst = (0.0, None)
@@ -121,6 +123,7 @@ def main():
                 fps = [round(world * bench.BATCH * steps / (t / 1e3)) for t in per_window]
                 print(f'  max over ranks per window: {per_window} -> frames/s {fps}')
                 print(f'  slowest window: rank {worst[1][0]} step completion stamps {worst[1][1]}')
+                print('  first result of each window, rank 0 (ms):', [r[2][0] for r in gathered[0][mode][rep]])
     if world > 1:
         dist.destroy_process_group()
 

@@ -25,19 +25,22 @@ def cuda_index(device):
 blocking_events = None
 
 
+def blocking_waits():
+    """Whether result waits of this process should block (see ``blocking_events``)."""
+    import os
+    if blocking_events is not None:
+        return bool(blocking_events)
+    env = os.environ.get('TRB_BLOCKING_SYNC')
+    if env is not None:
+        return env not in ('0', '')
+    ranks = int(os.environ.get('LOCAL_WORLD_SIZE', '1'))
+    try:
+        cpus = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cpus = os.cpu_count() or 1
+    return ranks * 4 >= cpus
+
+
 def completion_event():
     """Event a host thread will ``synchronize()`` on for the results of a batch."""
-    import os
-    mode = blocking_events
-    if mode is None:
-        env = os.environ.get('TRB_BLOCKING_SYNC')
-        if env is not None:
-            mode = env not in ('0', '')
-        else:
-            ranks = int(os.environ.get('LOCAL_WORLD_SIZE', '1'))
-            try:
-                cpus = len(os.sched_getaffinity(0))
-            except (AttributeError, OSError):
-                cpus = os.cpu_count() or 1
-            mode = ranks * 4 >= cpus
-    return torch.cuda.Event(blocking=bool(mode))
+    return torch.cuda.Event(blocking=blocking_waits())

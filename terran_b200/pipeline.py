@@ -9,6 +9,7 @@ double buffering), face detection and pose estimation of one batch run
 concurrently on two CUDA streams, and the host-side result unpacking of batch i
 overlaps the GPU work of batch i+1.
 """
+import os
 import queue
 import threading
 
@@ -26,6 +27,23 @@ class FrameFeeder:
     tensors are uploaded without a staging copy).  ``depth`` batches are in
     flight (reference: ``Queue(1)`` prefetch)."""
 
+    #: ONE upload stream per device for every feeder of the process.  The caching allocator keeps a
+    #: pool of blocks per stream: a feeder with a private stream would find that pool empty and
+    #: pay two or three ``cudaMalloc`` of a whole batch (199 MB for 32 x 1080p) before its first
+    #: frame is up — a driver call that takes anything from 1 ms to 0.5 s on a shared host
+    #: (profiles/r02_e2e_ranks.txt).  With the shared stream a new feeder re-uses the blocks the
+    #: previous one released.
+    _copy_streams = {}
+    _copy_streams_lock = threading.Lock()
+
+    @classmethod
+    def copy_stream(cls, device_index):
+        with cls._copy_streams_lock:
+            stream = cls._copy_streams.get(device_index)
+            if stream is None:
+                stream = cls._copy_streams[device_index] = torch.cuda.Stream(device=device_index)
+            return stream
+
     def __init__(self, source, device=default_device, depth=2):
         self.source = iter(source)
         self.device_index = cuda_index(device)
@@ -37,7 +55,10 @@ class FrameFeeder:
 
     def _run(self):
         torch.cuda.set_device(self.device_index)
-        stream = torch.cuda.Stream(device=self.device_index)
+        if os.environ.get('TRB_FEEDER_PRIVATE_STREAM', '0') == '1':      # (A/B switch of the profile above)
+            stream = torch.cuda.Stream(device=self.device_index)
+        else:
+            stream = self.copy_stream(self.device_index)
         staging = {}
         slot = 0
         try:
