@@ -244,8 +244,12 @@ __device__ __forceinline__ void mma_m16n8k16(float (&d)[4], const uint32_t (&a)[
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int COUT, int STRIDE, int ACT>
-__global__ void __launch_bounds__(256, 2) stem_mma_kernel(const StemArgs a, int H_out, int W_out, float in_off,
+// OCC = CTAs per SM the register budget is cut for.  The kernel is latency-bound (one window
+// fetch in flight per CTA while the previous tile is computed), so the 8-filter RetinaFace stem,
+// which needs 80 registers without spilling, runs three CTAs per SM (TRB_STEM_OCC=2|3|4 selects
+// the instantiation for A/B runs; 4 spills 88 bytes).
+template <int COUT, int STRIDE, int ACT, int OCC = 2>
+__global__ void __launch_bounds__(256, OCC) stem_mma_kernel(const StemArgs a, int H_out, int W_out, float in_off,
                                                           int tiles_w, int tiles_h, int total_tiles) {
   constexpr int NT = COUT / 8, TH = 8, TW = 64, SEGS = TW / 16;
   constexpr int IN_H = (TH - 1) * STRIDE + 3, IN_W = (TW - 1) * STRIDE + 3;
@@ -672,9 +676,14 @@ void stem_launch(const StemArgs& a, cudaStream_t s) {
     int dev = 0;
     TR_CUDA(cudaGetDevice(&dev));
     TR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const unsigned grid = static_cast<unsigned>(std::min<long>(total, 4L * sms));
+    static const int occ8 = [] { const char* e = getenv("TRB_STEM_OCC"); return e ? atoi(e) : 3; }();
+    const unsigned grid = static_cast<unsigned>(std::min<long>(total, (a.cout == 8 ? 2L * occ8 : 4L) * sms));
     bool done = true;
-    if (a.cout == 8 && a.act == ACT_RELU)
+    if (a.cout == 8 && a.act == ACT_RELU && occ8 == 3)
+      stem_mma_kernel<8, 2, ACT_RELU, 3><<<grid, 256, 0, s>>>(a, H_out, W_out, in_off, tiles_w, tiles_h, int(total));
+    else if (a.cout == 8 && a.act == ACT_RELU && occ8 == 4)
+      stem_mma_kernel<8, 2, ACT_RELU, 4><<<grid, 256, 0, s>>>(a, H_out, W_out, in_off, tiles_w, tiles_h, int(total));
+    else if (a.cout == 8 && a.act == ACT_RELU)
       stem_mma_kernel<8, 2, ACT_RELU><<<grid, 256, 0, s>>>(a, H_out, W_out, in_off, tiles_w, tiles_h, int(total));
     else if (a.cout == 64 && a.act == ACT_RELU)
       stem_mma_kernel<64, 1, ACT_RELU><<<grid, 256, 0, s>>>(a, H_out, W_out, in_off, tiles_w, tiles_h, int(total));
