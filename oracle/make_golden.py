@@ -263,10 +263,33 @@ def golden_baseline():
     np.savez_compressed(os.path.join(GOLDEN, 'retinaface_detection_1080p.npz'), **fx)
 
 
+def golden_letterbox():
+    """Faces WITHOUT landmarks: the reference's own ``preprocess_face_no_landmarks``
+    (arcface/wrapper.py:75-99) on seeded images of many sizes; checks ``oracle/letterbox.py``."""
+    from terran.face.recognition.arcface.wrapper import preprocess_face_no_landmarks
+    from oracle import letterbox as lb
+    rng = np.random.default_rng(21)
+    shapes = [(112, 112), (57, 41), (300, 181), (181, 300), (9, 640), (640, 9), (3, 5),
+              (111, 113), (1, 1), (217, 212), (270, 480)]
+    fx, worst = {}, 0.0
+    for i, (h, w) in enumerate(shapes):
+        image = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if i % 3 == 0 or h * w > 100000:        # smooth content: long filter windows over gradients (and small fixtures)
+            yy, xx = np.mgrid[0:h, 0:w]
+            image = np.stack([xx * 255 // max(w - 1, 1), yy * 255 // max(h - 1, 1), (xx + yy) % 256],
+                             -1).astype(np.uint8)
+        want = preprocess_face_no_landmarks(image, 112)
+        worst = max(worst, report(f'letterbox {h}x{w}', lb.letterbox(image), want))
+        fx[f'image_{i}'], fx[f'crop_{i}'] = image, want
+    assert worst == 0.0, 'oracle/letterbox.py differs from the reference'
+    fx['n'] = np.int64(len(shapes))
+    np.savez_compressed(os.path.join(GOLDEN, 'letterbox.npz'), **fx)
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     import_reference()
-    which = sys.argv[1:] or ['retinaface', 'arcface', 'openpose', 'baseline']
+    which = sys.argv[1:] or ['retinaface', 'arcface', 'openpose', 'baseline', 'letterbox']
     for name in which:
         print(f'[{name}]')
         globals()['golden_' + name]()

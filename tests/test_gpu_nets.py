@@ -347,6 +347,17 @@ def test_gpu_face_letterbox_matches_pil(native, arc):
     assert rec([]) == []
 
 
+def test_gpu_face_letterbox_matches_reference_golden(native, arc, golden):
+    """tr_face_letterbox against the outputs of the unmodified reference's
+    preprocess_face_no_landmarks (tests/golden/letterbox.npz): bit-exact."""
+    model, _ = arc
+    g = golden('letterbox.npz')
+    n = int(g['n'])
+    crops = model.letterbox_device([g[f'image_{i}'] for i in range(n)]).cpu().numpy()
+    for i in range(n):
+        np.testing.assert_array_equal(crops[i], g[f'crop_{i}'], err_msg=str(g[f'image_{i}'].shape))
+
+
 def test_recognition_ragged_image_list(native, retina, arc):
     """A list of differently sized images with their detected faces: resized, merged, aligned and
     embedded on the device (no host cv2 / PIL) — the features equal the batched path of each

@@ -266,3 +266,13 @@ def test_pil_resize_restatement_matches_pil():
         want = np.asarray(Image.fromarray(img).resize((ow, oh)))
         np.testing.assert_array_equal(lb.pil_resize_bicubic(img, ow, oh), want, err_msg=f'{h}x{w}')
         np.testing.assert_array_equal(lb.letterbox(img), lb.preprocess_face_no_landmarks(img))
+
+
+def test_letterbox_oracle_matches_reference(golden):
+    """oracle/letterbox.py against the outputs of the UNMODIFIED reference's
+    preprocess_face_no_landmarks (tests/golden/letterbox.npz, oracle/make_golden.py letterbox)."""
+    from oracle import letterbox as lb
+    g = golden('letterbox.npz')
+    for i in range(int(g['n'])):
+        np.testing.assert_array_equal(lb.letterbox(g[f'image_{i}']), g[f'crop_{i}'])
+        np.testing.assert_array_equal(lb.preprocess_face_no_landmarks(g[f'image_{i}']), g[f'crop_{i}'])
