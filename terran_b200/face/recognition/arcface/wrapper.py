@@ -138,6 +138,8 @@ class ArcFace:
             if min(int(im.shape[1] * (S / max(im.shape[:2]))), int(im.shape[0] * (S / max(im.shape[:2])))) < 1:
                 raise ValueError('height and width must be > 0')        # (PIL's own error)
         n = len(images)
+        if n == 0:
+            return torch.empty((0, 3, S, S), dtype=torch.uint8, device=torch.device('cuda', self.device_index))
         sizes = np.array([im.shape[:2] for im in images], np.int32).reshape(n, 2)
         nbytes = np.array([im.size for im in images], np.int64)
         offsets = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.int64)
