@@ -184,8 +184,10 @@ def unpack_detections(counts, rows, scale=None):
         coords = np.ascontiguousarray(coords)
     boxes = coords[..., :4]
     lmks = coords[..., 4:].reshape(coords.shape[0], coords.shape[1], 5, 2)
+    # (iterating an array yields its rows as views at C speed: ~2x faster than indexing [n, i])
     return [
-        [{'bbox': boxes[n, i], 'landmarks': lmks[n, i], 'score': scores[n, i]} for i in range(k)]
+        [{'bbox': b, 'landmarks': l, 'score': s}
+         for b, l, s in zip(boxes[n, :k], lmks[n, :k], scores[n, :k])]
         for n, k in enumerate(counts)
     ]
 

@@ -60,8 +60,9 @@ def unpack_poses(count, kps, score, status):
     top = int(count.max()) if len(count) else 0
     kps = kps[:, :max(top, 1)].cpu().numpy().copy()
     score = score[:, :max(top, 1)].cpu().numpy().copy()
+    # (kps / score are fresh per-call copies: the per-person arrays are views into them)
     return [
-        [{'keypoints': kps[n, i].copy(), 'score': score[n, i]} for i in range(k)]
+        [{'keypoints': kp, 'score': sc} for kp, sc in zip(kps[n, :k], score[n, :k])]
         for n, k in enumerate(count)
     ]
 
